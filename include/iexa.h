@@ -1,0 +1,231 @@
+/*
+ * iexa.h — C ABI of the B200-native NLP evaluation engine ("iexa").
+ *
+ * This is the drop-in boundary for the hot path of infiniteopt/InfiniteExaModels.jl:
+ * the NLPModels callbacks (obj, grad!, cons!, jac_structure!/jac_coord!,
+ * hess_structure!/hess_coord!, jprod!/jtprod!/hprod!) that MadNLP / Ipopt call on the
+ * model that `ExaTranscriptionBackend` builds.  The reference has NO C ABI of its own
+ * (it is pure Julia and reaches the evaluator through ExaModels.jl); every entry point
+ * below names the reference call site (file:line under /root/reference) it replaces.
+ *
+ * Conventions
+ *   - every function returns an int32 status (IEXA_OK == 0); iexa_last_error() gives a
+ *     thread-local message.  No C++ exception and no exit() crosses this boundary.
+ *   - indices handed to the caller (rows/cols, offsets) are 1-based like the Julia
+ *     solvers expect; index expressions in tapes are 1-based as in transform.jl.
+ *   - `memspace` says where the caller's buffers live (IEXA_MEM_HOST / IEXA_MEM_DEVICE).
+ *     Host buffers are staged through pinned memory and copied inside the call.
+ *   - `stream` is a cudaStream_t cast to void* (NULL = legacy default stream).  Device
+ *     calls are asynchronous on that stream except where a scalar is returned (iexa_obj).
+ *   - the engine never keeps caller pointers after a call returns.
+ *   - NaN/Inf are propagated untouched (the reference never throws during evaluation;
+ *     MadNLP maps them to INVALID_NUMBER_*, ext/InfiniteExaModelsMadNLP.jl:78-87).
+ *   - there is NO CPU fallback: evaluation entry points fail with IEXA_ERR_CUDA when no
+ *     CUDA device / kernel image is available.
+ */
+#ifndef IEXA_H
+#define IEXA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IEXA_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ---------------------------------------------------------------- */
+enum {
+  IEXA_OK = 0,
+  IEXA_ERR_INVALID = 1,     /* bad argument / malformed tape                          */
+  IEXA_ERR_STATE = 2,       /* call not allowed in this plan state (e.g. before finalize) */
+  IEXA_ERR_CUDA = 3,        /* CUDA runtime/driver error, or no device                 */
+  IEXA_ERR_NVRTC = 4,       /* run-time specialisation failed                          */
+  IEXA_ERR_UNSUPPORTED = 5, /* operator outside src/operators.jl:2-46                  */
+  IEXA_ERR_NOMEM = 6
+};
+
+enum { IEXA_MEM_HOST = 0, IEXA_MEM_DEVICE = 1 };
+
+/* ---- tape operators ---------------------------------------------------------------
+ * One entry per operator of the reference's table src/operators.jl:2-46 plus the four
+ * leaf kinds that src/transform.jl:290-330 (_map_variable) can produce.               */
+enum {
+  /* leaves */
+  IEXA_OP_CONST = 0, /* literal c                      (transform.jl:340, Null :393)  */
+  IEXA_OP_FIELD = 1, /* fp iterator field  data_src[alias]       (transform.jl:320-322) */
+  IEXA_OP_VAR = 2,   /* x[index expr]      (transform.jl:290-319)                     */
+  IEXA_OP_PAR = 3,   /* theta[index expr]  (transform.jl:323-330)                     */
+  /* binary  (operators.jl:3-7) */
+  IEXA_OP_ADD = 10, IEXA_OP_SUB = 11, IEXA_OP_MUL = 12, IEXA_OP_DIV = 13, IEXA_OP_POW = 14,
+  /* unary   (operators.jl:8-43; NEG/POS are the unary forms of :- and :+) */
+  IEXA_OP_NEG = 20, IEXA_OP_POS = 21, IEXA_OP_INV = 22, IEXA_OP_SQRT = 23, IEXA_OP_CBRT = 24,
+  IEXA_OP_ABS = 25, IEXA_OP_ABS2 = 26, IEXA_OP_EXP = 27, IEXA_OP_EXP2 = 28, IEXA_OP_LOG = 29,
+  IEXA_OP_LOG2 = 30, IEXA_OP_LOG10 = 31, IEXA_OP_LOG1P = 32, IEXA_OP_SIN = 33, IEXA_OP_COS = 34,
+  IEXA_OP_TAN = 35, IEXA_OP_ASIN = 36, IEXA_OP_ACOS = 37, IEXA_OP_CSC = 38, IEXA_OP_SEC = 39,
+  IEXA_OP_COT = 40, IEXA_OP_ATAN = 41, IEXA_OP_ACOT = 42, IEXA_OP_SIND = 43, IEXA_OP_COSD = 44,
+  IEXA_OP_TAND = 45, IEXA_OP_CSCD = 46, IEXA_OP_SECD = 47, IEXA_OP_COTD = 48, IEXA_OP_ATAND = 49,
+  IEXA_OP_ACOTD = 50, IEXA_OP_SINH = 51, IEXA_OP_COSH = 52, IEXA_OP_TANH = 53,
+  IEXA_OP_CSCH = 54, /* the TRUE csch; the reference maps :csch to csc (operators.jl:41) —
+                        a lowering that wants bug-compatibility emits IEXA_OP_CSC instead */
+  IEXA_OP_SECH = 55, IEXA_OP_COTH = 56, IEXA_OP_ATANH = 57, IEXA_OP_ACOTH = 58,
+  IEXA_OP__END = 59
+};
+
+/* One node of a postfix tape: children precede parents, the root is the last node.
+ * A tape is a TREE (a node id that is referenced twice is evaluated as two subtrees,
+ * like the expression objects ExaModels builds).                                      */
+typedef struct iexa_node {
+  int32_t op; /* IEXA_OP_*                                                             */
+  int32_t a;  /* unary/binary: lhs child node id | VAR/PAR: index-expr id | FIELD: fp column */
+  int32_t b;  /* binary: rhs child node id, otherwise 0                                */
+  int32_t pad;
+  double c;   /* CONST: the literal                                                    */
+} iexa_node;
+
+#define IEXA_MAX_INDEX_TERMS 4
+/* Affine integer index expression over the integer columns of the generator's iterator:
+ *   idx(k) = base + sum_j coef[j] * int_col[col[j]](k)            (1-based result)
+ * This is what transform.jl's Variable[data_src[group_alias]...] (:309-310,:316-318),
+ * `idx ± const` in make_reduced_expr (:485-505) and the (i1,i2) collocation pairs
+ * (:593-596) reduce to under column-major addressing.                                 */
+typedef struct iexa_index {
+  int64_t base;
+  int32_t nterms;
+  int32_t col[IEXA_MAX_INDEX_TERMS];
+  int32_t pad;
+  int64_t coef[IEXA_MAX_INDEX_TERMS];
+} iexa_index;
+
+typedef struct iexa_plan iexa_plan;
+
+typedef struct iexa_meta {
+  int64_t nvar, ncon, npar, nobj_gen, ncon_gen;
+  int64_t nnzj, nnzh, nnzg; /* global COO sizes (nnzg: sparse objective-gradient slots) */
+  int64_t loc_ncon, loc_nnzj, loc_nnzh; /* what THIS rank owns (== global when world==1) */
+  int32_t minimize, rank, world, device;
+  int32_t n_kernels_specialised; /* NVRTC-specialised kernel images in use             */
+  int32_t pad;
+} iexa_meta;
+
+/* finalize flags */
+enum {
+  IEXA_F_DEFAULT = 0,
+  IEXA_F_NO_SPECIALISE = 1, /* use only the AOT tape-interpreter kernels (no NVRTC)    */
+  IEXA_F_NO_DEVICE = 2      /* compile the plan on the host only (structure queries,
+                               byte accounting); every evaluation call then FAILS       */
+};
+
+const char *iexa_last_error(void);
+int32_t iexa_version(void);
+
+/* ---- plan construction (replaces ExaModels.ExaCore(...) at transform.jl:815 and the
+ *      builder calls listed below) ------------------------------------------------- */
+int32_t iexa_plan_create(iexa_plan **out, int32_t minimize);
+int32_t iexa_plan_destroy(iexa_plan *p);
+
+/* ExaModels.add_var  — transform.jl:113 (finite), :154 (infinite + derivative vars).
+ * x0/lvar/uvar may be NULL (0, -inf, +inf).  offset_out: 0-based offset of the block. */
+int32_t iexa_add_var(iexa_plan *p, int64_t n, const double *x0, const double *lvar,
+                     const double *uvar, int64_t *offset_out);
+/* ExaModels.add_par  — transform.jl:127 (finite parameters), :179 (parameter functions) */
+int32_t iexa_add_par(iexa_plan *p, int64_t n, const double *vals, int64_t *offset_out);
+/* element-wise patch of x0/lvar/uvar before finalize — transform.jl:216-231
+ * which: 0 = x0, 1 = lvar, 2 = uvar; i is a 1-based variable index                    */
+int32_t iexa_patch_var(iexa_plan *p, int32_t which, int64_t i, double value);
+
+/* Iterators.  A base iterator is the SoA form of transform.jl:31's Vector{NamedTuple}:
+ * n_int integer columns (group_idx / i1,i2 / support indices) and n_fp fp64 columns
+ * (support values, d_arg coefficients, quadrature weight c), each of length K.
+ * Integer columns equal to 1..K are detected and never stored or loaded.              */
+int32_t iexa_itr_base(iexa_plan *p, int64_t K, int32_t n_int, const int64_t *const *int_cols,
+                      int32_t n_fp, const double *const *fp_cols, int32_t *itr_out);
+/* Product iterator, first factor fastest (transform.jl:445, :541, :591, :670): columns are
+ * the concatenation of the factors' columns; nothing is materialised.                 */
+int32_t iexa_itr_product(iexa_plan *p, int32_t n, const int32_t *itrs, int32_t *itr_out);
+
+/* ExaModels.add_con — transform.jl:458 (constraints), :559 (derivative approximations),
+ * :597 (collocation restrictions).  row_offset_out: 0-based first row.                */
+int32_t iexa_add_con(iexa_plan *p, const iexa_node *nodes, int32_t n_nodes,
+                     const iexa_index *idx, int32_t n_idx, int32_t itr, double lcon,
+                     double ucon, int64_t *row_offset_out);
+/* ExaModels.add_obj — transform.jl:614, :700, :741                                    */
+int32_t iexa_add_obj(iexa_plan *p, const iexa_node *nodes, int32_t n_nodes,
+                     const iexa_index *idx, int32_t n_idx, int32_t itr);
+
+/* ExaModels.ExaModel(core) — infiniteopt_backend.jl:156.  Compiles every generator
+ * (symbolic sparsity + slot layout + AD programs), uploads columns/theta, selects or
+ * specialises kernels.  rank/world shard the support ranges (world==1: whole model).  */
+int32_t iexa_finalize(iexa_plan *p, int32_t device, int32_t rank, int32_t world, uint32_t flags);
+
+int32_t iexa_get_meta(const iexa_plan *p, iexa_meta *out);
+/* host copies of the NLPModelMeta vectors (get_x0/get_y0: infiniteopt_backend.jl:600-601)
+ * which: 0 x0, 1 lvar, 2 uvar (length nvar); 3 lcon, 4 ucon, 5 y0 (length ncon)        */
+int32_t iexa_get_vector(const iexa_plan *p, int32_t which, double *out);
+int32_t iexa_set_vector(iexa_plan *p, int32_t which, const double *in); /* x0 / y0 warm start */
+
+/* ExaModels.set_parameter! — infiniteopt_backend.jl:522,:546 ; model.θ — :479          */
+int32_t iexa_set_par(iexa_plan *p, int64_t offset0, int64_t n, const double *vals_host);
+int32_t iexa_get_par(const iexa_plan *p, int64_t offset0, int64_t n, double *vals_host);
+
+/* ---- NLPModels callbacks (ExaModels 0.11.2 methods reached from
+ *      ext/InfiniteExaModelsMadNLP.jl:49-50,64 and ext/InfiniteExaModelsIpopt.jl:48-49,59-60)
+ * idx_bytes: 4 or 8 (Int32 / Int64 index buffers).  Buffers sized by the LOCAL counts
+ * of iexa_meta when world > 1.                                                         */
+int32_t iexa_jac_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_bytes,
+                           int32_t memspace, void *stream);
+int32_t iexa_hess_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_bytes,
+                            int32_t memspace, void *stream);
+int32_t iexa_obj(iexa_plan *p, const double *x, double *f_host, int32_t memspace, void *stream);
+int32_t iexa_grad(iexa_plan *p, const double *x, double *g, int32_t memspace, void *stream);
+int32_t iexa_cons(iexa_plan *p, const double *x, double *c, int32_t memspace, void *stream);
+int32_t iexa_jac_coord(iexa_plan *p, const double *x, double *vals, int32_t memspace, void *stream);
+/* y may be NULL (objective-only Hessian)                                               */
+int32_t iexa_hess_coord(iexa_plan *p, const double *x, const double *y, double obj_weight,
+                        double *vals, int32_t memspace, void *stream);
+int32_t iexa_jprod(iexa_plan *p, const double *x, const double *v, double *Jv, int32_t memspace,
+                   void *stream);
+int32_t iexa_jtprod(iexa_plan *p, const double *x, const double *v, double *Jtv,
+                    int32_t memspace, void *stream);
+int32_t iexa_hprod(iexa_plan *p, const double *x, const double *y, const double *v,
+                   double obj_weight, double *Hv, int32_t memspace, void *stream);
+/* device-side objective partial (no host sync): writes 1 double to f_dev               */
+int32_t iexa_obj_device(iexa_plan *p, const double *x_dev, double *f_dev, void *stream);
+
+/* ---- sharding queries (world > 1).  A segment maps a contiguous local range of rows /
+ *      Jacobian slots / Hessian slots to its position in the global (unsharded) arrays. */
+typedef struct iexa_segment {
+  int64_t global_start, local_start, length; /* 0-based */
+} iexa_segment;
+/* which: 0 rows, 1 jac slots, 2 hess slots.  Returns the count; fills up to cap.       */
+int64_t iexa_segments(const iexa_plan *p, int32_t which, iexa_segment *out, int64_t cap);
+/* variable indices (1-based) whose gradient entries receive contributions from more than
+ * one rank (finite / shared variables and shard-boundary halos): the slice that must be
+ * all-reduced after iexa_grad.  Returns the count; fills up to cap.                    */
+int64_t iexa_shared_vars(const iexa_plan *p, int64_t *out, int64_t cap);
+
+/* ---- byte accounting used by bench.py's roofline: ALGORITHMIC bytes of
+ *      one call of each callback, computed from the finalised plan.
+ * which: 0 obj, 1 grad, 2 cons, 3 jac_coord, 4 hess_coord                              */
+int64_t iexa_algorithmic_bytes(const iexa_plan *p, int32_t which);
+/* number of kernel launches one call of callback `which` performs                      */
+int32_t iexa_launches_per_call(const iexa_plan *p, int32_t which);
+
+/* ---- COO -> CSR value permutation feeding cuDSS (today MadNLPGPU's transfer! kernel,
+ *      caller side of ext/InfiniteExaModelsMadNLP.jl:49-50).  Setup sorts the 1-based
+ *      COO pattern once; apply sums duplicates into CSR order with no atomics.         */
+typedef struct iexa_csr iexa_csr;
+int32_t iexa_csr_create(iexa_csr **out, int64_t nrows, int64_t ncols, int64_t nnz,
+                        const void *rows, const void *cols, int32_t idx_bytes,
+                        int32_t memspace, int32_t device);
+int32_t iexa_csr_destroy(iexa_csr *h);
+int64_t iexa_csr_nnz(const iexa_csr *h);
+/* rowptr: nrows+1 entries, colind: csr_nnz entries, 0-based int32 (cuDSS convention)    */
+int32_t iexa_csr_pattern(const iexa_csr *h, int32_t *rowptr, int32_t *colind, int32_t memspace);
+int32_t iexa_csr_apply(iexa_csr *h, const double *coo_vals, double *csr_vals, int32_t memspace,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IEXA_H */

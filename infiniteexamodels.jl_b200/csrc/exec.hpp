@@ -1,0 +1,106 @@
+// exec.hpp — primitive-op evaluation shared by the sm_100a tape interpreter (interp.cu)
+// and the test-only host executor (tests/hostcheck.cpp).  Device-side descriptors of a
+// compiled generator.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#include "dag.hpp"
+
+#ifdef __CUDACC__
+#define IEXA_HD __host__ __device__ __forceinline__
+#else
+#define IEXA_HD inline
+#endif
+
+namespace iexa {
+
+IEXA_HD double eval_arith(int32_t op, double a, double b) {
+  switch (op) {
+    case D_ADD: return a + b;
+    case D_SUB: return a - b;
+    case D_MUL: return a * b;
+    case D_DIV: return a / b;
+    case D_NEG: return -a;
+    case D_POW: return pow(a, b);
+    case D_SQRT: return sqrt(a);
+    case D_CBRT: return cbrt(a);
+    case D_ABS: return fabs(a);
+    case D_SIGNP: return a >= 0.0 ? 1.0 : -1.0;
+    case D_EXP: return exp(a);
+    case D_EXP2: return exp2(a);
+    case D_LOG: return log(a);
+    case D_LOG2: return log2(a);
+    case D_LOG10: return log10(a);
+    case D_LOG1P: return log1p(a);
+    case D_SIN: return sin(a);
+    case D_COS: return cos(a);
+    case D_TAN: return tan(a);
+    case D_ASIN: return asin(a);
+    case D_ACOS: return acos(a);
+    case D_ATAN: return atan(a);
+    case D_SINH: return sinh(a);
+    case D_COSH: return cosh(a);
+    case D_TANH: return tanh(a);
+    case D_ATANH: return atanh(a);
+    default: return NAN;
+  }
+}
+
+// ---- device descriptors ---------------------------------------------------------------
+struct ColD {
+  const void *ptr; // int32* / double* table; nullptr = iota (value = j + 1)
+  long long div, mod; // j = (k / div) % mod
+};
+struct IdxD {
+  long long base;
+  int32_t nterms;
+  int32_t slot[4]; // int column slots
+  int32_t pad;
+  long long coef[4];
+};
+struct ProgD {
+  const Instr *code;
+  const double *cpool;
+  int32_t ncode, nreg, nout, uses_w;
+};
+enum { PROG_VAL = 0, PROG_D1 = 1, PROG_D2 = 2 };
+struct GenD {
+  long long K, k0, k1;
+  long long row_local;  // local row of support k0 (constraints): W = y[row_local + k - k0]
+  long long row_global; // o0
+  const ColD *icol;
+  const ColD *fcol;
+  const IdxD *idx;
+  const int32_t *jac_slot;  // [o1step] index slot per first-order slot
+  const int32_t *hess_slot; // [2*o2step] index-slot pairs
+  int32_t n_icol, n_fcol, n_idx, is_obj;
+  ProgD prog[3];
+  long long out_local[3];  // local output offset of support k0 for val / d1 / d2
+  long long out_global[3]; // global offsets o0 / o1 (og for objectives) / o2
+  int32_t ostep[3];
+  int32_t pad;
+};
+
+IEXA_HD long long col_int(const ColD &c, long long k) {
+  long long j = (k / c.div) % c.mod;
+  return c.ptr ? (long long)((const int32_t *)c.ptr)[j] : j + 1;
+}
+IEXA_HD double col_fp(const ColD &c, long long k) {
+  long long j = (k / c.div) % c.mod;
+  return ((const double *)c.ptr)[j];
+}
+IEXA_HD long long idx_eval(const GenD &g, int32_t islot, long long k) {
+  const IdxD &e = g.idx[islot];
+  long long v = e.base;
+  for (int t = 0; t < e.nterms; ++t) v += e.coef[t] * col_int(g.icol[e.slot[t]], k);
+  return v;
+}
+
+// work item of the one-launch-per-callback kernels: block -> (generator, first support)
+struct WorkItem {
+  int32_t gen;
+  int32_t blk; // block index inside the generator's local support range
+};
+
+} // namespace iexa

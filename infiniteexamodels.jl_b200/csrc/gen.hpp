@@ -1,0 +1,486 @@
+// gen.hpp — compile ONE generator (expression tree × iterator) into sparsity metadata and
+// register programs.
+//
+// What is restated here (ExaModels 0.11.2, not vendored in /root/reference; see SURVEY.md
+// Appendix A — the slot-ORDER policy below is a documented hypothesis until dumps from a
+// real ExaModels exist, "parity unpinned"):
+//   * first-order occurrences are the Var leaves in left-to-right order; leaves whose index
+//     EXPRESSIONS are identical share a slot (o1step = #distinct), first occurrence wins;
+//   * second-order occurrences come from the hrpass0 / hrpass / hdrpass recursion:
+//     top-level +,-,const* chains emit nothing; below the first nonlinear node every leaf
+//     emits a diagonal slot and every binary node a cross walk over its two subtrees;
+//   * slots are laid out per support: slot = o + ostep*(k-1) + c.
+// The tape comes from the lowering of src/transform.jl:337-389 (_exafy) and :290-334
+// (_map_variable).
+#pragma once
+#include <algorithm>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+
+#include "../../include/iexa.h"
+#include "dag.hpp"
+
+namespace iexa {
+
+struct IndexExpr {
+  int64_t base = 0;
+  std::vector<std::pair<int32_t, int64_t>> terms; // (int column, coef), sorted, coef != 0
+  bool operator==(const IndexExpr &o) const { return base == o.base && terms == o.terms; }
+};
+
+struct GenCompiled {
+  // inputs
+  std::vector<iexa_node> tape;
+  std::vector<IndexExpr> uidx;   // distinct canonical index expressions ("index slots")
+  std::vector<int32_t> idx_map;  // caller's index id -> index slot
+  std::vector<int32_t> fp_cols;  // fp column slot -> iterator fp column
+  std::vector<int32_t> int_cols; // int column slot -> iterator int column (terms are rewritten to slots)
+  // sparsity (symbolic)
+  std::vector<int32_t> jac_slot;                      // per first-order slot: index slot of the variable
+  std::vector<std::pair<int32_t, int32_t>> hess_slot; // per second-order slot: (index slot, index slot)
+  int32_t o1step = 0, o2step = 0;
+  int32_t n_occ1 = 0, n_occ2 = 0; // occurrences before compression (reporting)
+  bool is_null = false;           // constant-only generator (ExaModels.Null, transform.jl:393)
+  // programs
+  Program val, d1, d2;
+  std::vector<uint8_t> x_slots_val, x_slots_d1, x_slots_d2; // which index slots each program LOADX-es
+};
+
+class GenCompiler {
+ public:
+  GenCompiler(const iexa_node *nodes, int32_t n, const iexa_index *idx, int32_t n_idx,
+              int32_t n_int_cols_itr, int32_t n_fp_cols_itr)
+      : n_(n), n_int_itr_(n_int_cols_itr), n_fp_itr_(n_fp_cols_itr) {
+    if (n <= 0) throw std::invalid_argument("empty tape");
+    g.tape.assign(nodes, nodes + n);
+    canon_indices(idx, n_idx);
+    analyse();
+  }
+
+  GenCompiled g;
+
+  void compile() {
+    build_values();
+    first_order();
+    second_order();
+    g.val = schedule({val_[n_ - 1]}, g.x_slots_val);
+    g.d1 = schedule(slot1_, g.x_slots_d1);
+    g.d2 = schedule(slot2_, g.x_slots_d2);
+  }
+
+ private:
+  enum Kind { K_CONSTCLASS = 0, K_VAR = 1, K_UN = 2, K_BIN = 3 };
+  enum Pass { P_NONE = 0, P_KEEP, P_FLIP, P_SCALE, P_ADD, P_SUB };
+  struct Info {
+    int kind = K_CONSTCLASS;
+    int c1 = -1, c2 = -1; // active children (tape ids)
+    int pass = P_NONE;    // hrpass0 pass-through class
+    int y1 = -1, y2 = -1, h11 = -1, h12 = -1, h22 = -1; // DAG ids of local partials
+  };
+  int32_t n_, n_int_itr_, n_fp_itr_;
+  std::vector<Info> info_;
+  std::vector<int> val_;
+  Dag dag_;
+  std::vector<int> slot1_, slot2_;
+  std::map<int32_t, int32_t> slot1_of_;
+  std::map<std::pair<int32_t, int32_t>, int32_t> slot2_of_;
+
+  static bool is_leaf(int op) { return op >= IEXA_OP_CONST && op <= IEXA_OP_PAR; }
+  static bool is_bin(int op) { return op >= IEXA_OP_ADD && op <= IEXA_OP_POW; }
+  static bool is_un(int op) { return op >= IEXA_OP_NEG && op < IEXA_OP__END; }
+
+  void canon_indices(const iexa_index *idx, int32_t n_idx) {
+    std::map<int32_t, int32_t> colslot;
+    // first pass: which int columns are referenced (stable order of first reference)
+    for (int32_t i = 0; i < n_idx; ++i) {
+      if (idx[i].nterms < 0 || idx[i].nterms > IEXA_MAX_INDEX_TERMS)
+        throw std::invalid_argument("index expression: bad nterms");
+      for (int t = 0; t < idx[i].nterms; ++t) {
+        int32_t c = idx[i].col[t];
+        if (c < 0 || c >= n_int_itr_) throw std::invalid_argument("index expression: int column out of range");
+        if (idx[i].coef[t] != 0 && !colslot.count(c)) {
+          int32_t s = (int32_t)g.int_cols.size();
+          colslot[c] = s;
+          g.int_cols.push_back(c);
+        }
+      }
+    }
+    g.idx_map.resize(n_idx);
+    for (int32_t i = 0; i < n_idx; ++i) {
+      std::map<int32_t, int64_t> acc;
+      for (int t = 0; t < idx[i].nterms; ++t)
+        if (idx[i].coef[t] != 0) acc[colslot[idx[i].col[t]]] += idx[i].coef[t];
+      IndexExpr e;
+      e.base = idx[i].base;
+      for (auto &kv : acc)
+        if (kv.second != 0) e.terms.push_back(kv);
+      int32_t found = -1;
+      for (size_t u = 0; u < g.uidx.size(); ++u)
+        if (g.uidx[u] == e) { found = (int32_t)u; break; }
+      if (found < 0) { found = (int32_t)g.uidx.size(); g.uidx.push_back(e); }
+      g.idx_map[i] = found;
+    }
+  }
+
+  void analyse() {
+    info_.assign(n_, Info());
+    std::map<int32_t, int32_t> fpslot;
+    for (int i = 0; i < n_; ++i) {
+      const iexa_node &nd = g.tape[i];
+      Info &in = info_[i];
+      if (is_leaf(nd.op)) {
+        if (nd.op == IEXA_OP_VAR || nd.op == IEXA_OP_PAR) {
+          if (nd.a < 0 || nd.a >= (int)g.idx_map.size())
+            throw std::invalid_argument("tape: index-expression id out of range");
+        }
+        if (nd.op == IEXA_OP_FIELD) {
+          if (nd.a < 0 || nd.a >= n_fp_itr_) throw std::invalid_argument("tape: fp column out of range");
+          if (!fpslot.count(nd.a)) { fpslot[nd.a] = (int32_t)g.fp_cols.size(); g.fp_cols.push_back(nd.a); }
+        }
+        in.kind = nd.op == IEXA_OP_VAR ? K_VAR : K_CONSTCLASS;
+      } else if (is_bin(nd.op)) {
+        if (nd.a < 0 || nd.a >= i || nd.b < 0 || nd.b >= i) throw std::invalid_argument("tape: child id not before parent");
+        bool a1 = info_[nd.a].kind != K_CONSTCLASS, a2 = info_[nd.b].kind != K_CONSTCLASS;
+        if (a1 && a2) {
+          in.kind = K_BIN; in.c1 = nd.a; in.c2 = nd.b;
+          in.pass = nd.op == IEXA_OP_ADD ? P_ADD : nd.op == IEXA_OP_SUB ? P_SUB : P_NONE;
+        } else if (a1 || a2) {
+          in.kind = K_UN; in.c1 = a1 ? nd.a : nd.b;
+          if (nd.op == IEXA_OP_ADD) in.pass = P_KEEP;
+          else if (nd.op == IEXA_OP_SUB) in.pass = a1 ? P_KEEP : P_FLIP;
+          else if (nd.op == IEXA_OP_MUL) in.pass = P_SCALE;
+        }
+      } else if (is_un(nd.op)) {
+        if (nd.a < 0 || nd.a >= i) throw std::invalid_argument("tape: child id not before parent");
+        if (info_[nd.a].kind != K_CONSTCLASS) {
+          in.kind = K_UN; in.c1 = nd.a;
+          in.pass = nd.op == IEXA_OP_NEG ? P_FLIP : nd.op == IEXA_OP_POS ? P_KEEP : P_NONE;
+        }
+      } else {
+        throw std::invalid_argument("tape: unsupported operator " + std::to_string(nd.op));
+      }
+    }
+    g.is_null = info_[n_ - 1].kind == K_CONSTCLASS;
+    fpslot_ = fpslot;
+  }
+  std::map<int32_t, int32_t> fpslot_;
+
+  // value + local partials of a unary function u -> f(u); returns value, sets y,h when active
+  int lower_unary(int op, int u, bool active, int &y, int &h) {
+    Dag &d = dag_;
+    const double D2R = 0.017453292519943295769, R2D = 57.295779513082320877;
+    int v = -1;
+    auto one = [&] { return d.cnst(1.0); };
+    switch (op) {
+      case IEXA_OP_NEG: v = d.neg(u); if (active) { y = d.cnst(-1.0); h = d.cnst(0.0); } break;
+      case IEXA_OP_POS: v = u; if (active) { y = one(); h = d.cnst(0.0); } break;
+      case IEXA_OP_INV: v = d.div(one(), u); if (active) { y = d.neg(d.sq(v)); h = d.mul(d.cnst(2.0), d.mul(v, d.sq(v))); } break;
+      case IEXA_OP_SQRT: v = d.un(D_SQRT, u); if (active) { y = d.div(d.cnst(0.5), v); h = d.div(d.mul(d.cnst(-0.5), y), u); } break;
+      case IEXA_OP_CBRT: v = d.un(D_CBRT, u); if (active) { y = d.div(v, d.mul(d.cnst(3.0), u)); h = d.div(d.mul(d.cnst(-2.0 / 3.0), y), u); } break;
+      case IEXA_OP_ABS: v = d.un(D_ABS, u); if (active) { y = d.un(D_SIGNP, u); h = d.cnst(0.0); } break;
+      case IEXA_OP_ABS2: v = d.sq(u); if (active) { y = d.mul(d.cnst(2.0), u); h = d.cnst(2.0); } break;
+      case IEXA_OP_EXP: v = d.un(D_EXP, u); if (active) { y = v; h = v; } break;
+      case IEXA_OP_EXP2: v = d.un(D_EXP2, u); if (active) { y = d.mul(v, d.cnst(M_LN2)); h = d.mul(y, d.cnst(M_LN2)); } break;
+      case IEXA_OP_LOG: v = d.un(D_LOG, u); if (active) { y = d.div(one(), u); h = d.neg(d.sq(y)); } break;
+      case IEXA_OP_LOG2: v = d.un(D_LOG2, u); if (active) { y = d.div(d.cnst(1.0 / M_LN2), u); h = d.neg(d.div(y, u)); } break;
+      case IEXA_OP_LOG10: v = d.un(D_LOG10, u); if (active) { y = d.div(d.cnst(1.0 / M_LN10), u); h = d.neg(d.div(y, u)); } break;
+      case IEXA_OP_LOG1P: v = d.un(D_LOG1P, u); if (active) { y = d.div(one(), d.add(one(), u)); h = d.neg(d.sq(y)); } break;
+      case IEXA_OP_SIN: v = d.un(D_SIN, u); if (active) { y = d.un(D_COS, u); h = d.neg(v); } break;
+      case IEXA_OP_COS: v = d.un(D_COS, u); if (active) { y = d.neg(d.un(D_SIN, u)); h = d.neg(v); } break;
+      case IEXA_OP_TAN: v = d.un(D_TAN, u); if (active) { y = d.add(one(), d.sq(v)); h = d.mul(d.mul(d.cnst(2.0), v), y); } break;
+      case IEXA_OP_ASIN: v = d.un(D_ASIN, u); if (active) { y = d.div(one(), d.un(D_SQRT, d.sub(one(), d.sq(u)))); h = d.mul(u, d.mul(y, d.sq(y))); } break;
+      case IEXA_OP_ACOS: v = d.un(D_ACOS, u); if (active) { y = d.neg(d.div(one(), d.un(D_SQRT, d.sub(one(), d.sq(u))))); h = d.mul(u, d.mul(y, d.sq(y))); } break;
+      case IEXA_OP_ATAN: v = d.un(D_ATAN, u); if (active) { y = d.div(one(), d.add(one(), d.sq(u))); h = d.mul(d.mul(d.cnst(-2.0), u), d.sq(y)); } break;
+      case IEXA_OP_ACOT: v = d.un(D_ATAN, d.div(one(), u)); if (active) { y = d.neg(d.div(one(), d.add(one(), d.sq(u)))); h = d.mul(d.mul(d.cnst(2.0), u), d.sq(y)); } break;
+      case IEXA_OP_CSC: { v = d.div(one(), d.un(D_SIN, u)); if (active) { y = d.neg(d.mul(d.sq(v), d.un(D_COS, u))); h = d.mul(v, d.sub(d.mul(d.cnst(2.0), d.sq(v)), one())); } break; }
+      case IEXA_OP_SEC: { v = d.div(one(), d.un(D_COS, u)); if (active) { y = d.mul(d.sq(v), d.un(D_SIN, u)); h = d.mul(v, d.sub(d.mul(d.cnst(2.0), d.sq(v)), one())); } break; }
+      case IEXA_OP_COT: { v = d.div(one(), d.un(D_TAN, u)); if (active) { y = d.neg(d.add(one(), d.sq(v))); h = d.mul(d.mul(d.cnst(-2.0), v), y); } break; }
+      case IEXA_OP_SINH: v = d.un(D_SINH, u); if (active) { y = d.un(D_COSH, u); h = v; } break;
+      case IEXA_OP_COSH: v = d.un(D_COSH, u); if (active) { y = d.un(D_SINH, u); h = v; } break;
+      case IEXA_OP_TANH: v = d.un(D_TANH, u); if (active) { y = d.sub(one(), d.sq(v)); h = d.mul(d.mul(d.cnst(-2.0), v), y); } break;
+      case IEXA_OP_CSCH: { v = d.div(one(), d.un(D_SINH, u)); if (active) { y = d.neg(d.mul(d.sq(v), d.un(D_COSH, u))); h = d.mul(v, d.add(d.mul(d.cnst(2.0), d.sq(v)), one())); } break; }
+      case IEXA_OP_SECH: { v = d.div(one(), d.un(D_COSH, u)); if (active) { y = d.neg(d.mul(d.sq(v), d.un(D_SINH, u))); h = d.mul(v, d.sub(one(), d.mul(d.cnst(2.0), d.sq(v)))); } break; }
+      case IEXA_OP_COTH: { v = d.div(one(), d.un(D_TANH, u)); if (active) { y = d.sub(one(), d.sq(v)); h = d.mul(d.mul(d.cnst(-2.0), v), y); } break; }
+      case IEXA_OP_ATANH: v = d.un(D_ATANH, u); if (active) { y = d.div(one(), d.sub(one(), d.sq(u))); h = d.mul(d.mul(d.cnst(2.0), u), d.sq(y)); } break;
+      case IEXA_OP_ACOTH: v = d.un(D_ATANH, d.div(one(), u)); if (active) { y = d.div(one(), d.sub(one(), d.sq(u))); h = d.mul(d.mul(d.cnst(2.0), u), d.sq(y)); } break;
+      // degree variants: g(u * pi/180)  (or 180/pi * g(u) for the inverse functions)
+      case IEXA_OP_SIND: case IEXA_OP_COSD: case IEXA_OP_TAND: case IEXA_OP_CSCD: case IEXA_OP_SECD: case IEXA_OP_COTD: {
+        static const int base[6] = {IEXA_OP_SIN, IEXA_OP_COS, IEXA_OP_TAN, IEXA_OP_CSC, IEXA_OP_SEC, IEXA_OP_COT};
+        int which = op == IEXA_OP_SIND ? 0 : op == IEXA_OP_COSD ? 1 : op == IEXA_OP_TAND ? 2 : op == IEXA_OP_CSCD ? 3 : op == IEXA_OP_SECD ? 4 : 5;
+        int ur = d.mul(u, d.cnst(D2R));
+        int yy = -1, hh = -1;
+        v = lower_unary(base[which], ur, active, yy, hh);
+        if (active) { y = d.mul(yy, d.cnst(D2R)); h = d.mul(hh, d.cnst(D2R * D2R)); }
+        break;
+      }
+      case IEXA_OP_ATAND: case IEXA_OP_ACOTD: {
+        int yy = -1, hh = -1;
+        int vv = lower_unary(op == IEXA_OP_ATAND ? IEXA_OP_ATAN : IEXA_OP_ACOT, u, active, yy, hh);
+        v = d.mul(vv, d.cnst(R2D));
+        if (active) { y = d.mul(yy, d.cnst(R2D)); h = d.mul(hh, d.cnst(R2D)); }
+        break;
+      }
+      default: throw std::invalid_argument("tape: unsupported unary operator " + std::to_string(op));
+    }
+    return v;
+  }
+
+  void build_values() {
+    Dag &d = dag_;
+    val_.assign(n_, -1);
+    for (int i = 0; i < n_; ++i) {
+      const iexa_node &nd = g.tape[i];
+      Info &in = info_[i];
+      switch (nd.op) {
+        case IEXA_OP_CONST: val_[i] = d.cnst(nd.c); continue;
+        case IEXA_OP_FIELD: val_[i] = d.field(fpslot_[nd.a]); continue;
+        case IEXA_OP_VAR: val_[i] = d.loadx(g.idx_map[nd.a]); continue;
+        case IEXA_OP_PAR: val_[i] = d.loadp(g.idx_map[nd.a]); continue;
+        default: break;
+      }
+      if (is_un(nd.op)) {
+        val_[i] = lower_unary(nd.op, val_[nd.a], in.kind == K_UN, in.y1, in.h11);
+        continue;
+      }
+      int u1 = val_[nd.a], u2 = val_[nd.b];
+      int v = -1;
+      switch (nd.op) {
+        case IEXA_OP_ADD: v = d.add(u1, u2); break;
+        case IEXA_OP_SUB: v = d.sub(u1, u2); break;
+        case IEXA_OP_MUL: v = d.mul(u1, u2); break;
+        case IEXA_OP_DIV: v = d.div(u1, u2); break;
+        case IEXA_OP_POW: v = d.pow(u1, u2); break;
+      }
+      val_[i] = v;
+      int one = d.cnst(1.0), zero = d.cnst(0.0);
+      if (in.kind == K_BIN) {
+        switch (nd.op) {
+          case IEXA_OP_ADD: in.y1 = one; in.y2 = one; in.h11 = in.h12 = in.h22 = zero; break;
+          case IEXA_OP_SUB: in.y1 = one; in.y2 = d.cnst(-1.0); in.h11 = in.h12 = in.h22 = zero; break;
+          case IEXA_OP_MUL: in.y1 = u2; in.y2 = u1; in.h11 = zero; in.h12 = one; in.h22 = zero; break;
+          case IEXA_OP_DIV:
+            in.y1 = d.div(one, u2);
+            in.y2 = d.neg(d.div(v, u2));
+            in.h11 = zero;
+            in.h12 = d.neg(d.sq(in.y1));
+            in.h22 = d.div(d.mul(d.cnst(-2.0), in.y2), u2);
+            break;
+          case IEXA_OP_POW: {
+            int lg = d.un(D_LOG, u1);
+            int pm1 = d.pow(u1, d.sub(u2, one));
+            in.y1 = d.mul(u2, pm1);
+            in.y2 = d.mul(v, lg);
+            in.h11 = d.mul(d.mul(u2, d.sub(u2, one)), d.pow(u1, d.sub(u2, d.cnst(2.0))));
+            in.h12 = d.mul(pm1, d.add(one, d.mul(u2, lg)));
+            in.h22 = d.mul(in.y2, lg);
+            break;
+          }
+        }
+      } else if (in.kind == K_UN) {
+        bool first_active = info_[nd.a].kind != K_CONSTCLASS;
+        if (first_active) { // x op c
+          int c = u2;
+          switch (nd.op) {
+            case IEXA_OP_ADD: case IEXA_OP_SUB: in.y1 = one; in.h11 = zero; break;
+            case IEXA_OP_MUL: in.y1 = c; in.h11 = zero; break;
+            case IEXA_OP_DIV: in.y1 = d.div(one, c); in.h11 = zero; break;
+            case IEXA_OP_POW:
+              in.y1 = d.mul(c, d.pow(u1, d.sub(c, one)));
+              in.h11 = d.mul(d.mul(c, d.sub(c, one)), d.pow(u1, d.sub(c, d.cnst(2.0))));
+              break;
+          }
+        } else { // c op x
+          int c = u1;
+          switch (nd.op) {
+            case IEXA_OP_ADD: in.y1 = one; in.h11 = zero; break;
+            case IEXA_OP_SUB: in.y1 = d.cnst(-1.0); in.h11 = zero; break;
+            case IEXA_OP_MUL: in.y1 = c; in.h11 = zero; break;
+            case IEXA_OP_DIV: in.y1 = d.neg(d.div(v, u2)); in.h11 = d.div(d.mul(d.cnst(-2.0), in.y1), u2); break;
+            case IEXA_OP_POW: { int lg = d.un(D_LOG, c); in.y1 = d.mul(v, lg); in.h11 = d.mul(in.y1, lg); break; }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- first order: jrpass / grpass (leaves left to right) --------------------------
+  void emit1(int32_t u, int value) {
+    ++g.n_occ1;
+    auto it = slot1_of_.find(u);
+    int32_t s;
+    if (it == slot1_of_.end()) {
+      s = (int32_t)g.jac_slot.size();
+      slot1_of_[u] = s;
+      g.jac_slot.push_back(u);
+      slot1_.push_back(dag_.cnst(0.0));
+    } else s = it->second;
+    slot1_[s] = dag_.add(slot1_[s], value);
+  }
+  void jr(int t, int adj) {
+    const Info &in = info_[t];
+    switch (in.kind) {
+      case K_VAR: emit1(g.idx_map[g.tape[t].a], adj); break;
+      case K_UN: jr(in.c1, dag_.mul(adj, in.y1)); break;
+      case K_BIN: jr(in.c1, dag_.mul(adj, in.y1)); jr(in.c2, dag_.mul(adj, in.y2)); break;
+      default: break;
+    }
+  }
+  void first_order() {
+    if (!g.is_null) jr(n_ - 1, dag_.cnst(1.0));
+    g.o1step = (int32_t)g.jac_slot.size();
+  }
+
+  // ---- second order: hrpass0 / hrpass / hdrpass --------------------------------------
+  void emit2(int32_t u1, int32_t u2, int value) {
+    ++g.n_occ2;
+    auto key = std::make_pair(u1, u2);
+    auto it = slot2_of_.find(key);
+    int32_t s;
+    if (it == slot2_of_.end()) {
+      s = (int32_t)g.hess_slot.size();
+      slot2_of_[key] = s;
+      g.hess_slot.push_back(key);
+      slot2_.push_back(dag_.cnst(0.0));
+    } else s = it->second;
+    slot2_[s] = dag_.add(slot2_[s], value);
+  }
+  void hr0(int t, int adj, int adj2) {
+    const Info &in = info_[t];
+    Dag &d = dag_;
+    switch (in.pass) {
+      case P_KEEP: hr0(in.c1, adj, adj2); return;
+      case P_FLIP: hr0(in.c1, d.neg(adj), adj2); return;
+      case P_SCALE: hr0(in.c1, d.mul(adj, in.y1), d.mul(adj2, d.sq(in.y1))); return;
+      case P_ADD: hr0(in.c1, adj, adj2); hr0(in.c2, adj, adj2); return;
+      case P_SUB: hr0(in.c1, adj, adj2); hr0(in.c2, d.neg(adj), adj2); return;
+      default: break;
+    }
+    if (in.kind == K_VAR || in.kind == K_CONSTCLASS) return; // linear leaf: no Hessian slot
+    hr(t, adj, adj2);
+  }
+  void hr(int t, int adj, int adj2) {
+    const Info &in = info_[t];
+    Dag &d = dag_;
+    switch (in.kind) {
+      case K_VAR: { int32_t u = g.idx_map[g.tape[t].a]; emit2(u, u, adj2); break; }
+      case K_UN:
+        hr(in.c1, d.mul(adj, in.y1), d.add(d.mul(adj2, d.sq(in.y1)), d.mul(adj, in.h11)));
+        break;
+      case K_BIN: {
+        int cross = d.add(d.mul(d.mul(adj2, in.y1), in.y2), d.mul(adj, in.h12));
+        hr(in.c1, d.mul(adj, in.y1), d.add(d.mul(adj2, d.sq(in.y1)), d.mul(adj, in.h11)));
+        hr(in.c2, d.mul(adj, in.y2), d.add(d.mul(adj2, d.sq(in.y2)), d.mul(adj, in.h22)));
+        hdr(in.c1, in.c2, cross);
+        break;
+      }
+      default: break;
+    }
+  }
+  void hdr(int t1, int t2, int adj) {
+    const Info &a = info_[t1], &b = info_[t2];
+    Dag &d = dag_;
+    if (a.kind == K_VAR && b.kind == K_VAR) {
+      int32_t u1 = g.idx_map[g.tape[t1].a], u2 = g.idx_map[g.tape[t2].a];
+      emit2(u1, u2, d.mul(adj, d.sel2(u1, u2)));
+    } else if (a.kind == K_UN && b.kind == K_UN) {
+      hdr(a.c1, b.c1, d.mul(d.mul(adj, a.y1), b.y1));
+    } else if (a.kind == K_UN && b.kind == K_BIN) {
+      hdr(a.c1, b.c1, d.mul(d.mul(adj, a.y1), b.y1));
+      hdr(a.c1, b.c2, d.mul(d.mul(adj, a.y1), b.y2));
+    } else if (a.kind == K_BIN && b.kind == K_UN) {
+      hdr(a.c1, b.c1, d.mul(d.mul(adj, a.y1), b.y1));
+      hdr(a.c2, b.c1, d.mul(d.mul(adj, a.y2), b.y1));
+    } else if (a.kind == K_BIN && b.kind == K_BIN) {
+      hdr(a.c1, b.c1, d.mul(d.mul(adj, a.y1), b.y1));
+      hdr(a.c1, b.c2, d.mul(d.mul(adj, a.y1), b.y2));
+      hdr(a.c2, b.c1, d.mul(d.mul(adj, a.y2), b.y1));
+      hdr(a.c2, b.c2, d.mul(d.mul(adj, a.y2), b.y2));
+    } else if (a.kind == K_VAR && b.kind == K_UN) {
+      hdr(t1, b.c1, d.mul(adj, b.y1));
+    } else if (a.kind == K_VAR && b.kind == K_BIN) {
+      hdr(t1, b.c1, d.mul(adj, b.y1));
+      hdr(t1, b.c2, d.mul(adj, b.y2));
+    } else if (a.kind == K_UN && b.kind == K_VAR) {
+      hdr(a.c1, t2, d.mul(adj, a.y1));
+    } else if (a.kind == K_BIN && b.kind == K_VAR) {
+      hdr(a.c1, t2, d.mul(adj, a.y1));
+      hdr(a.c2, t2, d.mul(adj, a.y2));
+    }
+  }
+  void second_order() {
+    if (!g.is_null) hr0(n_ - 1, dag_.w(), dag_.cnst(0.0));
+    g.o2step = (int32_t)g.hess_slot.size();
+  }
+
+  // ---- DAG -> register program ---------------------------------------------------------
+  Program schedule(const std::vector<int> &outs, std::vector<uint8_t> &x_slots) {
+    Program P;
+    const auto &N = dag_.nodes;
+    int nn = (int)N.size();
+    std::vector<uint8_t> live(nn, 0);
+    std::vector<int> stack(outs.begin(), outs.end());
+    while (!stack.empty()) {
+      int v = stack.back(); stack.pop_back();
+      if (live[v]) continue;
+      live[v] = 1;
+      int op = N[v].op;
+      if (dop_is_unary(op)) stack.push_back(N[v].a);
+      else if (dop_is_binary(op)) { stack.push_back(N[v].a); stack.push_back(N[v].b); }
+    }
+    // last use
+    std::vector<int> last(nn, -1);
+    for (int v = 0; v < nn; ++v) {
+      if (!live[v]) continue;
+      int op = N[v].op;
+      if (dop_is_unary(op)) last[N[v].a] = v;
+      else if (dop_is_binary(op)) { last[N[v].a] = v; last[N[v].b] = v; }
+    }
+    std::vector<std::vector<int>> outs_of(nn);
+    for (size_t j = 0; j < outs.size(); ++j) outs_of[outs[j]].push_back((int)j);
+    std::vector<int> reg(nn, -1), cidx(nn, -1);
+    std::vector<int> freelist;
+    int nreg = 0;
+    auto alloc = [&]() { if (!freelist.empty()) { int r = freelist.back(); freelist.pop_back(); return r; } return nreg++; };
+    auto operand = [&](int v) -> int32_t {
+      if (N[v].op == D_CONST) {
+        if (cidx[v] < 0) { cidx[v] = (int)P.cpool.size(); P.cpool.push_back(N[v].c); }
+        return ~cidx[v];
+      }
+      return reg[v];
+    };
+    x_slots.assign(g.uidx.size(), 0);
+    P.nout = (int32_t)outs.size();
+    for (int v = 0; v < nn; ++v) {
+      if (!live[v]) continue;
+      int op = N[v].op;
+      if (op == D_CONST) {
+        for (int j : outs_of[v]) P.code.push_back(Instr{D_OUT, j, operand(v), 0});
+        continue;
+      }
+      Instr I{op, 0, 0, 0};
+      if (dop_is_unary(op)) I.a = operand(N[v].a);
+      else if (dop_is_binary(op)) { I.a = operand(N[v].a); I.b = operand(N[v].b); }
+      else { I.a = N[v].a; I.b = N[v].b; }
+      if (op == D_LOADX) x_slots[N[v].a] = 1;
+      if (op == D_W) P.uses_w = true;
+      // free operand registers whose last use is here BEFORE allocating dst (dst may reuse them)
+      if (dop_is_unary(op) || dop_is_binary(op)) {
+        int a = N[v].a, b = dop_is_binary(op) ? N[v].b : -1;
+        if (N[a].op != D_CONST && last[a] == v) freelist.push_back(reg[a]);
+        if (b >= 0 && b != a && N[b].op != D_CONST && last[b] == v) freelist.push_back(reg[b]);
+        ++P.n_flop_nodes;
+      }
+      reg[v] = alloc();
+      I.dst = reg[v];
+      P.code.push_back(I);
+      for (int j : outs_of[v]) P.code.push_back(Instr{D_OUT, j, reg[v], 0});
+      if (last[v] < 0) freelist.push_back(reg[v]); // only feeds outputs (already emitted)
+    }
+    P.nreg = nreg;
+    return P;
+  }
+};
+
+} // namespace iexa

@@ -1,0 +1,207 @@
+// plan.hpp — host-side evaluation plan: x/theta layout, SoA iterator columns, compiled
+// generators, global + per-rank COO layout.  No CUDA in this header (the device engine
+// lives in engine.cu; tests/hostcheck.cpp reuses this header to validate the plan
+// compiler on machines without a GPU).
+//
+// Emission order == layout order, as fixed by build_exa_core! (src/transform.jl:771-796):
+// variables / parameters / constraints / objectives are appended in call order; rows of
+// generator g are o0_g + k, Jacobian slots o1_g + o1step_g*k + c, Hessian slots
+// o2_g + o2step_g*k + c with all OBJECTIVE generators first.
+#pragma once
+#include <cmath>
+#include <limits>
+#include <memory>
+#include <string>
+
+#include "gen.hpp"
+
+namespace iexa {
+
+struct HostColumn {
+  int64_t K = 0;
+  bool is_int = false;
+  bool iota = false;            // int column equal to 1..K: never stored
+  std::vector<int32_t> ivals;   // int column (narrowed; x/theta indices fit in int32)
+  std::vector<double> fvals;
+};
+
+struct ColRef {
+  int32_t col; // index into Plan::columns
+  int64_t div, mod; // value(k) = column[(k / div) % mod]
+};
+
+struct Iterator {
+  int64_t K = 1;
+  std::vector<ColRef> int_cols, fp_cols;
+};
+
+struct Generator {
+  bool is_obj = false;
+  int32_t itr = 0;
+  int64_t K = 1;
+  double lcon = 0, ucon = 0;
+  GenCompiled c;
+  // global layout (0-based)
+  int64_t o0 = 0, o1 = 0, o2 = 0, og = 0;
+  // this rank's support range and local layout
+  int64_t k0 = 0, k1 = 0;
+  int64_t l0 = 0, l1 = 0, l2 = 0;
+};
+
+struct Plan {
+  bool minimize = true;
+  bool finalized = false;
+  std::vector<double> x0, lvar, uvar, theta;
+  std::vector<HostColumn> columns;
+  std::vector<Iterator> itrs;
+  std::vector<Generator> objs, cons;
+  int64_t nvar = 0, npar = 0, ncon = 0, nnzj = 0, nnzh = 0, nnzg = 0;
+  int64_t loc_ncon = 0, loc_nnzj = 0, loc_nnzh = 0;
+  int32_t rank = 0, world = 1, device = -1;
+  std::vector<double> lcon, ucon, y0;
+
+  Plan() {
+    itrs.emplace_back(); // iterator 0 is the empty iterator [(;)] (transform.jl:440, :614)
+  }
+
+  int64_t add_var(int64_t n, const double *s, const double *l, const double *u) {
+    int64_t off = nvar;
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int64_t i = 0; i < n; ++i) {
+      x0.push_back(s ? s[i] : 0.0);
+      lvar.push_back(l ? l[i] : -inf);
+      uvar.push_back(u ? u[i] : inf);
+    }
+    nvar += n;
+    return off;
+  }
+  int64_t add_par(int64_t n, const double *v) {
+    int64_t off = npar;
+    theta.insert(theta.end(), v, v + n);
+    npar += n;
+    return off;
+  }
+
+  int32_t itr_base(int64_t K, int32_t n_int, const int64_t *const *ic, int32_t n_fp,
+                   const double *const *fc) {
+    if (K < 0) throw std::invalid_argument("iterator: negative length");
+    Iterator it;
+    it.K = K;
+    for (int32_t j = 0; j < n_int; ++j) {
+      HostColumn c;
+      c.K = K; c.is_int = true; c.iota = true;
+      for (int64_t k = 0; k < K; ++k)
+        if (ic[j][k] != k + 1) { c.iota = false; break; }
+      if (!c.iota) {
+        c.ivals.resize(K);
+        for (int64_t k = 0; k < K; ++k) {
+          int64_t v = ic[j][k];
+          if (v < INT32_MIN || v > INT32_MAX) throw std::invalid_argument("iterator: integer field exceeds int32");
+          c.ivals[k] = (int32_t)v;
+        }
+      }
+      it.int_cols.push_back(ColRef{(int32_t)columns.size(), 1, K > 0 ? K : 1});
+      columns.push_back(std::move(c));
+    }
+    for (int32_t j = 0; j < n_fp; ++j) {
+      HostColumn c;
+      c.K = K; c.is_int = false;
+      c.fvals.assign(fc[j], fc[j] + K);
+      it.fp_cols.push_back(ColRef{(int32_t)columns.size(), 1, K > 0 ? K : 1});
+      columns.push_back(std::move(c));
+    }
+    itrs.push_back(std::move(it));
+    return (int32_t)itrs.size() - 1;
+  }
+
+  int32_t itr_product(int32_t n, const int32_t *ids) {
+    Iterator it;
+    it.K = 1;
+    for (int32_t f = 0; f < n; ++f) {
+      if (ids[f] < 0 || ids[f] >= (int32_t)itrs.size()) throw std::invalid_argument("product: bad iterator id");
+      const Iterator &s = itrs[ids[f]];
+      for (auto c : s.int_cols) { c.div *= it.K; it.int_cols.push_back(c); }
+      for (auto c : s.fp_cols) { c.div *= it.K; it.fp_cols.push_back(c); }
+      it.K *= s.K;
+    }
+    itrs.push_back(std::move(it));
+    return (int32_t)itrs.size() - 1;
+  }
+
+  Generator make_gen(const iexa_node *nodes, int32_t n, const iexa_index *idx, int32_t n_idx,
+                     int32_t itr) {
+    if (finalized) throw std::logic_error("plan already finalized");
+    if (itr < 0 || itr >= (int32_t)itrs.size()) throw std::invalid_argument("bad iterator id");
+    const Iterator &it = itrs[itr];
+    GenCompiler gc(nodes, n, idx, n_idx, (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size());
+    gc.compile();
+    Generator g;
+    g.itr = itr;
+    g.K = it.K;
+    g.c = std::move(gc.g);
+    return g;
+  }
+
+  int64_t add_con(const iexa_node *nodes, int32_t n, const iexa_index *idx, int32_t n_idx,
+                  int32_t itr, double lc, double uc) {
+    Generator g = make_gen(nodes, n, idx, n_idx, itr);
+    g.is_obj = false; g.lcon = lc; g.ucon = uc;
+    g.o0 = ncon;
+    ncon += g.K;
+    for (int64_t k = 0; k < g.K; ++k) { lcon.push_back(lc); ucon.push_back(uc); y0.push_back(0.0); }
+    cons.push_back(std::move(g));
+    return cons.back().o0;
+  }
+  void add_obj(const iexa_node *nodes, int32_t n, const iexa_index *idx, int32_t n_idx, int32_t itr) {
+    Generator g = make_gen(nodes, n, idx, n_idx, itr);
+    g.is_obj = true;
+    objs.push_back(std::move(g));
+  }
+
+  // column accessors for a generator (host side: structure checks, hostcheck, sharding analysis)
+  int64_t int_col_value(const Generator &g, int32_t slot, int64_t k) const {
+    const ColRef &r = itrs[g.itr].int_cols[g.c.int_cols[slot]];
+    int64_t j = (k / r.div) % r.mod;
+    const HostColumn &c = columns[r.col];
+    return c.iota ? j + 1 : (int64_t)c.ivals[j];
+  }
+  double fp_col_value(const Generator &g, int32_t slot, int64_t k) const {
+    const ColRef &r = itrs[g.itr].fp_cols[g.c.fp_cols[slot]];
+    return columns[r.col].fvals[(k / r.div) % r.mod];
+  }
+  int64_t index_value(const Generator &g, int32_t islot, int64_t k) const {
+    const IndexExpr &e = g.c.uidx[islot];
+    int64_t v = e.base;
+    for (auto &t : e.terms) v += t.second * int_col_value(g, t.first, k);
+    return v;
+  }
+
+  void layout(int32_t rank_, int32_t world_) {
+    if (world_ < 1 || rank_ < 0 || rank_ >= world_) throw std::invalid_argument("bad rank/world");
+    rank = rank_; world = world_;
+    nnzj = nnzh = nnzg = 0;
+    loc_ncon = loc_nnzj = loc_nnzh = 0;
+    auto range = [&](Generator &g) {
+      // contiguous support blocks; length-1 generators live on rank 0
+      g.k0 = (g.K * rank) / world;
+      g.k1 = (g.K * (rank + 1)) / world;
+    };
+    for (auto &g : objs) {
+      range(g);
+      g.og = nnzg; nnzg += g.K * g.c.o1step;
+      g.o2 = nnzh; nnzh += g.K * g.c.o2step;
+      g.l2 = loc_nnzh; loc_nnzh += (g.k1 - g.k0) * g.c.o2step;
+    }
+    for (auto &g : cons) {
+      range(g);
+      g.o1 = nnzj; nnzj += g.K * g.c.o1step;
+      g.o2 = nnzh; nnzh += g.K * g.c.o2step;
+      g.l0 = loc_ncon; loc_ncon += (g.k1 - g.k0);
+      g.l1 = loc_nnzj; loc_nnzj += (g.k1 - g.k0) * g.c.o1step;
+      g.l2 = loc_nnzh; loc_nnzh += (g.k1 - g.k0) * g.c.o2step;
+    }
+    finalized = true;
+  }
+};
+
+} // namespace iexa
