@@ -211,6 +211,12 @@ int64_t iexa_algorithmic_bytes(const iexa_plan *p, int32_t which);
 /* number of kernel launches one call of callback `which` performs                      */
 int32_t iexa_launches_per_call(const iexa_plan *p, int32_t which);
 
+/* ---- diagnostics: the CUDA translation unit that iexa_finalize specialises with NVRTC.
+ *      _source returns its length (copies up to cap-1 bytes); _compile runs NVRTC for sm_100a
+ *      without loading the image (works on a machine without a GPU).                       */
+int64_t iexa_debug_codegen_source(const iexa_plan *p, char *buf, int64_t cap);
+int32_t iexa_debug_codegen_compile(const iexa_plan *p, int64_t *cubin_bytes);
+
 /* ---- COO -> CSR value permutation feeding cuDSS (today MadNLPGPU's transfer! kernel,
  *      caller side of ext/InfiniteExaModelsMadNLP.jl:49-50).  Setup sorts the 1-based
  *      COO pattern once; apply sums duplicates into CSR order with no atomics.         */

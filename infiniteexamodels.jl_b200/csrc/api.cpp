@@ -1,0 +1,376 @@
+// api.cpp — extern "C" entry points declared in include/iexa.h.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/iexa.h"
+#include "engine.hpp"
+#include "plan.hpp"
+
+#include "api_internal.hpp"
+#include "codegen.hpp"
+
+namespace iexa {
+bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string &err);
+} // namespace iexa
+
+namespace iexa { thread_local std::string g_last_error; }
+#define g_err iexa::g_last_error
+static int32_t fail(int32_t code, const std::string &msg) { g_err = msg; return code; }
+
+#define GUARD_BEGIN try {
+#define GUARD_END                                                              \
+  }                                                                            \
+  catch (const std::invalid_argument &e) { return fail(IEXA_ERR_INVALID, e.what()); } \
+  catch (const std::logic_error &e) { return fail(IEXA_ERR_STATE, e.what()); } \
+  catch (const std::bad_alloc &) { return fail(IEXA_ERR_NOMEM, "out of host memory"); } \
+  catch (const std::exception &e) { return fail(IEXA_ERR_INVALID, e.what()); } \
+  catch (...) { return fail(IEXA_ERR_INVALID, "unknown C++ exception"); }
+
+#define NEED_PLAN(p) if (!(p)) return fail(IEXA_ERR_INVALID, "null plan")
+#define NEED_ENGINE(p)                                                                          \
+  NEED_PLAN(p);                                                                                 \
+  if (!(p)->plan.finalized) return fail(IEXA_ERR_STATE, "plan not finalized");                  \
+  if (!(p)->engine) return fail(IEXA_ERR_CUDA, "plan has no CUDA engine (finalized with IEXA_F_NO_DEVICE or no GPU): there is no CPU fallback")
+
+extern "C" {
+
+const char *iexa_last_error(void) { return g_err.c_str(); }
+int32_t iexa_version(void) { return IEXA_VERSION; }
+
+int32_t iexa_plan_create(iexa_plan **out, int32_t minimize) {
+  GUARD_BEGIN
+  if (!out) return fail(IEXA_ERR_INVALID, "null out");
+  *out = new iexa_plan();
+  (*out)->plan.minimize = minimize != 0;
+  return IEXA_OK;
+  GUARD_END
+}
+int32_t iexa_plan_destroy(iexa_plan *p) {
+  GUARD_BEGIN
+  delete p;
+  return IEXA_OK;
+  GUARD_END
+}
+
+int32_t iexa_add_var(iexa_plan *p, int64_t n, const double *x0, const double *lvar, const double *uvar,
+                     int64_t *offset_out) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (p->plan.finalized) return fail(IEXA_ERR_STATE, "plan already finalized");
+  if (n < 0) return fail(IEXA_ERR_INVALID, "negative length");
+  int64_t off = p->plan.add_var(n, x0, lvar, uvar);
+  if (offset_out) *offset_out = off;
+  return IEXA_OK;
+  GUARD_END
+}
+int32_t iexa_add_par(iexa_plan *p, int64_t n, const double *vals, int64_t *offset_out) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (p->plan.finalized) return fail(IEXA_ERR_STATE, "plan already finalized");
+  if (n < 0 || (n > 0 && !vals)) return fail(IEXA_ERR_INVALID, "bad parameter block");
+  int64_t off = p->plan.add_par(n, vals);
+  if (offset_out) *offset_out = off;
+  return IEXA_OK;
+  GUARD_END
+}
+int32_t iexa_patch_var(iexa_plan *p, int32_t which, int64_t i, double value) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (p->plan.finalized && which != 0) return fail(IEXA_ERR_STATE, "bounds are frozen after finalize");
+  if (i < 1 || i > p->plan.nvar) return fail(IEXA_ERR_INVALID, "variable index out of range");
+  std::vector<double> *v = which == 0 ? &p->plan.x0 : which == 1 ? &p->plan.lvar : which == 2 ? &p->plan.uvar : nullptr;
+  if (!v) return fail(IEXA_ERR_INVALID, "which must be 0,1,2");
+  (*v)[i - 1] = value;
+  return IEXA_OK;
+  GUARD_END
+}
+
+int32_t iexa_itr_base(iexa_plan *p, int64_t K, int32_t n_int, const int64_t *const *int_cols, int32_t n_fp,
+                      const double *const *fp_cols, int32_t *itr_out) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (p->plan.finalized) return fail(IEXA_ERR_STATE, "plan already finalized");
+  if (n_int < 0 || n_fp < 0 || !itr_out) return fail(IEXA_ERR_INVALID, "bad iterator arguments");
+  *itr_out = p->plan.itr_base(K, n_int, int_cols, n_fp, fp_cols);
+  return IEXA_OK;
+  GUARD_END
+}
+int32_t iexa_itr_product(iexa_plan *p, int32_t n, const int32_t *itrs, int32_t *itr_out) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (p->plan.finalized) return fail(IEXA_ERR_STATE, "plan already finalized");
+  if (n < 0 || !itr_out) return fail(IEXA_ERR_INVALID, "bad product arguments");
+  *itr_out = p->plan.itr_product(n, itrs);
+  return IEXA_OK;
+  GUARD_END
+}
+
+int32_t iexa_add_con(iexa_plan *p, const iexa_node *nodes, int32_t n_nodes, const iexa_index *idx, int32_t n_idx,
+                     int32_t itr, double lcon, double ucon, int64_t *row_offset_out) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (!nodes || n_idx < 0 || (n_idx > 0 && !idx)) return fail(IEXA_ERR_INVALID, "bad tape arguments");
+  int64_t off = p->plan.add_con(nodes, n_nodes, idx, n_idx, itr, lcon, ucon);
+  if (row_offset_out) *row_offset_out = off;
+  return IEXA_OK;
+  GUARD_END
+}
+int32_t iexa_add_obj(iexa_plan *p, const iexa_node *nodes, int32_t n_nodes, const iexa_index *idx, int32_t n_idx,
+                     int32_t itr) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (!nodes || n_idx < 0 || (n_idx > 0 && !idx)) return fail(IEXA_ERR_INVALID, "bad tape arguments");
+  p->plan.add_obj(nodes, n_nodes, idx, n_idx, itr);
+  return IEXA_OK;
+  GUARD_END
+}
+
+int32_t iexa_finalize(iexa_plan *p, int32_t device, int32_t rank, int32_t world, uint32_t flags) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (p->plan.finalized) return fail(IEXA_ERR_STATE, "plan already finalized");
+  p->plan.layout(rank, world);
+  p->plan.device = device;
+  p->flags = flags;
+  if (flags & IEXA_F_NO_DEVICE) return IEXA_OK;
+  std::string err;
+  iexa::Engine *e = iexa::make_cuda_engine(p->plan, device, flags, err);
+  if (!e) return fail(IEXA_ERR_CUDA, err);
+  p->engine.reset(e);
+  return IEXA_OK;
+  GUARD_END
+}
+
+int32_t iexa_get_meta(const iexa_plan *p, iexa_meta *m) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (!m) return fail(IEXA_ERR_INVALID, "null out");
+  const iexa::Plan &P = p->plan;
+  std::memset(m, 0, sizeof *m);
+  m->nvar = P.nvar; m->ncon = P.ncon; m->npar = P.npar;
+  m->nobj_gen = (int64_t)P.objs.size(); m->ncon_gen = (int64_t)P.cons.size();
+  m->nnzj = P.nnzj; m->nnzh = P.nnzh; m->nnzg = P.nnzg;
+  m->loc_ncon = P.loc_ncon; m->loc_nnzj = P.loc_nnzj; m->loc_nnzh = P.loc_nnzh;
+  m->minimize = P.minimize; m->rank = P.rank; m->world = P.world; m->device = P.device;
+  m->n_kernels_specialised = p->engine ? p->engine->n_specialised() : 0;
+  return IEXA_OK;
+  GUARD_END
+}
+
+int32_t iexa_get_vector(const iexa_plan *p, int32_t which, double *out) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  const iexa::Plan &P = p->plan;
+  const std::vector<double> *v = which == 0 ? &P.x0 : which == 1 ? &P.lvar : which == 2 ? &P.uvar
+                                 : which == 3 ? &P.lcon : which == 4 ? &P.ucon : which == 5 ? &P.y0 : nullptr;
+  if (!v || !out) return fail(IEXA_ERR_INVALID, "bad vector selector");
+  if (!v->empty()) std::memcpy(out, v->data(), v->size() * 8);
+  return IEXA_OK;
+  GUARD_END
+}
+int32_t iexa_set_vector(iexa_plan *p, int32_t which, const double *in) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  iexa::Plan &P = p->plan;
+  std::vector<double> *v = which == 0 ? &P.x0 : which == 5 ? &P.y0 : nullptr;
+  if (!v || !in) return fail(IEXA_ERR_INVALID, "only x0 (0) and y0 (5) can be set");
+  if (!v->empty()) std::memcpy(v->data(), in, v->size() * 8);
+  return IEXA_OK;
+  GUARD_END
+}
+
+int32_t iexa_set_par(iexa_plan *p, int64_t off, int64_t n, const double *vals) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (off < 0 || n < 0 || off + n > p->plan.npar || (n > 0 && !vals)) return fail(IEXA_ERR_INVALID, "parameter range out of bounds");
+  std::memcpy(p->plan.theta.data() + off, vals, (size_t)n * 8);
+  if (p->engine) {
+    std::string err;
+    int rc = p->engine->set_par(off, n, vals, err);
+    if (rc) return fail(rc, err);
+  }
+  return IEXA_OK;
+  GUARD_END
+}
+int32_t iexa_get_par(const iexa_plan *p, int64_t off, int64_t n, double *vals) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (off < 0 || n < 0 || off + n > p->plan.npar || (n > 0 && !vals)) return fail(IEXA_ERR_INVALID, "parameter range out of bounds");
+  std::memcpy(vals, p->plan.theta.data() + off, (size_t)n * 8);
+  return IEXA_OK;
+  GUARD_END
+}
+
+#define ENGINE_CALL(expr)          \
+  GUARD_BEGIN                      \
+  NEED_ENGINE(p);                  \
+  std::string err;                 \
+  int rc = p->engine->expr;        \
+  if (rc) return fail(rc, err);    \
+  return IEXA_OK;                  \
+  GUARD_END
+
+int32_t iexa_jac_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_bytes, int32_t memspace, void *stream) {
+  ENGINE_CALL(structure(0, rows, cols, idx_bytes, memspace, stream, err))
+}
+int32_t iexa_hess_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_bytes, int32_t memspace, void *stream) {
+  ENGINE_CALL(structure(1, rows, cols, idx_bytes, memspace, stream, err))
+}
+int32_t iexa_obj(iexa_plan *p, const double *x, double *f_host, int32_t memspace, void *stream) {
+  ENGINE_CALL(obj(x, f_host, memspace, stream, err))
+}
+int32_t iexa_obj_device(iexa_plan *p, const double *x_dev, double *f_dev, void *stream) {
+  ENGINE_CALL(obj_device(x_dev, f_dev, stream, err))
+}
+int32_t iexa_grad(iexa_plan *p, const double *x, double *g, int32_t memspace, void *stream) {
+  ENGINE_CALL(grad(x, g, memspace, stream, err))
+}
+int32_t iexa_cons(iexa_plan *p, const double *x, double *c, int32_t memspace, void *stream) {
+  ENGINE_CALL(cons(x, c, memspace, stream, err))
+}
+int32_t iexa_jac_coord(iexa_plan *p, const double *x, double *vals, int32_t memspace, void *stream) {
+  ENGINE_CALL(jac(x, vals, memspace, stream, err))
+}
+int32_t iexa_hess_coord(iexa_plan *p, const double *x, const double *y, double obj_weight, double *vals,
+                        int32_t memspace, void *stream) {
+  ENGINE_CALL(hess(x, y, obj_weight, vals, memspace, stream, err))
+}
+int32_t iexa_jprod(iexa_plan *p, const double *x, const double *v, double *Jv, int32_t memspace, void *stream) {
+  ENGINE_CALL(jprod(x, v, Jv, memspace, stream, err))
+}
+int32_t iexa_jtprod(iexa_plan *p, const double *x, const double *v, double *Jtv, int32_t memspace, void *stream) {
+  ENGINE_CALL(jtprod(x, v, Jtv, memspace, stream, err))
+}
+int32_t iexa_hprod(iexa_plan *p, const double *x, const double *y, const double *v, double obj_weight, double *Hv,
+                   int32_t memspace, void *stream) {
+  ENGINE_CALL(hprod(x, y, v, obj_weight, Hv, memspace, stream, err))
+}
+
+// ---- sharding queries ----------------------------------------------------------------------------
+int64_t iexa_segments(const iexa_plan *p, int32_t which, iexa_segment *out, int64_t cap) {
+  if (!p || !p->plan.finalized) return -1;
+  const iexa::Plan &P = p->plan;
+  int64_t n = 0;
+  auto push = [&](int64_t gs, int64_t ls, int64_t len) {
+    if (len <= 0) return;
+    if (out && n < cap) out[n] = iexa_segment{gs, ls, len};
+    ++n;
+  };
+  if (which == 2)
+    for (auto &g : P.objs) push(g.o2 + g.k0 * g.c.o2step, g.l2, (g.k1 - g.k0) * g.c.o2step);
+  for (auto &g : P.cons) {
+    if (which == 0) push(g.o0 + g.k0, g.l0, g.k1 - g.k0);
+    else if (which == 1) push(g.o1 + g.k0 * g.c.o1step, g.l1, (g.k1 - g.k0) * g.c.o1step);
+    else push(g.o2 + g.k0 * g.c.o2step, g.l2, (g.k1 - g.k0) * g.c.o2step);
+  }
+  return n;
+}
+
+int64_t iexa_shared_vars(const iexa_plan *p, int64_t *out, int64_t cap) {
+  // variables referenced through a CONSTANT index by an objective generator with more than one
+  // support, or by any generator whose support range is split across ranks: their gradient
+  // entries are partial sums on every rank.  (Halo entries of shifted references such as
+  // y[i-1] are covered because each objective generator touches x only through its own k.)
+  if (!p || !p->plan.finalized) return -1;
+  const iexa::Plan &P = p->plan;
+  std::vector<int64_t> v;
+  for (auto &g : P.objs)
+    for (int32_t s : g.c.jac_slot)
+      if (g.c.uidx[s].terms.empty()) v.push_back(g.c.uidx[s].base);
+  std::sort(v.begin(), v.end());
+  v.erase(std::unique(v.begin(), v.end()), v.end());
+  for (size_t i = 0; i < v.size() && (int64_t)i < cap && out; ++i) out[i] = v[i];
+  return (int64_t)v.size();
+}
+
+// ---- algorithmic bytes --------------------------------------------------------
+int64_t iexa_algorithmic_bytes(const iexa_plan *pc, int32_t which) {
+  if (!pc || !pc->plan.finalized || which < 0 || which > 4) return -1;
+  iexa_plan *p = const_cast<iexa_plan *>(pc);
+  if (p->bytes_cache[which] >= 0) return p->bytes_cache[which];
+  const iexa::Plan &P = p->plan;
+  std::vector<const iexa::Generator *> gens;
+  const bool use_obj = which == 0 || which == 1 || which == 4;
+  const bool use_con = which >= 2;
+  if (use_obj) for (auto &g : P.objs) gens.push_back(&g);
+  if (use_con) for (auto &g : P.cons) gens.push_back(&g);
+  std::vector<bool> xs((size_t)P.nvar, false), ts((size_t)P.npar, false);
+  std::vector<std::vector<bool>> colseen(P.columns.size());
+  int64_t bytes = 0;
+  for (const iexa::Generator *gp : gens) {
+    const iexa::Generator &g = *gp;
+    const iexa::Program &pr = (which == 0 || which == 2) ? g.c.val : (which == 1 || which == 3) ? g.c.d1 : g.c.d2;
+    if (pr.nout == 0) continue;
+    const iexa::Iterator &it = P.itrs[g.itr];
+    std::vector<int32_t> lx, lp;
+    std::vector<int32_t> fcols, icols_used;
+    std::vector<bool> iused(g.c.int_cols.size(), false);
+    auto mark_idx = [&](int32_t islot) { for (auto &t : g.c.uidx[islot].terms) iused[t.first] = true; };
+    for (const iexa::Instr &I : pr.code) {
+      if (I.op == iexa::D_LOADX) { lx.push_back(I.a); mark_idx(I.a); }
+      else if (I.op == iexa::D_LOADP) { lp.push_back(I.a); mark_idx(I.a); }
+      else if (I.op == iexa::D_FIELD) fcols.push_back(I.a);
+      else if (I.op == iexa::D_SEL2) { mark_idx(I.a); mark_idx(I.b); }
+    }
+    if (which == 1) for (int32_t s : g.c.jac_slot) mark_idx(s);
+    for (int64_t k = g.k0; k < g.k1; ++k) {
+      for (int32_t s : lx) { int64_t i = P.index_value(g, s, k) - 1; if (i >= 0 && i < P.nvar && !xs[i]) { xs[i] = true; bytes += 8; } }
+      for (int32_t s : lp) { int64_t i = P.index_value(g, s, k) - 1; if (i >= 0 && i < P.npar && !ts[i]) { ts[i] = true; bytes += 8; } }
+    }
+    auto touch_col = [&](const iexa::ColRef &r, int esz) {
+      const iexa::HostColumn &c = P.columns[r.col];
+      if (c.is_int && c.iota) return;
+      auto &seen = colseen[r.col];
+      if (seen.empty()) seen.assign((size_t)c.K, false);
+      // entries reached by the local support range
+      if (r.div == 1 && r.mod == g.K) {
+        for (int64_t k = g.k0; k < g.k1; ++k) if (!seen[k]) { seen[k] = true; bytes += esz; }
+      } else {
+        for (int64_t k = g.k0; k < g.k1; ++k) { int64_t j = (k / r.div) % r.mod; if (!seen[j]) { seen[j] = true; bytes += esz; } }
+      }
+    };
+    for (int32_t s : fcols) touch_col(it.fp_cols[g.c.fp_cols[s]], 8);
+    for (size_t s = 0; s < iused.size(); ++s) if (iused[s]) touch_col(it.int_cols[g.c.int_cols[s]], 4);
+    if (which == 4 && !g.is_obj && pr.uses_w) bytes += 8 * (g.k1 - g.k0); // multipliers y
+  }
+  switch (which) {
+    case 0: bytes += 8; break;
+    case 1: bytes += 8 * P.nvar; break;
+    case 2: bytes += 8 * P.loc_ncon; break;
+    case 3: bytes += 8 * P.loc_nnzj; break;
+    case 4: bytes += 8 * P.loc_nnzh; break;
+  }
+  p->bytes_cache[which] = bytes;
+  return bytes;
+}
+
+int64_t iexa_debug_codegen_source(const iexa_plan *p, char *buf, int64_t cap) {
+  if (!p || !p->plan.finalized) return -1;
+  std::string src = iexa::Specialiser::generate_source(p->plan);
+  if (buf && cap > 0) {
+    size_t n = std::min<size_t>((size_t)cap - 1, src.size());
+    std::memcpy(buf, src.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)src.size();
+}
+int32_t iexa_debug_codegen_compile(const iexa_plan *p, int64_t *cubin_bytes) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (!p->plan.finalized) return fail(IEXA_ERR_STATE, "plan not finalized");
+  std::string src = iexa::Specialiser::generate_source(p->plan), err;
+  std::vector<char> cubin;
+  if (!iexa::compile_cubin(src, cubin, err)) return fail(IEXA_ERR_NVRTC, err);
+  if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+  return IEXA_OK;
+  GUARD_END
+}
+
+int32_t iexa_launches_per_call(const iexa_plan *p, int32_t which) {
+  if (!p || !p->engine) return 0;
+  return p->engine->launches(which);
+}
+
+} // extern "C"

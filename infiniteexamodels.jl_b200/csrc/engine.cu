@@ -1,0 +1,681 @@
+// engine.cu — sm_100a device engine: plan upload, the AOT tape-interpreter kernels, structure
+// fill, reductions, and the launch logic of every NLPModels callback.
+//
+// Launch shape: ONE kernel launch per callback for the whole model (the reference stack
+// launches one KernelAbstractions kernel per generator per callback plus fill!/compress
+// kernels — SURVEY.md §2.2).  A work table maps blockIdx.x -> (generator, block of supports);
+// every thread owns one support point k and runs the generator's register program.
+// Outputs go straight to their precomputed slots  out[l + ostep*(k-k0) + c]  — every slot is
+// rewritten on every call, so no fill!(vals, 0) pass is needed.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+
+#include "codegen.hpp"
+#include "engine.hpp"
+#include "exec.hpp"
+
+namespace iexa {
+
+#define CK(call)                                                                  \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) {                                                      \
+      err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+      return IEXA_ERR_CUDA;                                                       \
+    }                                                                             \
+  } while (0)
+
+constexpr int BLOCK = 128;
+enum { SINK_DENSE = 0, SINK_SUM = 1, SINK_SCATTER = 2 };
+
+// ------------------------------------------------------------------------------------------
+// Tape interpreter.  Registers live in a per-thread local array (interleaved per thread by
+// the hardware => coalesced, L1-resident for typical programs).  All control flow is
+// warp-uniform: every thread of the block runs the same generator.
+// ------------------------------------------------------------------------------------------
+template <int NREG>
+__global__ void __launch_bounds__(BLOCK)
+interp_kernel(const GenD *__restrict__ gens, const WorkItem *__restrict__ work, int prog, int sink,
+              const double *__restrict__ x, const double *__restrict__ theta,
+              const double *__restrict__ y, double sigma, double *__restrict__ out,
+              double *__restrict__ partials) {
+  const WorkItem w = work[blockIdx.x];
+  const GenD &g = gens[w.gen];
+  long long k = g.k0 + (long long)w.blk * BLOCK + threadIdx.x;
+  const bool active = k < g.k1;
+  if (!active) k = g.k1 - 1; // keep loads in range; outputs are masked
+  const ProgD P = g.prog[prog];
+  const Instr *__restrict__ code = P.code;
+  const double *__restrict__ cp = P.cpool;
+  double r[NREG];
+  double acc = 0.0;
+  double W = sigma;
+  if (!g.is_obj) W = y ? y[g.row_local + (k - g.k0)] : 0.0;
+  const long long obase = g.out_local[prog] + (k - g.k0) * (long long)g.ostep[prog];
+
+  for (int pc = 0; pc < P.ncode; ++pc) {
+    const int4 raw = __ldg(reinterpret_cast<const int4 *>(code + pc));
+    const int op = raw.x, dst = raw.y, ia = raw.z, ib = raw.w;
+    switch (op) {
+      case D_FIELD: r[dst] = col_fp(g.fcol[ia], k); break;
+      case D_LOADX: r[dst] = __ldg(x + (idx_eval(g, ia, k) - 1)); break;
+      case D_LOADP: r[dst] = __ldg(theta + (idx_eval(g, ia, k) - 1)); break;
+      case D_W: r[dst] = W; break;
+      case D_SEL2: r[dst] = idx_eval(g, ia, k) == idx_eval(g, ib, k) ? 2.0 : 1.0; break;
+      case D_OUT: {
+        const double v = ia >= 0 ? r[ia] : cp[~ia];
+        if (sink == SINK_DENSE) {
+          if (active) out[obase + dst] = v;
+        } else if (sink == SINK_SUM) {
+          if (active) acc += v;
+        } else {
+          const int islot = g.jac_slot[dst];
+          if (g.idx[islot].nterms == 0) { // shared variable: warp-shuffle reduce, one atomic per warp
+            double s = active ? v : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(out + (g.idx[islot].base - 1), s);
+          } else if (active) {
+            atomicAdd(out + (idx_eval(g, islot, k) - 1), v);
+          }
+        }
+        break;
+      }
+      default: {
+        const double a = ia >= 0 ? r[ia] : cp[~ia];
+        const double b = ib >= 0 ? r[ib] : cp[~ib];
+        r[dst] = eval_arith(op, a, b);
+      }
+    }
+  }
+  if (sink == SINK_SUM) {
+    __shared__ double red[BLOCK / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < BLOCK / 32; ++i) s += red[i];
+      partials[blockIdx.x] = s;
+    }
+  }
+}
+
+// same interpreter with the register file in global scratch (programs with > 256 live values:
+// expanded measures, transform.jl:430-435).  scratch[reg * nthreads + tid].
+__global__ void __launch_bounds__(BLOCK)
+interp_kernel_big(const GenD *__restrict__ gens, const WorkItem *__restrict__ work, int prog, int sink,
+                  const double *__restrict__ x, const double *__restrict__ theta,
+                  const double *__restrict__ y, double sigma, double *__restrict__ out,
+                  double *__restrict__ partials, double *__restrict__ scratch) {
+  const WorkItem w = work[blockIdx.x];
+  const GenD &g = gens[w.gen];
+  long long k = g.k0 + (long long)w.blk * BLOCK + threadIdx.x;
+  const bool active = k < g.k1;
+  if (!active) k = g.k1 - 1;
+  const ProgD P = g.prog[prog];
+  const size_t nthr = (size_t)gridDim.x * BLOCK;
+  double *r = scratch + ((size_t)blockIdx.x * BLOCK + threadIdx.x);
+  double acc = 0.0;
+  double W = sigma;
+  if (!g.is_obj) W = y ? y[g.row_local + (k - g.k0)] : 0.0;
+  const long long obase = g.out_local[prog] + (k - g.k0) * (long long)g.ostep[prog];
+  for (int pc = 0; pc < P.ncode; ++pc) {
+    const Instr I = P.code[pc];
+    switch (I.op) {
+      case D_FIELD: r[I.dst * nthr] = col_fp(g.fcol[I.a], k); break;
+      case D_LOADX: r[I.dst * nthr] = x[idx_eval(g, I.a, k) - 1]; break;
+      case D_LOADP: r[I.dst * nthr] = theta[idx_eval(g, I.a, k) - 1]; break;
+      case D_W: r[I.dst * nthr] = W; break;
+      case D_SEL2: r[I.dst * nthr] = idx_eval(g, I.a, k) == idx_eval(g, I.b, k) ? 2.0 : 1.0; break;
+      case D_OUT: {
+        const double v = I.a >= 0 ? r[I.a * nthr] : P.cpool[~I.a];
+        if (sink == SINK_DENSE) { if (active) out[obase + I.dst] = v; }
+        else if (sink == SINK_SUM) { if (active) acc += v; }
+        else if (active) atomicAdd(out + (idx_eval(g, g.jac_slot[I.dst], k) - 1), v);
+        break;
+      }
+      default: {
+        const double a = I.a >= 0 ? r[I.a * nthr] : P.cpool[~I.a];
+        const double b = I.b >= 0 ? r[I.b * nthr] : P.cpool[~I.b];
+        r[I.dst * nthr] = eval_arith(I.op, a, b);
+      }
+    }
+  }
+  if (sink == SINK_SUM) {
+    __shared__ double red[BLOCK];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int i = 0; i < BLOCK; ++i) s += red[i];
+      partials[blockIdx.x] = s;
+    }
+  }
+}
+
+// deterministic second stage of the objective reduction (fixed summation tree)
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__restrict__ p, int n,
+                                                               double *__restrict__ out) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) s += p[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// rows/cols of the Jacobian (which=0) or lower-triangular Hessian (which=1); 1-based
+template <typename IT>
+__global__ void __launch_bounds__(BLOCK)
+structure_kernel(const GenD *__restrict__ gens, const WorkItem *__restrict__ work, int which,
+                 int local_rows, IT *__restrict__ rows, IT *__restrict__ cols) {
+  const WorkItem w = work[blockIdx.x];
+  const GenD &g = gens[w.gen];
+  const long long k = g.k0 + (long long)w.blk * BLOCK + threadIdx.x;
+  if (k >= g.k1) return;
+  if (which == 0) {
+    const int n = g.ostep[PROG_D1];
+    const long long base = g.out_local[PROG_D1] + (k - g.k0) * n;
+    const long long row = (local_rows ? g.row_local + (k - g.k0) : g.row_global + k) + 1;
+    for (int c = 0; c < n; ++c) {
+      rows[base + c] = (IT)row;
+      cols[base + c] = (IT)idx_eval(g, g.jac_slot[c], k);
+    }
+  } else {
+    const int n = g.ostep[PROG_D2];
+    const long long base = g.out_local[PROG_D2] + (k - g.k0) * n;
+    for (int c = 0; c < n; ++c) {
+      const long long i = idx_eval(g, g.hess_slot[2 * c], k), j = idx_eval(g, g.hess_slot[2 * c + 1], k);
+      rows[base + c] = (IT)(i >= j ? i : j);
+      cols[base + c] = (IT)(i >= j ? j : i);
+    }
+  }
+}
+
+// COO products used by jprod!/jtprod!/hprod! (matrix-free solvers only; not on the MadNLP/Ipopt path)
+__global__ void coo_prod_kernel(long long nnz, const int *__restrict__ rows, const int *__restrict__ cols,
+                                const double *__restrict__ vals, const double *__restrict__ v,
+                                double *__restrict__ out, int mode) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nnz;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int i = rows[p] - 1, j = cols[p] - 1;
+    const double a = vals[p];
+    if (mode == 0) atomicAdd(out + i, a * v[j]);          // Jv
+    else if (mode == 1) atomicAdd(out + j, a * v[i]);     // J'v
+    else {                                                 // Hv, lower-triangular storage
+      atomicAdd(out + i, a * v[j]);
+      if (i != j) atomicAdd(out + j, a * v[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n ? n : 8);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <typename T> T *as() { return (T *)p; }
+};
+
+struct HostArena {
+  std::vector<char> bytes;
+  size_t add(const void *data, size_t n, size_t align = 16) {
+    size_t off = (bytes.size() + align - 1) / align * align;
+    bytes.resize(off + n);
+    if (n) std::memcpy(bytes.data() + off, data, n);
+    return off;
+  }
+};
+
+class CudaEngine : public Engine {
+ public:
+  CudaEngine(Plan &plan, int device, uint32_t flags) : plan_(plan), device_(device), flags_(flags) {}
+  ~CudaEngine() override {
+    cudaSetDevice(device_);
+    for (auto &kv : registered_) cudaHostUnregister(kv.first);
+    if (pinned_f_) cudaFreeHost(pinned_f_);
+    spec_.reset();
+  }
+
+  int init(std::string &err) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      cudaGetLastError();
+      err = "no CUDA device available: the engine has no CPU fallback";
+      return IEXA_ERR_CUDA;
+    }
+    if (device_ < 0 || device_ >= ndev) { err = "bad device ordinal"; return IEXA_ERR_INVALID; }
+    CK(cudaSetDevice(device_));
+    CK(cudaFree(0));
+    int rc = upload(err);
+    if (rc) return rc;
+    CK(cudaMallocHost((void **)&pinned_f_, 64));
+    if (!(flags_ & IEXA_F_NO_SPECIALISE)) {
+      spec_.reset(new Specialiser());
+      std::string serr;
+      if (!spec_->build(plan_, gens_host_, device_, serr)) {
+        // specialisation is an optimisation of the SAME device program; the AOT interpreter
+        // kernels remain the (GPU) execution path.  Surface why.
+        spec_error_ = serr;
+        spec_.reset();
+      }
+    }
+    return IEXA_OK;
+  }
+
+  // ---- callbacks ---------------------------------------------------------------------------
+  int structure(int which, void *rows, void *cols, int idx_bytes, int memspace, void *stream,
+                std::string &err) override {
+    CK(cudaSetDevice(device_));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = which == 0 ? plan_.loc_nnzj : plan_.loc_nnzh;
+    if (idx_bytes != 4 && idx_bytes != 8) { err = "idx_bytes must be 4 or 8"; return IEXA_ERR_INVALID; }
+    void *dr = rows, *dc = cols;
+    if (memspace == IEXA_MEM_HOST) {
+      CK(stage_a_.ensure((size_t)n * idx_bytes));
+      CK(stage_b_.ensure((size_t)n * idx_bytes));
+      dr = stage_a_.p; dc = stage_b_.p;
+    }
+    const Table &T = table_[which == 0 ? CB_JAC : CB_HESS];
+    if (T.nblocks > 0) {
+      if (idx_bytes == 4)
+        structure_kernel<int32_t><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, which, 0, (int32_t *)dr, (int32_t *)dc);
+      else
+        structure_kernel<long long><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, which, 0, (long long *)dr, (long long *)dc);
+      CK(cudaGetLastError());
+    }
+    if (memspace == IEXA_MEM_HOST) {
+      CK(cudaMemcpyAsync(rows, dr, (size_t)n * idx_bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(cols, dc, (size_t)n * idx_bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    return IEXA_OK;
+  }
+
+  int obj_device(const double *x_dev, double *f_dev, void *stream, std::string &err) override {
+    CK(cudaSetDevice(device_));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Table &T = table_[CB_OBJ];
+    if (T.nblocks == 0) { CK(cudaMemsetAsync(f_dev, 0, 8, st)); return IEXA_OK; }
+    CK(partials_.ensure((size_t)T.nblocks * 8));
+    int rc = launch(CB_OBJ, PROG_VAL, SINK_SUM, x_dev, nullptr, 1.0, nullptr, st, err);
+    if (rc) return rc;
+    reduce_partials_kernel<<<1, 1024, 0, st>>>(partials_.as<double>(), T.nblocks, f_dev);
+    CK(cudaGetLastError());
+    return IEXA_OK;
+  }
+
+  int obj(const double *x, double *f_host, int memspace, void *stream, std::string &err) override {
+    CK(cudaSetDevice(device_));
+    cudaStream_t st = (cudaStream_t)stream;
+    const double *xd = nullptr;
+    int rc = in(x, plan_.nvar, memspace, stage_x_, st, xd, err);
+    if (rc) return rc;
+    CK(fdev_.ensure(8));
+    rc = obj_device(xd, fdev_.as<double>(), stream, err);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(pinned_f_, fdev_.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *f_host = *pinned_f_;
+    return IEXA_OK;
+  }
+
+  int grad(const double *x, double *g, int memspace, void *stream, std::string &err) override {
+    CK(cudaSetDevice(device_));
+    cudaStream_t st = (cudaStream_t)stream;
+    const double *xd = nullptr;
+    int rc = in(x, plan_.nvar, memspace, stage_x_, st, xd, err);
+    if (rc) return rc;
+    double *gd = g;
+    if (memspace == IEXA_MEM_HOST) { CK(stage_out_.ensure((size_t)plan_.nvar * 8)); gd = stage_out_.as<double>(); }
+    CK(cudaMemsetAsync(gd, 0, (size_t)plan_.nvar * 8, st));
+    rc = launch(CB_GRAD, PROG_D1, SINK_SCATTER, xd, nullptr, 1.0, gd, st, err);
+    if (rc) return rc;
+    return out(g, gd, plan_.nvar, memspace, st, err);
+  }
+
+  int cons(const double *x, double *c, int memspace, void *stream, std::string &err) override {
+    return dense_cb(CB_CONS, PROG_VAL, x, nullptr, 1.0, c, plan_.loc_ncon, memspace, stream, err);
+  }
+  int jac(const double *x, double *vals, int memspace, void *stream, std::string &err) override {
+    return dense_cb(CB_JAC, PROG_D1, x, nullptr, 1.0, vals, plan_.loc_nnzj, memspace, stream, err);
+  }
+  int hess(const double *x, const double *y, double sigma, double *vals, int memspace, void *stream,
+           std::string &err) override {
+    return dense_cb(CB_HESS, PROG_D2, x, y, sigma, vals, plan_.loc_nnzh, memspace, stream, err);
+  }
+
+  int jprod(const double *x, const double *v, double *Jv, int memspace, void *stream, std::string &err) override {
+    return prod(0, x, nullptr, v, 1.0, Jv, memspace, stream, err);
+  }
+  int jtprod(const double *x, const double *v, double *Jtv, int memspace, void *stream, std::string &err) override {
+    return prod(1, x, nullptr, v, 1.0, Jtv, memspace, stream, err);
+  }
+  int hprod(const double *x, const double *y, const double *v, double sigma, double *Hv, int memspace,
+            void *stream, std::string &err) override {
+    return prod(2, x, y, v, sigma, Hv, memspace, stream, err);
+  }
+
+  int set_par(int64_t off, int64_t n, const double *vals, std::string &err) override {
+    CK(cudaSetDevice(device_));
+    if (n > 0) CK(cudaMemcpy(theta_.as<double>() + off, vals, (size_t)n * 8, cudaMemcpyHostToDevice));
+    return IEXA_OK;
+  }
+
+  int launches(int cb) const override {
+    if (cb < 0 || cb >= CB__N) return 0;
+    int n = table_[cb].nblocks > 0 ? 1 : 0;
+    if (cb == CB_OBJ && n) n += 1;
+    return n;
+  }
+  int n_specialised() const override { return spec_ ? spec_->n_kernels() : 0; }
+  const std::string &spec_error() const { return spec_error_; }
+
+ private:
+  struct Table {
+    WorkItem *work = nullptr;
+    int nblocks = 0;
+    int max_nreg = 0;
+  };
+
+  Plan &plan_;
+  int device_;
+  uint32_t flags_;
+  DevBuf leaf_, desc_, gens_, theta_, work_;
+  DevBuf partials_, fdev_, stage_x_, stage_y_, stage_v_, stage_out_, stage_a_, stage_b_, scratch_;
+  DevBuf coo_rows_j_, coo_cols_j_, coo_rows_h_, coo_cols_h_, coo_vals_;
+  bool coo_j_ready_ = false, coo_h_ready_ = false;
+  GenD *gens_dev_ = nullptr;
+  std::vector<GenD> gens_host_; // device pointers inside; objs first then cons
+  Table table_[CB__N];
+  double *pinned_f_ = nullptr;
+  std::map<void *, size_t> registered_;
+  std::unique_ptr<Specialiser> spec_;
+  std::string spec_error_;
+
+  // ---- upload --------------------------------------------------------------------------------
+  int upload(std::string &err) {
+    Plan &P = plan_;
+    HostArena A; // leaf data
+    std::vector<size_t> col_off(P.columns.size(), (size_t)-1);
+    auto need_col = [&](int32_t c) {
+      if (col_off[c] != (size_t)-1) return;
+      const HostColumn &hc = P.columns[c];
+      if (hc.is_int) { if (!hc.iota) col_off[c] = A.add(hc.ivals.data(), hc.ivals.size() * 4); }
+      else col_off[c] = A.add(hc.fvals.data(), hc.fvals.size() * 8);
+    };
+    std::vector<Generator *> all;
+    for (auto &g : P.objs) all.push_back(&g);
+    for (auto &g : P.cons) all.push_back(&g);
+    struct Offs { size_t code[3], cpool[3], jac_slot, hess_slot; };
+    std::vector<Offs> offs(all.size());
+    for (size_t gi = 0; gi < all.size(); ++gi) {
+      Generator &g = *all[gi];
+      const Iterator &it = P.itrs[g.itr];
+      for (int32_t s : g.c.int_cols) need_col(it.int_cols[s].col);
+      for (int32_t s : g.c.fp_cols) need_col(it.fp_cols[s].col);
+      Program *pr[3] = {&g.c.val, &g.c.d1, &g.c.d2};
+      for (int p = 0; p < 3; ++p) {
+        offs[gi].code[p] = A.add(pr[p]->code.data(), pr[p]->code.size() * sizeof(Instr));
+        offs[gi].cpool[p] = A.add(pr[p]->cpool.data(), pr[p]->cpool.size() * 8);
+      }
+      offs[gi].jac_slot = A.add(g.c.jac_slot.data(), g.c.jac_slot.size() * 4);
+      std::vector<int32_t> hs;
+      for (auto &pr2 : g.c.hess_slot) { hs.push_back(pr2.first); hs.push_back(pr2.second); }
+      offs[gi].hess_slot = A.add(hs.data(), hs.size() * 4);
+    }
+    CK(leaf_.ensure(A.bytes.size() + 16));
+    CK(cudaMemcpy(leaf_.p, A.bytes.data(), A.bytes.size(), cudaMemcpyHostToDevice));
+    char *lb = (char *)leaf_.p;
+
+    HostArena D; // descriptors (ColD / IdxD arrays)
+    struct DOffs { size_t icol, fcol, idx; };
+    std::vector<DOffs> doffs(all.size());
+    for (size_t gi = 0; gi < all.size(); ++gi) {
+      Generator &g = *all[gi];
+      const Iterator &it = P.itrs[g.itr];
+      std::vector<ColD> ic, fc;
+      for (int32_t s : g.c.int_cols) {
+        const ColRef &r = it.int_cols[s];
+        ic.push_back(ColD{P.columns[r.col].iota ? nullptr : (const void *)(lb + col_off[r.col]), r.div, r.mod});
+      }
+      for (int32_t s : g.c.fp_cols) {
+        const ColRef &r = it.fp_cols[s];
+        fc.push_back(ColD{(const void *)(lb + col_off[r.col]), r.div, r.mod});
+      }
+      std::vector<IdxD> ix;
+      for (auto &e : g.c.uidx) {
+        IdxD d{};
+        d.base = e.base;
+        d.nterms = (int32_t)e.terms.size();
+        for (int t = 0; t < d.nterms; ++t) { d.slot[t] = e.terms[t].first; d.coef[t] = e.terms[t].second; }
+        ix.push_back(d);
+      }
+      doffs[gi].icol = D.add(ic.data(), ic.size() * sizeof(ColD));
+      doffs[gi].fcol = D.add(fc.data(), fc.size() * sizeof(ColD));
+      doffs[gi].idx = D.add(ix.data(), ix.size() * sizeof(IdxD));
+    }
+    CK(desc_.ensure(D.bytes.size() + 16));
+    CK(cudaMemcpy(desc_.p, D.bytes.data(), D.bytes.size(), cudaMemcpyHostToDevice));
+    char *db = (char *)desc_.p;
+
+    gens_host_.assign(all.size(), GenD{});
+    for (size_t gi = 0; gi < all.size(); ++gi) {
+      Generator &g = *all[gi];
+      GenD &d = gens_host_[gi];
+      d.K = g.K; d.k0 = g.k0; d.k1 = g.k1;
+      d.row_local = g.l0; d.row_global = g.o0;
+      d.icol = (const ColD *)(db + doffs[gi].icol);
+      d.fcol = (const ColD *)(db + doffs[gi].fcol);
+      d.idx = (const IdxD *)(db + doffs[gi].idx);
+      d.jac_slot = (const int32_t *)(lb + offs[gi].jac_slot);
+      d.hess_slot = (const int32_t *)(lb + offs[gi].hess_slot);
+      d.n_icol = (int32_t)g.c.int_cols.size();
+      d.n_fcol = (int32_t)g.c.fp_cols.size();
+      d.n_idx = (int32_t)g.c.uidx.size();
+      d.is_obj = g.is_obj ? 1 : 0;
+      Program *pr[3] = {&g.c.val, &g.c.d1, &g.c.d2};
+      for (int p = 0; p < 3; ++p) {
+        d.prog[p].code = (const Instr *)(lb + offs[gi].code[p]);
+        d.prog[p].cpool = (const double *)(lb + offs[gi].cpool[p]);
+        d.prog[p].ncode = (int32_t)pr[p]->code.size();
+        d.prog[p].nreg = pr[p]->nreg;
+        d.prog[p].nout = pr[p]->nout;
+        d.prog[p].uses_w = pr[p]->uses_w;
+      }
+      d.out_local[PROG_VAL] = g.is_obj ? 0 : g.l0;
+      d.out_local[PROG_D1] = g.is_obj ? 0 : g.l1;
+      d.out_local[PROG_D2] = g.l2;
+      d.out_global[PROG_VAL] = g.o0;
+      d.out_global[PROG_D1] = g.is_obj ? g.og : g.o1;
+      d.out_global[PROG_D2] = g.o2;
+      d.ostep[PROG_VAL] = 1;
+      d.ostep[PROG_D1] = g.c.o1step;
+      d.ostep[PROG_D2] = g.c.o2step;
+    }
+    CK(gens_.ensure(gens_host_.size() * sizeof(GenD) + 16));
+    CK(cudaMemcpy(gens_.p, gens_host_.data(), gens_host_.size() * sizeof(GenD), cudaMemcpyHostToDevice));
+    gens_dev_ = gens_.as<GenD>();
+
+    CK(theta_.ensure((size_t)(P.npar > 0 ? P.npar : 1) * 8));
+    if (P.npar > 0) CK(cudaMemcpy(theta_.p, P.theta.data(), (size_t)P.npar * 8, cudaMemcpyHostToDevice));
+
+    // work tables
+    const int nobj = (int)P.objs.size(), ncon = (int)P.cons.size();
+    std::vector<WorkItem> items;
+    size_t starts[CB__N + 1];
+    auto add_range = [&](int g0, int g1, int prog, bool skip_empty_out, int &max_nreg) {
+      for (int gi = g0; gi < g1; ++gi) {
+        const Generator &g = *all[gi];
+        const Program &pr = prog == PROG_VAL ? g.c.val : prog == PROG_D1 ? g.c.d1 : g.c.d2;
+        if (skip_empty_out && pr.nout == 0) continue;
+        max_nreg = std::max(max_nreg, pr.nreg);
+        int64_t n = g.k1 - g.k0;
+        for (int64_t b = 0; b * BLOCK < n; ++b) items.push_back(WorkItem{gi, (int32_t)b});
+      }
+    };
+    int mr[CB__N] = {0, 0, 0, 0, 0};
+    starts[CB_OBJ] = items.size();  add_range(0, nobj, PROG_VAL, false, mr[CB_OBJ]);
+    starts[CB_GRAD] = items.size(); add_range(0, nobj, PROG_D1, true, mr[CB_GRAD]);
+    starts[CB_CONS] = items.size(); add_range(nobj, nobj + ncon, PROG_VAL, false, mr[CB_CONS]);
+    starts[CB_JAC] = items.size();  add_range(nobj, nobj + ncon, PROG_D1, true, mr[CB_JAC]);
+    starts[CB_HESS] = items.size(); add_range(0, nobj + ncon, PROG_D2, true, mr[CB_HESS]);
+    starts[CB__N] = items.size();
+    CK(work_.ensure(items.size() * sizeof(WorkItem) + 16));
+    if (!items.empty()) CK(cudaMemcpy(work_.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    for (int cb = 0; cb < CB__N; ++cb) {
+      table_[cb].work = work_.as<WorkItem>() + starts[cb];
+      table_[cb].nblocks = (int)(starts[cb + 1] - starts[cb]);
+      table_[cb].max_nreg = mr[cb];
+    }
+    return IEXA_OK;
+  }
+
+  // ---- helpers -------------------------------------------------------------------------------
+  void try_register(const void *p, size_t bytes) {
+    // pin caller-owned host buffers once so the H2D/D2H copies run at PCIe speed; solvers reuse
+    // the same x / c / vals vectors on every iteration
+    if (!p || bytes < (1u << 16)) return;
+    auto it = registered_.find((void *)p);
+    if (it != registered_.end() && it->second >= bytes) return;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return;
+    cudaGetLastError();
+    if (it != registered_.end()) { cudaHostUnregister(it->first); registered_.erase(it); }
+    if (registered_.size() >= 32) return;
+    if (cudaHostRegister((void *)p, bytes, cudaHostRegisterDefault) == cudaSuccess) registered_[(void *)p] = bytes;
+    else cudaGetLastError();
+  }
+
+  int in(const double *src, int64_t n, int memspace, DevBuf &stage, cudaStream_t st, const double *&dev,
+         std::string &err) {
+    if (!src) { dev = nullptr; return IEXA_OK; }
+    if (memspace == IEXA_MEM_DEVICE) { dev = src; return IEXA_OK; }
+    CK(stage.ensure((size_t)n * 8));
+    try_register(src, (size_t)n * 8);
+    CK(cudaMemcpyAsync(stage.p, src, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    dev = stage.as<double>();
+    return IEXA_OK;
+  }
+  int out(double *dst, const double *dev, int64_t n, int memspace, cudaStream_t st, std::string &err) {
+    if (memspace == IEXA_MEM_DEVICE) return IEXA_OK;
+    try_register(dst, (size_t)n * 8);
+    CK(cudaMemcpyAsync(dst, dev, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return IEXA_OK;
+  }
+
+  int launch(int cb, int prog, int sink, const double *xd, const double *yd, double sigma, double *outd,
+             cudaStream_t st, std::string &err) {
+    const Table &T = table_[cb];
+    if (T.nblocks == 0) return IEXA_OK;
+    double *part = partials_.as<double>();
+    const double *th = theta_.as<double>();
+    if (spec_ && spec_->has(cb)) {
+      if (!spec_->launch(cb, T.nblocks, gens_dev_, T.work, xd, th, yd, sigma, outd, part, st, err)) return IEXA_ERR_CUDA;
+      return IEXA_OK;
+    }
+    if (T.max_nreg <= 32)
+      interp_kernel<32><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, sigma, outd, part);
+    else if (T.max_nreg <= 96)
+      interp_kernel<96><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, sigma, outd, part);
+    else if (T.max_nreg <= 256)
+      interp_kernel<256><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, sigma, outd, part);
+    else {
+      CK(scratch_.ensure((size_t)T.max_nreg * T.nblocks * BLOCK * 8));
+      interp_kernel_big<<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, sigma, outd, part,
+                                                     scratch_.as<double>());
+    }
+    CK(cudaGetLastError());
+    return IEXA_OK;
+  }
+
+  int dense_cb(int cb, int prog, const double *x, const double *y, double sigma, double *o, int64_t n,
+               int memspace, void *stream, std::string &err) {
+    CK(cudaSetDevice(device_));
+    cudaStream_t st = (cudaStream_t)stream;
+    const double *xd = nullptr, *yd = nullptr;
+    int rc = in(x, plan_.nvar, memspace, stage_x_, st, xd, err);
+    if (rc) return rc;
+    rc = in(y, plan_.loc_ncon, memspace, stage_y_, st, yd, err);
+    if (rc) return rc;
+    double *od = o;
+    if (memspace == IEXA_MEM_HOST) { CK(stage_out_.ensure((size_t)n * 8)); od = stage_out_.as<double>(); }
+    rc = launch(cb, prog, SINK_DENSE, xd, yd, sigma, od, st, err);
+    if (rc) return rc;
+    return out(o, od, n, memspace, st, err);
+  }
+
+  int ensure_coo(int which, cudaStream_t st, std::string &err) {
+    bool &ready = which == 0 ? coo_j_ready_ : coo_h_ready_;
+    if (ready) return IEXA_OK;
+    const int64_t n = which == 0 ? plan_.loc_nnzj : plan_.loc_nnzh;
+    DevBuf &r = which == 0 ? coo_rows_j_ : coo_rows_h_, &c = which == 0 ? coo_cols_j_ : coo_cols_h_;
+    CK(r.ensure((size_t)n * 4)); CK(c.ensure((size_t)n * 4));
+    const Table &T = table_[which == 0 ? CB_JAC : CB_HESS];
+    if (T.nblocks > 0) {
+      structure_kernel<int32_t><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, which, 1, r.as<int32_t>(), c.as<int32_t>());
+      CK(cudaGetLastError());
+    }
+    ready = true;
+    return IEXA_OK;
+  }
+
+  int prod(int mode, const double *x, const double *y, const double *v, double sigma, double *o, int memspace,
+           void *stream, std::string &err) {
+    CK(cudaSetDevice(device_));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int which = mode == 2 ? 1 : 0;
+    const int64_t nnz = which == 0 ? plan_.loc_nnzj : plan_.loc_nnzh;
+    const int64_t nv = mode == 1 ? plan_.loc_ncon : plan_.nvar;
+    const int64_t no = mode == 0 ? plan_.loc_ncon : plan_.nvar;
+    int rc = ensure_coo(which, st, err);
+    if (rc) return rc;
+    const double *xd = nullptr, *yd = nullptr, *vd = nullptr;
+    if ((rc = in(x, plan_.nvar, memspace, stage_x_, st, xd, err))) return rc;
+    if ((rc = in(y, plan_.loc_ncon, memspace, stage_y_, st, yd, err))) return rc;
+    if ((rc = in(v, nv, memspace, stage_v_, st, vd, err))) return rc;
+    CK(coo_vals_.ensure((size_t)nnz * 8));
+    rc = which == 0 ? launch(CB_JAC, PROG_D1, SINK_DENSE, xd, nullptr, 1.0, coo_vals_.as<double>(), st, err)
+                    : launch(CB_HESS, PROG_D2, SINK_DENSE, xd, yd, sigma, coo_vals_.as<double>(), st, err);
+    if (rc) return rc;
+    double *od = o;
+    if (memspace == IEXA_MEM_HOST) { CK(stage_out_.ensure((size_t)no * 8)); od = stage_out_.as<double>(); }
+    CK(cudaMemsetAsync(od, 0, (size_t)no * 8, st));
+    if (nnz > 0) {
+      const DevBuf &r = which == 0 ? coo_rows_j_ : coo_rows_h_, &c = which == 0 ? coo_cols_j_ : coo_cols_h_;
+      int nb = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 16);
+      coo_prod_kernel<<<nb, 256, 0, st>>>(nnz, (const int *)r.p, (const int *)c.p, coo_vals_.as<double>(), vd, od, mode);
+      CK(cudaGetLastError());
+    }
+    return out(o, od, no, memspace, st, err);
+  }
+};
+
+Engine *make_cuda_engine(Plan &plan, int device, uint32_t flags, std::string &err) {
+  std::unique_ptr<CudaEngine> e(new CudaEngine(plan, device, flags));
+  if (e->init(err) != IEXA_OK) return nullptr;
+  return e.release();
+}
+
+} // namespace iexa

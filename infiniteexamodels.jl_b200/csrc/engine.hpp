@@ -1,0 +1,37 @@
+// engine.hpp — interface between the C ABI (api.cpp) and the CUDA engine (engine.cu).
+#pragma once
+#include <string>
+
+#include "plan.hpp"
+
+namespace iexa {
+
+enum Callback { CB_OBJ = 0, CB_GRAD = 1, CB_CONS = 2, CB_JAC = 3, CB_HESS = 4, CB__N = 5 };
+
+struct Engine {
+  virtual ~Engine() {}
+  // all return IEXA_* status; err receives a message on failure
+  virtual int structure(int which /*0 jac, 1 hess*/, void *rows, void *cols, int idx_bytes,
+                        int memspace, void *stream, std::string &err) = 0;
+  virtual int obj(const double *x, double *f_host, int memspace, void *stream, std::string &err) = 0;
+  virtual int obj_device(const double *x_dev, double *f_dev, void *stream, std::string &err) = 0;
+  virtual int grad(const double *x, double *g, int memspace, void *stream, std::string &err) = 0;
+  virtual int cons(const double *x, double *c, int memspace, void *stream, std::string &err) = 0;
+  virtual int jac(const double *x, double *vals, int memspace, void *stream, std::string &err) = 0;
+  virtual int hess(const double *x, const double *y, double sigma, double *vals, int memspace,
+                   void *stream, std::string &err) = 0;
+  virtual int jprod(const double *x, const double *v, double *Jv, int memspace, void *stream,
+                    std::string &err) = 0;
+  virtual int jtprod(const double *x, const double *v, double *Jtv, int memspace, void *stream,
+                     std::string &err) = 0;
+  virtual int hprod(const double *x, const double *y, const double *v, double sigma, double *Hv,
+                    int memspace, void *stream, std::string &err) = 0;
+  virtual int set_par(int64_t off, int64_t n, const double *vals, std::string &err) = 0;
+  virtual int launches(int cb) const = 0;
+  virtual int n_specialised() const = 0;
+};
+
+// engine.cu; returns nullptr and fills err when no CUDA device / kernel image is usable
+Engine *make_cuda_engine(Plan &plan, int device, uint32_t flags, std::string &err);
+
+} // namespace iexa

@@ -1,0 +1,247 @@
+"""``ExaModel`` — the NLPModel the solvers consume — and the NLPModels callback API.
+
+Mirrors what the reference hands to ``MadNLPSolver(model; ...)`` / ``IpoptSolver(model)``
+(ext/InfiniteExaModelsMadNLP.jl:49, ext/InfiniteExaModelsIpopt.jl:48): an object with ``meta``
+(nvar, ncon, nnzj, nnzh, x0, lvar, uvar, y0, lcon, ucon, minimize), a mutable parameter vector
+``θ`` (infiniteopt_backend.jl:479,522,546) and the callbacks ``obj, grad!, cons!,
+jac_structure!, jac_coord!, hess_structure!, hess_coord!, jprod!, jtprod!, hprod!``.
+Python has no ``!``; the in-place callbacks carry a trailing underscore.
+
+Every callback is a single call into the C ABI (libiexa_b200.so).  Buffers may be numpy arrays
+(host memory: the Ipopt-style path, copies happen inside the call) or CUDA torch tensors (device
+memory: the MadNLP-style path, asynchronous on the current torch stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import lib as _lib
+from .core import ExaCore, Itr
+
+
+@dataclass
+class NLPModelMeta:
+    nvar: int
+    ncon: int
+    nnzj: int
+    nnzh: int
+    x0: np.ndarray
+    lvar: np.ndarray
+    uvar: np.ndarray
+    y0: np.ndarray
+    lcon: np.ndarray
+    ucon: np.ndarray
+    minimize: bool
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+class ExaModel:
+    """``ExaModels.ExaModel(core)`` (infiniteopt_backend.jl:156) backed by the CUDA engine."""
+
+    def __init__(self, core: ExaCore, device: int = 0, rank: int = 0, world: int = 1,
+                 flags: int = _lib.IEXA_F_DEFAULT, library=None):
+        self.L = L = library or _lib.load()
+        self.core = core
+        h = C.c_void_p()
+        _lib.check(L, L.iexa_plan_create(C.byref(h), int(core.minimize)))
+        self.h = h
+        self._keep = []
+        off = C.c_int64()
+        x0, lv, uv = (np.ascontiguousarray(v, dtype=np.float64) for v in (core.x0_vec, core.lvar_vec, core.uvar_vec))
+        if core.nvar:
+            _lib.check(L, L.iexa_add_var(h, core.nvar, x0.ctypes.data, lv.ctypes.data, uv.ctypes.data, C.byref(off)))
+        th = np.ascontiguousarray(core.theta_vec, dtype=np.float64)
+        if core.npar:
+            _lib.check(L, L.iexa_add_par(h, core.npar, th.ctypes.data, C.byref(off)))
+        itr_ids = {}
+
+        def itr_id(it: Itr) -> int:
+            if id(it) in itr_ids:
+                return itr_ids[id(it)]
+            out = C.c_int32()
+            if it.factors is None:
+                if it.K == 1 and not it.ints and not it.fps:
+                    itr_ids[id(it)] = 0  # the empty iterator [(;)]
+                    return 0
+                ic = [it.ints[n] for n in it.ints]
+                fc = [it.fps[n] for n in it.fps]
+                icp = (C.c_void_p * max(len(ic), 1))(*[c.ctypes.data for c in ic])
+                fcp = (C.c_void_p * max(len(fc), 1))(*[c.ctypes.data for c in fc])
+                _lib.check(L, L.iexa_itr_base(h, it.K, len(ic), icp, len(fc), fcp, C.byref(out)))
+            else:
+                ids = (C.c_int32 * len(it.factors))(*[itr_id(f) for f in it.factors])
+                _lib.check(L, L.iexa_itr_product(h, len(it.factors), ids, C.byref(out)))
+            itr_ids[id(it)] = out.value
+            return out.value
+
+        for g in core.gens:
+            nodes = np.ascontiguousarray(g.tape.nodes)
+            index = np.ascontiguousarray(g.tape.index)
+            iid = itr_id(g.itr)
+            ip = index.ctypes.data if len(index) else None
+            if g.is_obj:
+                _lib.check(L, L.iexa_add_obj(h, nodes.ctypes.data, len(nodes), ip, len(index), iid))
+            else:
+                _lib.check(L, L.iexa_add_con(h, nodes.ctypes.data, len(nodes), ip, len(index), iid,
+                                             g.lcon, g.ucon, C.byref(off)))
+        _lib.check(L, L.iexa_finalize(h, device, rank, world, flags))
+        m = _lib.Meta()
+        _lib.check(L, L.iexa_get_meta(h, C.byref(m)))
+        self.cmeta = m
+        self.device, self.rank, self.world = device, rank, world
+
+        def vec(which, n):
+            a = np.zeros(n)
+            if n:
+                _lib.check(L, L.iexa_get_vector(h, which, a.ctypes.data))
+            return a
+
+        self.meta = NLPModelMeta(m.nvar, m.ncon, m.nnzj, m.nnzh, vec(0, m.nvar), vec(1, m.nvar), vec(2, m.nvar),
+                                 vec(5, m.ncon), vec(3, m.ncon), vec(4, m.ncon), bool(m.minimize))
+        # local (this rank's) sizes; equal to the global ones when world == 1
+        self.loc_ncon, self.loc_nnzj, self.loc_nnzh = m.loc_ncon, m.loc_nnzj, m.loc_nnzh
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.iexa_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- θ (model.θ, set_parameter!) -----------------------------------------------------------
+    @property
+    def θ(self) -> np.ndarray:
+        n = self.cmeta.npar
+        a = np.zeros(n)
+        if n:
+            _lib.check(self.L, self.L.iexa_get_par(self.h, 0, n, a.ctypes.data))
+        return a
+
+    theta = θ
+
+    def set_parameter(self, par, vals) -> None:
+        """``ExaModels.set_parameter!(core, param, vals)`` — infiniteopt_backend.jl:522,546."""
+        v = np.ascontiguousarray(np.asarray(vals, dtype=np.float64).reshape(-1, order="F"))
+        assert v.size == par.length, "parameter block length mismatch"
+        _lib.check(self.L, self.L.iexa_set_par(self.h, par.offset, v.size, v.ctypes.data))
+
+    # ---- buffers ---------------------------------------------------------------------------------
+    def _buf(self, a, n=None, write=False):
+        if a is None:
+            return None, None, None
+        if _is_torch(a):
+            import torch
+            assert a.dtype in (torch.float64, torch.int32, torch.int64) and a.is_contiguous()
+            if n is not None:
+                assert a.numel() >= n, f"buffer too small: {a.numel()} < {n}"
+            if a.is_cuda:
+                return a.data_ptr(), _lib.IEXA_MEM_DEVICE, torch.cuda.current_stream(a.device).cuda_stream
+            return a.data_ptr(), _lib.IEXA_MEM_HOST, None
+        assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"]
+        if n is not None:
+            assert a.size >= n, f"buffer too small: {a.size} < {n}"
+        return a.ctypes.data, _lib.IEXA_MEM_HOST, None
+
+    def _pair(self, *bufs):
+        ms = {b[1] for b in bufs if b[0] is not None}
+        assert len(ms) == 1, "all buffers of one call must live in the same memory space"
+        st = next((b[2] for b in bufs if b[2] is not None), None)
+        return ms.pop(), st
+
+
+# ---- NLPModels API ------------------------------------------------------------------------------------
+def get_x0(m: ExaModel): return m.meta.x0
+def get_y0(m: ExaModel): return m.meta.y0
+
+
+def obj(m: ExaModel, x) -> float:
+    bx = m._buf(x, m.meta.nvar)
+    f = C.c_double()
+    _lib.check(m.L, m.L.iexa_obj(m.h, bx[0], C.byref(f), bx[1], bx[2]))
+    return f.value
+
+
+def grad_(m: ExaModel, x, g):
+    bx, bg = m._buf(x, m.meta.nvar), m._buf(g, m.meta.nvar)
+    ms, st = m._pair(bx, bg)
+    _lib.check(m.L, m.L.iexa_grad(m.h, bx[0], bg[0], ms, st))
+    return g
+
+
+def cons_(m: ExaModel, x, c):
+    bx, bc = m._buf(x, m.meta.nvar), m._buf(c, m.loc_ncon)
+    ms, st = m._pair(bx, bc)
+    _lib.check(m.L, m.L.iexa_cons(m.h, bx[0], bc[0], ms, st))
+    return c
+
+
+def _idx_bytes(a):
+    if _is_torch(a):
+        import torch
+        return 4 if a.dtype == torch.int32 else 8
+    return a.dtype.itemsize
+
+
+def jac_structure_(m: ExaModel, rows, cols):
+    br, bc = m._buf(rows, m.loc_nnzj), m._buf(cols, m.loc_nnzj)
+    ms, st = m._pair(br, bc)
+    _lib.check(m.L, m.L.iexa_jac_structure(m.h, br[0], bc[0], _idx_bytes(rows), ms, st))
+    return rows, cols
+
+
+def hess_structure_(m: ExaModel, rows, cols):
+    br, bc = m._buf(rows, m.loc_nnzh), m._buf(cols, m.loc_nnzh)
+    ms, st = m._pair(br, bc)
+    _lib.check(m.L, m.L.iexa_hess_structure(m.h, br[0], bc[0], _idx_bytes(rows), ms, st))
+    return rows, cols
+
+
+def jac_coord_(m: ExaModel, x, vals):
+    bx, bv = m._buf(x, m.meta.nvar), m._buf(vals, m.loc_nnzj)
+    ms, st = m._pair(bx, bv)
+    _lib.check(m.L, m.L.iexa_jac_coord(m.h, bx[0], bv[0], ms, st))
+    return vals
+
+
+def hess_coord_(m: ExaModel, x, y, vals, obj_weight: float = 1.0):
+    bx, by, bv = m._buf(x, m.meta.nvar), m._buf(y, m.loc_ncon), m._buf(vals, m.loc_nnzh)
+    ms, st = m._pair(bx, by, bv)
+    _lib.check(m.L, m.L.iexa_hess_coord(m.h, bx[0], by[0], float(obj_weight), bv[0], ms, st))
+    return vals
+
+
+def jprod_(m: ExaModel, x, v, Jv):
+    bx, bv, bo = m._buf(x, m.meta.nvar), m._buf(v, m.meta.nvar), m._buf(Jv, m.loc_ncon)
+    ms, st = m._pair(bx, bv, bo)
+    _lib.check(m.L, m.L.iexa_jprod(m.h, bx[0], bv[0], bo[0], ms, st))
+    return Jv
+
+
+def jtprod_(m: ExaModel, x, v, Jtv):
+    bx, bv, bo = m._buf(x, m.meta.nvar), m._buf(v, m.loc_ncon), m._buf(Jtv, m.meta.nvar)
+    ms, st = m._pair(bx, bv, bo)
+    _lib.check(m.L, m.L.iexa_jtprod(m.h, bx[0], bv[0], bo[0], ms, st))
+    return Jtv
+
+
+def hprod_(m: ExaModel, x, y, v, Hv, obj_weight: float = 1.0):
+    bx, by, bv, bo = m._buf(x, m.meta.nvar), m._buf(y, m.loc_ncon), m._buf(v, m.meta.nvar), m._buf(Hv, m.meta.nvar)
+    ms, st = m._pair(bx, by, bv, bo)
+    _lib.check(m.L, m.L.iexa_hprod(m.h, bx[0], by[0], bv[0], float(obj_weight), bo[0], ms, st))
+    return Hv
+
+
+def algorithmic_bytes(m: ExaModel, which: int) -> int:
+    return int(m.L.iexa_algorithmic_bytes(m.h, which))
+
+
+def launches_per_call(m: ExaModel, which: int) -> int:
+    return int(m.L.iexa_launches_per_call(m.h, which))

@@ -1,0 +1,108 @@
+// hostcheck.cpp — TEST-ONLY host executor of the engine's register programs.
+//
+// Built (g++, no CUDA runtime) into tests/hostcheck/libiexa_hostcheck.so together with api.cpp
+// and codegen.cpp so that `pytest -m "not gpu"` can validate the plan compiler (symbolic
+// sparsity, AD programs, layout, byte accounting, NVRTC source generation) on a machine without
+// a GPU.  It is NOT part of libiexa_b200.so and is not a fallback: in this library
+// make_cuda_engine() always fails, exactly like the product on a GPU-less machine.
+#include <cmath>
+#include <cstring>
+
+#include "../../include/iexa.h"
+#include "../../infiniteexamodels.jl_b200/csrc/api_internal.hpp"
+#include "../../infiniteexamodels.jl_b200/csrc/exec.hpp"
+
+namespace iexa {
+Engine *make_cuda_engine(Plan &, int, uint32_t, std::string &err) {
+  err = "hostcheck build: no CUDA engine";
+  return nullptr;
+}
+
+static void run_program(const Plan &P, const Generator &g, const Program &pr, int64_t k, const double *x,
+                        double W, std::vector<double> &r, double *out) {
+  r.resize(pr.nreg > 0 ? pr.nreg : 1);
+  for (const Instr &I : pr.code) {
+    switch (I.op) {
+      case D_FIELD: r[I.dst] = P.fp_col_value(g, I.a, k); break;
+      case D_LOADX: r[I.dst] = x[P.index_value(g, I.a, k) - 1]; break;
+      case D_LOADP: r[I.dst] = P.theta[P.index_value(g, I.a, k) - 1]; break;
+      case D_W: r[I.dst] = W; break;
+      case D_SEL2: r[I.dst] = P.index_value(g, I.a, k) == P.index_value(g, I.b, k) ? 2.0 : 1.0; break;
+      case D_OUT: out[I.dst] = I.a >= 0 ? r[I.a] : pr.cpool[~I.a]; break;
+      default: {
+        double a = I.a >= 0 ? r[I.a] : pr.cpool[~I.a];
+        double b = I.b >= 0 ? r[I.b] : pr.cpool[~I.b];
+        r[I.dst] = eval_arith(I.op, a, b);
+      }
+    }
+  }
+}
+} // namespace iexa
+
+using namespace iexa;
+
+extern "C" {
+
+// which: 0 obj (out[0]), 1 grad (dense nvar), 2 cons, 3 jac_coord, 4 hess_coord  — GLOBAL layout
+int32_t hostcheck_eval(iexa_plan *p, int32_t which, const double *x, const double *y, double sigma, double *out) {
+  if (!p || !p->plan.finalized) return IEXA_ERR_STATE;
+  const Plan &P = p->plan;
+  std::vector<double> r, tmp;
+  if (which == 0) out[0] = 0.0;
+  if (which == 1) std::memset(out, 0, sizeof(double) * (size_t)P.nvar);
+  auto each = [&](const Generator &g) {
+    const Program &pr = (which == 0 || which == 2) ? g.c.val : (which == 1 || which == 3) ? g.c.d1 : g.c.d2;
+    tmp.assign(pr.nout > 0 ? pr.nout : 1, 0.0);
+    for (int64_t k = 0; k < g.K; ++k) {
+      double W = g.is_obj ? sigma : (y ? y[g.o0 + k] : 0.0);
+      run_program(P, g, pr, k, x, W, r, tmp.data());
+      switch (which) {
+        case 0: out[0] += tmp[0]; break;
+        case 1: for (int c = 0; c < g.c.o1step; ++c) out[P.index_value(g, g.c.jac_slot[c], k) - 1] += tmp[c]; break;
+        case 2: out[g.o0 + k] = tmp[0]; break;
+        case 3: for (int c = 0; c < g.c.o1step; ++c) out[g.o1 + k * g.c.o1step + c] = tmp[c]; break;
+        case 4: for (int c = 0; c < g.c.o2step; ++c) out[g.o2 + k * g.c.o2step + c] = tmp[c]; break;
+      }
+    }
+  };
+  if (which == 0 || which == 1 || which == 4) for (auto &g : P.objs) each(g);
+  if (which >= 2) for (auto &g : P.cons) each(g);
+  return IEXA_OK;
+}
+
+// which: 0 jac, 1 hess; 1-based int64 rows/cols, GLOBAL layout
+int32_t hostcheck_structure(iexa_plan *p, int32_t which, int64_t *rows, int64_t *cols) {
+  if (!p || !p->plan.finalized) return IEXA_ERR_STATE;
+  const Plan &P = p->plan;
+  auto each = [&](const Generator &g) {
+    for (int64_t k = 0; k < g.K; ++k) {
+      if (which == 0) {
+        for (int c = 0; c < g.c.o1step; ++c) {
+          rows[g.o1 + k * g.c.o1step + c] = g.o0 + k + 1;
+          cols[g.o1 + k * g.c.o1step + c] = P.index_value(g, g.c.jac_slot[c], k);
+        }
+      } else {
+        for (int c = 0; c < g.c.o2step; ++c) {
+          int64_t i = P.index_value(g, g.c.hess_slot[c].first, k), j = P.index_value(g, g.c.hess_slot[c].second, k);
+          rows[g.o2 + k * g.c.o2step + c] = i >= j ? i : j;
+          cols[g.o2 + k * g.c.o2step + c] = i >= j ? j : i;
+        }
+      }
+    }
+  };
+  if (which == 1) for (auto &g : P.objs) each(g);
+  for (auto &g : P.cons) each(g);
+  return IEXA_OK;
+}
+
+// per-generator compile statistics: out[8] = {o1step, o2step, n_occ1, n_occ2, nreg_val, nreg_d1, nreg_d2, ncode_d2}
+int32_t hostcheck_gen_stats(iexa_plan *p, int32_t is_obj, int32_t i, int64_t *out) {
+  if (!p) return IEXA_ERR_INVALID;
+  const auto &v = is_obj ? p->plan.objs : p->plan.cons;
+  if (i < 0 || i >= (int)v.size()) return IEXA_ERR_INVALID;
+  const Generator &g = v[i];
+  out[0] = g.c.o1step; out[1] = g.c.o2step; out[2] = g.c.n_occ1; out[3] = g.c.n_occ2;
+  out[4] = g.c.val.nreg; out[5] = g.c.d1.nreg; out[6] = g.c.d2.nreg; out[7] = (int64_t)g.c.d2.code.size();
+  return IEXA_OK;
+}
+}
