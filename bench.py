@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — cons! + jac_coord! + hess_coord! throughput on the BASELINE.json workload.
+
+One "step" = one eval = one call of each of the three callbacks at the same (x, y) on the
+ESCAPE34/quadrotor.jl transcription (OrthogonalCollocation(3), piecewise-constant controls) with
+10^6 public time supports (BASELINE.json configs[2]; the configuration the north-star evals/s and
+roofline target is quoted on; it fits one B200).  With --gpus N the SAME model is sharded by
+contiguous support blocks over N ranks (strong scaling, no data-path collective: every rank owns
+its rows / Jacobian slots / Hessian slots).
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference's
+evaluator (oracle/, all host threads) on a bounded sample of the same workload — ExaModels.jl
+itself cannot be installed here (no Julia, no network).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "ESCAPE34/quadrotor.jl OC(3), 10^6 time supports: cons!+jac_coord!+hess_coord!"
+METRIC = "cons+jac+hess evals/s"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--supports", type=int, default=1_000_000, help="public time supports (default: the named size)")
+    ap.add_argument("--cpu-sample", type=int, default=20_000, help="supports of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--interp", action="store_true", help="AOT tape-interpreter kernels only (no NVRTC)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [s.strip() for s in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_eval_rate(sample_supports: int, full_supports: int, threads: int, reps: int = 2):
+    """evals/s of the oracle (CPU restatement of the reference evaluator) on a bounded sample,
+    scaled linearly to the full support count."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    import iexa_b200 as ex  # noqa: F401  (models only; the oracle does the arithmetic)
+    from iexa_b200 import models
+    from oracle.oracle import OracleModel
+    core = models.quadrotor(sample_supports, "oc")
+    om = OracleModel(core)
+    rng = np.random.default_rng(0)
+    x = core.x0_vec + 0.1 * rng.uniform(-1, 1, core.nvar)
+    y = rng.uniform(-1, 1, core.ncon)
+    om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)  # warm-up
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)
+        ts.append(time.perf_counter() - t0)
+    t = min(ts)
+    scale = (2 * full_supports - 1) / (2 * sample_supports - 1)
+    return 1.0 / (t * scale), t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # each "step" is one eval of the bounded sample; K steps after W warm-ups
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    from iexa_b200 import models
+    from oracle.oracle import OracleModel
+    ns = args.cpu_sample
+    core = models.quadrotor(ns, "oc")
+    om = OracleModel(core)
+    rng = np.random.default_rng(0)
+    x = core.x0_vec + 0.1 * rng.uniform(-1, 1, core.nvar)
+    y = rng.uniform(-1, 1, core.ncon)
+    for _ in range(args.warmup):
+        om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    scale = (2 * args.supports - 1) / (2 * ns - 1)
+    v = 1.0 / (dt * scale)
+    sample = (f"oracle (C restatement of ExaModels' per-support recursive AD, OpenMP over supports) on "
+              f"{ns} of {args.supports} public supports, time scaled linearly by {scale:.1f}")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "supports": args.supports},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "ExaModels.jl (the reference's evaluator) is not installable offline: no Julia, no network",
+    }))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import iexa_b200 as ex
+    from iexa_b200 import models
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    core = models.quadrotor(args.supports, "oc")
+    flags = ex.lib.IEXA_F_NO_SPECIALISE if args.interp else ex.lib.IEXA_F_DEFAULT
+    m = ex.ExaModel(core, device=local_rank, rank=rank, world=world, flags=flags)
+    rng = np.random.default_rng(0)
+    x_h = core.x0_vec + 0.1 * rng.uniform(-1, 1, core.nvar)
+    y_full = rng.uniform(-1, 1, core.ncon)
+    # this rank's multipliers, in its local row layout
+    segs = (ex.lib.Segment * 4096)()
+    nseg = m.L.iexa_segments(m.h, 0, segs, 4096)
+    y_h = np.zeros(max(m.loc_ncon, 1))
+    for s in segs[:nseg]:
+        y_h[s.local_start:s.local_start + s.length] = y_full[s.global_start:s.global_start + s.length]
+    x = torch.from_numpy(x_h).to(dev)
+    y = torch.from_numpy(y_h).to(dev)
+    c = torch.empty(max(m.loc_ncon, 1), dtype=torch.float64, device=dev)
+    jv = torch.empty(max(m.loc_nnzj, 1), dtype=torch.float64, device=dev)
+    hv = torch.empty(max(m.loc_nnzh, 1), dtype=torch.float64, device=dev)
+
+    def step():
+        ex.cons_(m, x, c)
+        ex.jac_coord_(m, x, jv)
+        ex.hess_coord_(m, x, y, hv, 1.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for i in range(args.steps):  # per-callback events on the launching (current torch) stream
+        ev[i][0].record(); ex.cons_(m, x, c)
+        ev[i][1].record(); ex.jac_coord_(m, x, jv)
+        ev[i][2].record(); ex.hess_coord_(m, x, y, hv, 1.0)
+        ev[i][3].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0][0].elapsed_time(ev[-1][3])
+    per = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in ev]).mean(axis=0)  # ms
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tmax.item()) / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- e2e: the same step through the C ABI with HOST buffers (pinned), copies inside the call
+    e2e = None
+    if not args.no_e2e:
+        xp = torch.from_numpy(x_h).pin_memory()
+        yp = torch.from_numpy(y_h).pin_memory()
+        cp = torch.empty(max(m.loc_ncon, 1), dtype=torch.float64).pin_memory()
+        jp = torch.empty(max(m.loc_nnzj, 1), dtype=torch.float64).pin_memory()
+        hp = torch.empty(max(m.loc_nnzh, 1), dtype=torch.float64).pin_memory()
+
+        def step_host():
+            ex.cons_(m, xp, cp); ex.jac_coord_(m, xp, jp); ex.hess_coord_(m, xp, yp, hp, 1.0)
+
+        n_e2e = max(2, min(args.steps, 5))
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            step_host()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = 8 * (3 * m.meta.nvar + m.loc_ncon)
+        d2h = 8 * (m.loc_ncon + m.loc_nnzj + m.loc_nnzh)
+        e2e = {"value": 1.0 / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": n_e2e, "note": "host (pinned) buffers through iexa_cons/iexa_jac_coord/iexa_hess_coord; PCIe copies inside the timed region"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (largest share of the step), measured live above
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    names = ["cons", "jac_coord", "hess_coord"]
+    which = [ex.lib.CB_CONS, ex.lib.CB_JAC, ex.lib.CB_HESS]
+    bytes_cb = [ex.algorithmic_bytes(m, w) for w in which]
+    dom = int(np.argmax(per))
+    achieved = bytes_cb[dom] / (per[dom] * 1e-3) / 1e9
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf)).get(names[dom])
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": f"iexa_cb_{names[dom].split('_')[0]}", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_launch": int(bytes_cb[dom]), "avg_launch_ms": float(per[dom]),
+                "per_callback": {n: {"ms": float(t), "GB/s": b / (t * 1e-3) / 1e9, "frac": b / (t * 1e-3) / 1e9 / peak,
+                                     "bytes": int(b)} for n, t, b in zip(names, per, bytes_cb)},
+                "all_three": {"bytes": int(sum(bytes_cb)), "GB/s": sum(bytes_cb) / (per.sum() * 1e-3) / 1e9,
+                              "frac": sum(bytes_cb) / (per.sum() * 1e-3) / 1e9 / peak}}
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        v1, t1 = cpu_eval_rate(args.cpu_sample, args.supports, 1)
+        cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"oracle (C restatement of ExaModels' sequential per-support AD) on {args.cpu_sample} of "
+                         f"{args.supports} public supports ({t1:.2f} s/eval measured), scaled linearly; ExaModels' "
+                         f"CPU backend is sequential (Julia threads = 1)"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "supports": args.supports, "nvar": int(m.meta.nvar), "ncon": int(m.meta.ncon),
+                   "nnzj": int(m.meta.nnzj), "nnzh": int(m.meta.nnzh), "sharding": f"contiguous support blocks x{world}",
+                   "l2": "inputs larger than L2 (x = %.0f MB, outputs %.1f GB per eval)" % (m.meta.nvar * 8 / 1e6, (m.loc_nnzj + m.loc_nnzh + m.loc_ncon) * 8 / 1e9),
+                   "kernels": "interpreter" if args.interp else f"nvrtc-specialised ({m.cmeta.n_kernels_specialised})"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(args.steps * sum(ex.launches_per_call(m, w) for w in which)),
+        "clocks": clocks, "wall_s_timed_region": t_wall,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

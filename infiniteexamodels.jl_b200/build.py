@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {s}:\n{out}")
         if verbose and out.strip():
             print(out)
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB, *objs, "-ldl", "-Xcompiler", "-fPIC"])
+    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ldl", "-Xcompiler", "-fPIC"])
     return LIB
 
 
