@@ -11,10 +11,6 @@
 #include "api_internal.hpp"
 #include "codegen.hpp"
 
-namespace iexa {
-bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string &err);
-} // namespace iexa
-
 namespace iexa { thread_local std::string g_last_error; }
 #define g_err iexa::g_last_error
 static int32_t fail(int32_t code, const std::string &msg) { g_err = msg; return code; }

@@ -2,10 +2,10 @@
 //
 // The reference stack specialises its evaluation code per expression-tree TYPE through Julia's
 // JIT (ExaModels builds a distinct node type per tree).  The engine's
-// equivalent: the register programs of all generators of one callback are printed into ONE
-// straight-line CUDA kernel (switch over the generator id of the block), compiled for sm_100a
-// with NVRTC at iexa_finalize, and launched exactly like the AOT interpreter kernel (same work
-// table, same descriptors).  Registers replace the interpreter's local-memory register file.
+// equivalent: the fused register programs (plan.hpp: Group) of one callback are printed into ONE
+// straight-line CUDA kernel (switch over the group id of the block), compiled for sm_100a with
+// NVRTC at iexa_finalize and launched once per callback.  Registers replace the interpreter's
+// local-memory register file; shared memory turns the AoS COO layout into coalesced stores.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -17,23 +17,41 @@
 
 namespace iexa {
 
+// entries of the generated kernels' __constant__ table (values are resolved per rank at load)
+enum { CI_K0 = 0, CI_K1, CI_IDX_BASE, CI_ICOL_PTR, CI_FCOL_PTR, CI_MEM_ROWLOC, CI_MEM_OUT };
+struct CiEntry {
+  int kind, group, a, b;
+};
+
+struct GeneratedSource {
+  std::string text;
+  std::vector<CiEntry> ci;
+  std::vector<int> groups_of[5]; // groups with work, per callback
+  size_t smem_bytes[5] = {0, 0, 0, 0, 0};
+};
+
+GeneratedSource generate_source(const Plan &plan);
+bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string &err);
+
 class Specialiser {
  public:
   Specialiser();
   ~Specialiser();
-  // builds one kernel per callback that has work; false + err if NVRTC/driver are unavailable
-  bool build(const Plan &plan, const std::vector<GenD> &gens_host, int device, std::string &err);
+  // col_dev_ptr[c]: device address of Plan::columns[c] (nullptr for iota columns)
+  bool build(const Plan &plan, const std::vector<const void *> &col_dev_ptr, std::string &err);
   bool has(int cb) const { return cb >= 0 && cb < 5 && fn_[cb] != nullptr; }
-  bool launch(int cb, int nblocks, const GenD *gens, const WorkItem *work, const double *x,
-              const double *theta, const double *y, double sigma, double *out, double *partials,
-              cudaStream_t st, std::string &err);
+  const std::vector<int> &groups_of(int cb) const { return groups_of_[cb]; }
+  bool launch(int cb, int nblocks, const WorkItem *work, const double *x, const double *theta,
+              const double *y, double sigma, double *out, double *partials, cudaStream_t st,
+              std::string &err);
   int n_kernels() const { return n_kernels_; }
-  // source of the generated translation unit (tests / DESIGN.md excerpts)
   static std::string generate_source(const Plan &plan);
 
  private:
   void *module_ = nullptr; // CUmodule
   void *fn_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t smem_[5] = {0, 0, 0, 0, 0};
+  std::vector<int> groups_of_[5];
   int n_kernels_ = 0;
 };
 

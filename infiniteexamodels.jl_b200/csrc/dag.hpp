@@ -22,7 +22,7 @@ enum DOp : int32_t {
   D_FIELD,     // fp iterator column a
   D_LOADX,     // x[index slot a]
   D_LOADP,     // theta[index slot a]
-  D_W,         // root weight: y[row] for constraints, obj_weight for objectives
+  D_W,         // root weight of group member a: y[row] for constraints, obj_weight for objectives
   D_SEL2,      // (index slot a == index slot b) ? 2.0 : 1.0   (lower-triangle diagonal rule)
   D_ADD, D_SUB, D_MUL, D_DIV, D_NEG, D_POW,
   D_SQRT, D_CBRT, D_ABS, D_SIGNP, D_EXP, D_EXP2, D_LOG, D_LOG2, D_LOG10, D_LOG1P,
@@ -75,7 +75,7 @@ class Dag {
   int field(int col) { return intern(D_FIELD, col, 0, 0.0); }
   int loadx(int islot) { return intern(D_LOADX, islot, 0, 0.0); }
   int loadp(int islot) { return intern(D_LOADP, islot, 0, 0.0); }
-  int w() { return intern(D_W, 0, 0, 0.0); }
+  int w(int member = 0) { return intern(D_W, member, 0, 0.0); }
   int sel2(int ia, int ib) {
     if (ia == ib) return cnst(2.0);
     if (ia > ib) std::swap(ia, ib);

@@ -273,7 +273,7 @@ class CudaEngine : public Engine {
     if (!(flags_ & IEXA_F_NO_SPECIALISE)) {
       spec_.reset(new Specialiser());
       std::string serr;
-      if (!spec_->build(plan_, gens_host_, device_, serr)) {
+      if (!spec_->build(plan_, col_dev_ptr_, serr) || build_group_tables(serr) != IEXA_OK) {
         // specialisation is an optimisation of the SAME device program; the AOT interpreter
         // kernels remain the (GPU) execution path.  Surface why.
         spec_error_ = serr;
@@ -317,10 +317,11 @@ class CudaEngine : public Engine {
     cudaStream_t st = (cudaStream_t)stream;
     const Table &T = table_[CB_OBJ];
     if (T.nblocks == 0) { CK(cudaMemsetAsync(f_dev, 0, 8, st)); return IEXA_OK; }
-    CK(partials_.ensure((size_t)T.nblocks * 8));
+    const int nb = (spec_ && spec_->has(CB_OBJ)) ? gtable_[CB_OBJ].nblocks : T.nblocks;
+    CK(partials_.ensure((size_t)std::max(nb, T.nblocks) * 8));
     int rc = launch(CB_OBJ, PROG_VAL, SINK_SUM, x_dev, nullptr, 1.0, nullptr, st, err);
     if (rc) return rc;
-    reduce_partials_kernel<<<1, 1024, 0, st>>>(partials_.as<double>(), T.nblocks, f_dev);
+    reduce_partials_kernel<<<1, 1024, 0, st>>>(partials_.as<double>(), nb, f_dev);
     CK(cudaGetLastError());
     return IEXA_OK;
   }
@@ -408,6 +409,9 @@ class CudaEngine : public Engine {
   GenD *gens_dev_ = nullptr;
   std::vector<GenD> gens_host_; // device pointers inside; objs first then cons
   Table table_[CB__N];
+  Table gtable_[CB__N]; // specialised path: block -> (group, block of supports)
+  DevBuf gwork_;
+  std::vector<const void *> col_dev_ptr_;
   double *pinned_f_ = nullptr;
   std::map<void *, size_t> registered_;
   std::unique_ptr<Specialiser> spec_;
@@ -447,6 +451,9 @@ class CudaEngine : public Engine {
     CK(leaf_.ensure(A.bytes.size() + 16));
     CK(cudaMemcpy(leaf_.p, A.bytes.data(), A.bytes.size(), cudaMemcpyHostToDevice));
     char *lb = (char *)leaf_.p;
+    col_dev_ptr_.assign(P.columns.size(), nullptr);
+    for (size_t c = 0; c < P.columns.size(); ++c)
+      if (col_off[c] != (size_t)-1) col_dev_ptr_[c] = lb + col_off[c];
 
     HostArena D; // descriptors (ColD / IdxD arrays)
     struct DOffs { size_t icol, fcol, idx; };
@@ -551,6 +558,28 @@ class CudaEngine : public Engine {
     return IEXA_OK;
   }
 
+  int build_group_tables(std::string &err) {
+    std::vector<WorkItem> items;
+    size_t starts[CB__N + 1];
+    for (int cb = 0; cb < CB__N; ++cb) {
+      starts[cb] = items.size();
+      if (!spec_->has(cb)) continue;
+      for (int gi : spec_->groups_of(cb)) {
+        const Group &G = plan_.groups[gi];
+        int64_t n = G.k1 - G.k0;
+        for (int64_t b = 0; b * BLOCK < n; ++b) items.push_back(WorkItem{gi, (int32_t)b});
+      }
+    }
+    starts[CB__N] = items.size();
+    CK(gwork_.ensure(items.size() * sizeof(WorkItem) + 16));
+    if (!items.empty()) CK(cudaMemcpy(gwork_.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    for (int cb = 0; cb < CB__N; ++cb) {
+      gtable_[cb].work = gwork_.as<WorkItem>() + starts[cb];
+      gtable_[cb].nblocks = (int)(starts[cb + 1] - starts[cb]);
+    }
+    return IEXA_OK;
+  }
+
   // ---- helpers -------------------------------------------------------------------------------
   void try_register(const void *p, size_t bytes) {
     // pin caller-owned host buffers once so the H2D/D2H copies run at PCIe speed; solvers reuse
@@ -592,7 +621,9 @@ class CudaEngine : public Engine {
     double *part = partials_.as<double>();
     const double *th = theta_.as<double>();
     if (spec_ && spec_->has(cb)) {
-      if (!spec_->launch(cb, T.nblocks, gens_dev_, T.work, xd, th, yd, sigma, outd, part, st, err)) return IEXA_ERR_CUDA;
+      const Table &GT = gtable_[cb];
+      if (GT.nblocks == 0) return IEXA_OK;
+      if (!spec_->launch(cb, GT.nblocks, GT.work, xd, th, yd, sigma, outd, part, st, err)) return IEXA_ERR_CUDA;
       return IEXA_OK;
     }
     if (T.max_nreg <= 32)

@@ -30,13 +30,23 @@ struct IndexExpr {
   bool operator==(const IndexExpr &o) const { return base == o.base && terms == o.terms; }
 };
 
+// slot numbering shared by everything compiled into one Dag: a single generator, or a GROUP of
+// generators over the same iterator that are fused into one program (plan.hpp: Group)
+struct SlotCtx {
+  std::vector<IndexExpr> uidx;   // distinct canonical index expressions ("index slots")
+  std::vector<int32_t> fp_cols;  // fp column slot -> iterator fp column
+  std::vector<int32_t> int_cols; // int column slot -> iterator int column (terms are rewritten to slots)
+  std::map<int32_t, int32_t> icolslot, fcolslot;
+};
+
 struct GenCompiled {
   // inputs
   std::vector<iexa_node> tape;
-  std::vector<IndexExpr> uidx;   // distinct canonical index expressions ("index slots")
+  std::vector<iexa_index> raw_idx;
+  std::vector<IndexExpr> uidx;   // copy of the SlotCtx the generator was compiled against
   std::vector<int32_t> idx_map;  // caller's index id -> index slot
-  std::vector<int32_t> fp_cols;  // fp column slot -> iterator fp column
-  std::vector<int32_t> int_cols; // int column slot -> iterator int column (terms are rewritten to slots)
+  std::vector<int32_t> fp_cols;
+  std::vector<int32_t> int_cols;
   // sparsity (symbolic)
   std::vector<int32_t> jac_slot;                      // per first-order slot: index slot of the variable
   std::vector<std::pair<int32_t, int32_t>> hess_slot; // per second-order slot: (index slot, index slot)
@@ -48,29 +58,53 @@ struct GenCompiled {
   std::vector<uint8_t> x_slots_val, x_slots_d1, x_slots_d2; // which index slots each program LOADX-es
 };
 
+Program schedule(const Dag &dag, const std::vector<int> &outs, size_t n_islots, std::vector<uint8_t> &x_slots);
+
 class GenCompiler {
  public:
+  // standalone: own slot context and Dag
   GenCompiler(const iexa_node *nodes, int32_t n, const iexa_index *idx, int32_t n_idx,
               int32_t n_int_cols_itr, int32_t n_fp_cols_itr)
-      : n_(n), n_int_itr_(n_int_cols_itr), n_fp_itr_(n_fp_cols_itr) {
-    if (n <= 0) throw std::invalid_argument("empty tape");
-    g.tape.assign(nodes, nodes + n);
-    canon_indices(idx, n_idx);
-    analyse();
+      : n_(n), n_int_itr_(n_int_cols_itr), n_fp_itr_(n_fp_cols_itr), ctx_(own_ctx_), dag_(own_dag_), wid_(0) {
+    init(nodes, idx, n_idx);
+  }
+  // fused: shared slot context and Dag; wid = member id used for the root weight W
+  GenCompiler(const iexa_node *nodes, int32_t n, const iexa_index *idx, int32_t n_idx,
+              int32_t n_int_cols_itr, int32_t n_fp_cols_itr, SlotCtx &ctx, Dag &dag, int wid)
+      : n_(n), n_int_itr_(n_int_cols_itr), n_fp_itr_(n_fp_cols_itr), ctx_(ctx), dag_(dag), wid_(wid) {
+    init(nodes, idx, n_idx);
   }
 
   GenCompiled g;
 
-  void compile() {
+  // symbolic AD into the Dag; afterwards val_root()/slot1()/slot2() name the outputs
+  void differentiate() {
     build_values();
     first_order();
     second_order();
-    g.val = schedule({val_[n_ - 1]}, g.x_slots_val);
-    g.d1 = schedule(slot1_, g.x_slots_d1);
-    g.d2 = schedule(slot2_, g.x_slots_d2);
+  }
+  int val_root() const { return val_[n_ - 1]; }
+  const std::vector<int> &slot1() const { return slot1_; }
+  const std::vector<int> &slot2() const { return slot2_; }
+
+  void compile() {
+    differentiate();
+    g.uidx = ctx_.uidx; g.fp_cols = ctx_.fp_cols; g.int_cols = ctx_.int_cols;
+    g.val = schedule(dag_, {val_[n_ - 1]}, ctx_.uidx.size(), g.x_slots_val);
+    g.d1 = schedule(dag_, slot1_, ctx_.uidx.size(), g.x_slots_d1);
+    g.d2 = schedule(dag_, slot2_, ctx_.uidx.size(), g.x_slots_d2);
   }
 
  private:
+  void init(const iexa_node *nodes, const iexa_index *idx, int32_t n_idx) {
+    if (n_ <= 0) throw std::invalid_argument("empty tape");
+    g.tape.assign(nodes, nodes + n_);
+    if (n_idx > 0) g.raw_idx.assign(idx, idx + n_idx);
+    canon_indices(idx, n_idx);
+    analyse();
+  }
+  SlotCtx own_ctx_;
+  Dag own_dag_;
   enum Kind { K_CONSTCLASS = 0, K_VAR = 1, K_UN = 2, K_BIN = 3 };
   enum Pass { P_NONE = 0, P_KEEP, P_FLIP, P_SCALE, P_ADD, P_SUB };
   struct Info {
@@ -82,7 +116,9 @@ class GenCompiler {
   int32_t n_, n_int_itr_, n_fp_itr_;
   std::vector<Info> info_;
   std::vector<int> val_;
-  Dag dag_;
+  SlotCtx &ctx_;
+  Dag &dag_;
+  int wid_;
   std::vector<int> slot1_, slot2_;
   std::map<int32_t, int32_t> slot1_of_;
   std::map<std::pair<int32_t, int32_t>, int32_t> slot2_of_;
@@ -92,18 +128,16 @@ class GenCompiler {
   static bool is_un(int op) { return op >= IEXA_OP_NEG && op < IEXA_OP__END; }
 
   void canon_indices(const iexa_index *idx, int32_t n_idx) {
-    std::map<int32_t, int32_t> colslot;
-    // first pass: which int columns are referenced (stable order of first reference)
+    // which int columns are referenced (stable order of first reference)
     for (int32_t i = 0; i < n_idx; ++i) {
       if (idx[i].nterms < 0 || idx[i].nterms > IEXA_MAX_INDEX_TERMS)
         throw std::invalid_argument("index expression: bad nterms");
       for (int t = 0; t < idx[i].nterms; ++t) {
         int32_t c = idx[i].col[t];
         if (c < 0 || c >= n_int_itr_) throw std::invalid_argument("index expression: int column out of range");
-        if (idx[i].coef[t] != 0 && !colslot.count(c)) {
-          int32_t s = (int32_t)g.int_cols.size();
-          colslot[c] = s;
-          g.int_cols.push_back(c);
+        if (idx[i].coef[t] != 0 && !ctx_.icolslot.count(c)) {
+          ctx_.icolslot[c] = (int32_t)ctx_.int_cols.size();
+          ctx_.int_cols.push_back(c);
         }
       }
     }
@@ -111,22 +145,21 @@ class GenCompiler {
     for (int32_t i = 0; i < n_idx; ++i) {
       std::map<int32_t, int64_t> acc;
       for (int t = 0; t < idx[i].nterms; ++t)
-        if (idx[i].coef[t] != 0) acc[colslot[idx[i].col[t]]] += idx[i].coef[t];
+        if (idx[i].coef[t] != 0) acc[ctx_.icolslot[idx[i].col[t]]] += idx[i].coef[t];
       IndexExpr e;
       e.base = idx[i].base;
       for (auto &kv : acc)
         if (kv.second != 0) e.terms.push_back(kv);
       int32_t found = -1;
-      for (size_t u = 0; u < g.uidx.size(); ++u)
-        if (g.uidx[u] == e) { found = (int32_t)u; break; }
-      if (found < 0) { found = (int32_t)g.uidx.size(); g.uidx.push_back(e); }
+      for (size_t u = 0; u < ctx_.uidx.size(); ++u)
+        if (ctx_.uidx[u] == e) { found = (int32_t)u; break; }
+      if (found < 0) { found = (int32_t)ctx_.uidx.size(); ctx_.uidx.push_back(e); }
       g.idx_map[i] = found;
     }
   }
 
   void analyse() {
     info_.assign(n_, Info());
-    std::map<int32_t, int32_t> fpslot;
     for (int i = 0; i < n_; ++i) {
       const iexa_node &nd = g.tape[i];
       Info &in = info_[i];
@@ -137,7 +170,7 @@ class GenCompiler {
         }
         if (nd.op == IEXA_OP_FIELD) {
           if (nd.a < 0 || nd.a >= n_fp_itr_) throw std::invalid_argument("tape: fp column out of range");
-          if (!fpslot.count(nd.a)) { fpslot[nd.a] = (int32_t)g.fp_cols.size(); g.fp_cols.push_back(nd.a); }
+          if (!ctx_.fcolslot.count(nd.a)) { ctx_.fcolslot[nd.a] = (int32_t)ctx_.fp_cols.size(); ctx_.fp_cols.push_back(nd.a); }
         }
         in.kind = nd.op == IEXA_OP_VAR ? K_VAR : K_CONSTCLASS;
       } else if (is_bin(nd.op)) {
@@ -163,9 +196,7 @@ class GenCompiler {
       }
     }
     g.is_null = info_[n_ - 1].kind == K_CONSTCLASS;
-    fpslot_ = fpslot;
   }
-  std::map<int32_t, int32_t> fpslot_;
 
   // value + local partials of a unary function u -> f(u); returns value, sets y,h when active
   int lower_unary(int op, int u, bool active, int &y, int &h) {
@@ -235,7 +266,7 @@ class GenCompiler {
       Info &in = info_[i];
       switch (nd.op) {
         case IEXA_OP_CONST: val_[i] = d.cnst(nd.c); continue;
-        case IEXA_OP_FIELD: val_[i] = d.field(fpslot_[nd.a]); continue;
+        case IEXA_OP_FIELD: val_[i] = d.field(ctx_.fcolslot[nd.a]); continue;
         case IEXA_OP_VAR: val_[i] = d.loadx(g.idx_map[nd.a]); continue;
         case IEXA_OP_PAR: val_[i] = d.loadp(g.idx_map[nd.a]); continue;
         default: break;
@@ -410,77 +441,77 @@ class GenCompiler {
     }
   }
   void second_order() {
-    if (!g.is_null) hr0(n_ - 1, dag_.w(), dag_.cnst(0.0));
+    if (!g.is_null) hr0(n_ - 1, dag_.w(wid_), dag_.cnst(0.0));
     g.o2step = (int32_t)g.hess_slot.size();
   }
 
-  // ---- DAG -> register program ---------------------------------------------------------
-  Program schedule(const std::vector<int> &outs, std::vector<uint8_t> &x_slots) {
-    Program P;
-    const auto &N = dag_.nodes;
-    int nn = (int)N.size();
-    std::vector<uint8_t> live(nn, 0);
-    std::vector<int> stack(outs.begin(), outs.end());
-    while (!stack.empty()) {
-      int v = stack.back(); stack.pop_back();
-      if (live[v]) continue;
-      live[v] = 1;
-      int op = N[v].op;
-      if (dop_is_unary(op)) stack.push_back(N[v].a);
-      else if (dop_is_binary(op)) { stack.push_back(N[v].a); stack.push_back(N[v].b); }
-    }
-    // last use
-    std::vector<int> last(nn, -1);
-    for (int v = 0; v < nn; ++v) {
-      if (!live[v]) continue;
-      int op = N[v].op;
-      if (dop_is_unary(op)) last[N[v].a] = v;
-      else if (dop_is_binary(op)) { last[N[v].a] = v; last[N[v].b] = v; }
-    }
-    std::vector<std::vector<int>> outs_of(nn);
-    for (size_t j = 0; j < outs.size(); ++j) outs_of[outs[j]].push_back((int)j);
-    std::vector<int> reg(nn, -1), cidx(nn, -1);
-    std::vector<int> freelist;
-    int nreg = 0;
-    auto alloc = [&]() { if (!freelist.empty()) { int r = freelist.back(); freelist.pop_back(); return r; } return nreg++; };
-    auto operand = [&](int v) -> int32_t {
-      if (N[v].op == D_CONST) {
-        if (cidx[v] < 0) { cidx[v] = (int)P.cpool.size(); P.cpool.push_back(N[v].c); }
-        return ~cidx[v];
-      }
-      return reg[v];
-    };
-    x_slots.assign(g.uidx.size(), 0);
-    P.nout = (int32_t)outs.size();
-    for (int v = 0; v < nn; ++v) {
-      if (!live[v]) continue;
-      int op = N[v].op;
-      if (op == D_CONST) {
-        for (int j : outs_of[v]) P.code.push_back(Instr{D_OUT, j, operand(v), 0});
-        continue;
-      }
-      Instr I{op, 0, 0, 0};
-      if (dop_is_unary(op)) I.a = operand(N[v].a);
-      else if (dop_is_binary(op)) { I.a = operand(N[v].a); I.b = operand(N[v].b); }
-      else { I.a = N[v].a; I.b = N[v].b; }
-      if (op == D_LOADX) x_slots[N[v].a] = 1;
-      if (op == D_W) P.uses_w = true;
-      // free operand registers whose last use is here BEFORE allocating dst (dst may reuse them)
-      if (dop_is_unary(op) || dop_is_binary(op)) {
-        int a = N[v].a, b = dop_is_binary(op) ? N[v].b : -1;
-        if (N[a].op != D_CONST && last[a] == v) freelist.push_back(reg[a]);
-        if (b >= 0 && b != a && N[b].op != D_CONST && last[b] == v) freelist.push_back(reg[b]);
-        ++P.n_flop_nodes;
-      }
-      reg[v] = alloc();
-      I.dst = reg[v];
-      P.code.push_back(I);
-      for (int j : outs_of[v]) P.code.push_back(Instr{D_OUT, j, reg[v], 0});
-      if (last[v] < 0) freelist.push_back(reg[v]); // only feeds outputs (already emitted)
-    }
-    P.nreg = nreg;
-    return P;
-  }
 };
+
+// ---- DAG -> register program -----------------------------------------------------------------
+inline Program schedule(const Dag &dag, const std::vector<int> &outs, size_t n_islots, std::vector<uint8_t> &x_slots) {
+  Program P;
+  const auto &N = dag.nodes;
+  int nn = (int)N.size();
+  std::vector<uint8_t> live(nn, 0);
+  std::vector<int> stack(outs.begin(), outs.end());
+  while (!stack.empty()) {
+    int v = stack.back(); stack.pop_back();
+    if (live[v]) continue;
+    live[v] = 1;
+    int op = N[v].op;
+    if (dop_is_unary(op)) stack.push_back(N[v].a);
+    else if (dop_is_binary(op)) { stack.push_back(N[v].a); stack.push_back(N[v].b); }
+  }
+  std::vector<int> last(nn, -1);
+  for (int v = 0; v < nn; ++v) {
+    if (!live[v]) continue;
+    int op = N[v].op;
+    if (dop_is_unary(op)) last[N[v].a] = v;
+    else if (dop_is_binary(op)) { last[N[v].a] = v; last[N[v].b] = v; }
+  }
+  std::vector<std::vector<int>> outs_of(nn);
+  for (size_t j = 0; j < outs.size(); ++j) outs_of[outs[j]].push_back((int)j);
+  std::vector<int> reg(nn, -1), cidx(nn, -1);
+  std::vector<int> freelist;
+  int nreg = 0;
+  auto alloc = [&]() { if (!freelist.empty()) { int r = freelist.back(); freelist.pop_back(); return r; } return nreg++; };
+  auto operand = [&](int v) -> int32_t {
+    if (N[v].op == D_CONST) {
+      if (cidx[v] < 0) { cidx[v] = (int)P.cpool.size(); P.cpool.push_back(N[v].c); }
+      return ~cidx[v];
+    }
+    return reg[v];
+  };
+  x_slots.assign(n_islots, 0);
+  P.nout = (int32_t)outs.size();
+  for (int v = 0; v < nn; ++v) {
+    if (!live[v]) continue;
+    int op = N[v].op;
+    if (op == D_CONST) {
+      for (int j : outs_of[v]) P.code.push_back(Instr{D_OUT, j, operand(v), 0});
+      continue;
+    }
+    Instr I{op, 0, 0, 0};
+    if (dop_is_unary(op)) I.a = operand(N[v].a);
+    else if (dop_is_binary(op)) { I.a = operand(N[v].a); I.b = operand(N[v].b); }
+    else { I.a = N[v].a; I.b = N[v].b; }
+    if (op == D_LOADX) x_slots[N[v].a] = 1;
+    if (op == D_W) P.uses_w = true;
+    // free operand registers whose last use is here BEFORE allocating dst (dst may reuse them)
+    if (dop_is_unary(op) || dop_is_binary(op)) {
+      int a = N[v].a, b = dop_is_binary(op) ? N[v].b : -1;
+      if (N[a].op != D_CONST && last[a] == v) freelist.push_back(reg[a]);
+      if (b >= 0 && b != a && N[b].op != D_CONST && last[b] == v) freelist.push_back(reg[b]);
+      ++P.n_flop_nodes;
+    }
+    reg[v] = alloc();
+    I.dst = reg[v];
+    P.code.push_back(I);
+    for (int j : outs_of[v]) P.code.push_back(Instr{D_OUT, j, reg[v], 0});
+    if (last[v] < 0) freelist.push_back(reg[v]); // only feeds outputs (already emitted)
+  }
+  P.nreg = nreg;
+  return P;
+}
 
 } // namespace iexa

@@ -48,6 +48,24 @@ struct Generator {
   int64_t l0 = 0, l1 = 0, l2 = 0;
 };
 
+// Generators over the SAME iterator are fused into one program: one thread evaluates every
+// member at its support point, so shared loads (x, theta, columns) and shared sub-expressions
+// (sin/cos of the same state) are done once.  Layout is untouched: each member still owns its
+// rows / slots.  (The reference stack evaluates every generator in its own kernel launch.)
+struct Group {
+  bool is_obj = false;
+  int32_t itr = 0;
+  int64_t K = 1;
+  int64_t k0 = 0, k1 = 0;
+  std::vector<int32_t> members; // indices into Plan::objs or Plan::cons
+  SlotCtx ctx;
+  Program prog[3];                                    // val, d1, d2 over all members
+  std::vector<std::pair<int32_t, int32_t>> outmap[3]; // program output j -> (member position, slot)
+  std::vector<std::vector<int32_t>> jac_slot;         // per member: group index slot of each first-order slot
+  std::vector<uint8_t> x_slots[3];
+  size_t dag_nodes = 0;
+};
+
 struct Plan {
   bool minimize = true;
   bool finalized = false;
@@ -55,6 +73,7 @@ struct Plan {
   std::vector<HostColumn> columns;
   std::vector<Iterator> itrs;
   std::vector<Generator> objs, cons;
+  std::vector<Group> groups; // built by layout(); objective groups first
   int64_t nvar = 0, npar = 0, ncon = 0, nnzj = 0, nnzh = 0, nnzg = 0;
   int64_t loc_ncon = 0, loc_nnzj = 0, loc_nnzh = 0;
   int32_t rank = 0, world = 1, device = -1;
@@ -200,8 +219,65 @@ struct Plan {
       g.l1 = loc_nnzj; loc_nnzj += (g.k1 - g.k0) * g.c.o1step;
       g.l2 = loc_nnzh; loc_nnzh += (g.k1 - g.k0) * g.c.o2step;
     }
+    build_groups();
     finalized = true;
   }
+
+  // fuse generators that share (kind, iterator); a group is closed when it grows past the caps
+  void build_groups(size_t max_dag_nodes = 6000, int max_slots = 96) {
+    groups.clear();
+    for (int pass = 0; pass < 2; ++pass) {
+      std::vector<Generator> &gens = pass == 0 ? objs : cons;
+      std::map<int32_t, int> open; // itr -> group index
+      std::vector<std::unique_ptr<Dag>> dags;
+      std::vector<std::vector<int>> outs[3];
+      std::vector<int> slots1, slots2;
+      size_t first_group = groups.size();
+      for (size_t gi = 0; gi < gens.size(); ++gi) {
+        Generator &g = gens[gi];
+        const Iterator &it = itrs[g.itr];
+        int gid = -1;
+        auto f = open.find(g.itr);
+        if (f != open.end()) {
+          size_t li = f->second - first_group;
+          int s1 = g.c.o1step > 1 ? (g.c.o1step | 1) : 0, s2 = g.c.o2step > 1 ? (g.c.o2step | 1) : 0;
+          if (dags[li]->nodes.size() < max_dag_nodes && slots1[li] + s1 <= max_slots && slots2[li] + s2 <= max_slots)
+            gid = f->second;
+        }
+        if (gid < 0) {
+          gid = (int)groups.size();
+          groups.emplace_back();
+          Group &G = groups.back();
+          G.is_obj = pass == 0; G.itr = g.itr; G.K = g.K; G.k0 = g.k0; G.k1 = g.k1;
+          dags.emplace_back(new Dag());
+          for (auto &o : outs) o.emplace_back();
+          slots1.push_back(0); slots2.push_back(0);
+          open[g.itr] = gid;
+        }
+        size_t li = gid - first_group;
+        Group &G = groups[gid];
+        int mpos = (int)G.members.size();
+        GenCompiler gc(g.c.tape.data(), (int32_t)g.c.tape.size(), g.c.raw_idx.data(), (int32_t)g.c.raw_idx.size(),
+                       (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size(), G.ctx, *dags[li], mpos);
+        gc.differentiate();
+        G.members.push_back((int32_t)gi);
+        G.jac_slot.push_back(gc.g.jac_slot);
+        outs[0][li].push_back(gc.val_root());
+        G.outmap[0].push_back({mpos, 0});
+        for (size_t c = 0; c < gc.slot1().size(); ++c) { outs[1][li].push_back(gc.slot1()[c]); G.outmap[1].push_back({mpos, (int32_t)c}); }
+        for (size_t c = 0; c < gc.slot2().size(); ++c) { outs[2][li].push_back(gc.slot2()[c]); G.outmap[2].push_back({mpos, (int32_t)c}); }
+        slots1[li] += g.c.o1step > 1 ? (g.c.o1step | 1) : 0;
+        slots2[li] += g.c.o2step > 1 ? (g.c.o2step | 1) : 0;
+      }
+      for (size_t li = 0; li < dags.size(); ++li) {
+        Group &G = groups[first_group + li];
+        for (int p = 0; p < 3; ++p) G.prog[p] = schedule(*dags[li], outs[p][li], G.ctx.uidx.size(), G.x_slots[p]);
+        G.dag_nodes = dags[li]->nodes.size();
+      }
+    }
+  }
+
+  const Generator &member(const Group &G, int mpos) const { return (G.is_obj ? objs : cons)[G.members[mpos]]; }
 };
 
 } // namespace iexa

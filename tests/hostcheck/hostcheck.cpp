@@ -37,6 +37,39 @@ static void run_program(const Plan &P, const Generator &g, const Program &pr, in
     }
   }
 }
+
+// fused group programs (plan.hpp: Group) — slot numbering comes from the group's SlotCtx
+static int64_t g_int_col(const Plan &P, const Group &G, int32_t slot, int64_t k) {
+  const ColRef &r = P.itrs[G.itr].int_cols[G.ctx.int_cols[slot]];
+  int64_t j = (k / r.div) % r.mod;
+  const HostColumn &c = P.columns[r.col];
+  return c.iota ? j + 1 : (int64_t)c.ivals[j];
+}
+static int64_t g_index(const Plan &P, const Group &G, int32_t islot, int64_t k) {
+  const IndexExpr &e = G.ctx.uidx[islot];
+  int64_t v = e.base;
+  for (auto &t : e.terms) v += t.second * g_int_col(P, G, t.first, k);
+  return v;
+}
+static void run_group(const Plan &P, const Group &G, const Program &pr, int64_t k, const double *x, const double *y,
+                      double sigma, std::vector<double> &r, double *out) {
+  r.resize(pr.nreg > 0 ? pr.nreg : 1);
+  for (const Instr &I : pr.code) {
+    switch (I.op) {
+      case D_FIELD: { const ColRef &c = P.itrs[G.itr].fp_cols[G.ctx.fp_cols[I.a]]; r[I.dst] = P.columns[c.col].fvals[(k / c.div) % c.mod]; break; }
+      case D_LOADX: r[I.dst] = x[g_index(P, G, I.a, k) - 1]; break;
+      case D_LOADP: r[I.dst] = P.theta[g_index(P, G, I.a, k) - 1]; break;
+      case D_W: r[I.dst] = G.is_obj ? sigma : (y ? y[P.member(G, I.a).o0 + k] : 0.0); break;
+      case D_SEL2: r[I.dst] = g_index(P, G, I.a, k) == g_index(P, G, I.b, k) ? 2.0 : 1.0; break;
+      case D_OUT: out[I.dst] = I.a >= 0 ? r[I.a] : pr.cpool[~I.a]; break;
+      default: {
+        double a = I.a >= 0 ? r[I.a] : pr.cpool[~I.a];
+        double b = I.b >= 0 ? r[I.b] : pr.cpool[~I.b];
+        r[I.dst] = eval_arith(I.op, a, b);
+      }
+    }
+  }
+}
 } // namespace iexa
 
 using namespace iexa;
@@ -67,6 +100,39 @@ int32_t hostcheck_eval(iexa_plan *p, int32_t which, const double *x, const doubl
   };
   if (which == 0 || which == 1 || which == 4) for (auto &g : P.objs) each(g);
   if (which >= 2) for (auto &g : P.cons) each(g);
+  return IEXA_OK;
+}
+
+// same as hostcheck_eval but through the FUSED group programs; returns the number of groups via ngroups
+int32_t hostcheck_eval_groups(iexa_plan *p, int32_t which, const double *x, const double *y, double sigma, double *out,
+                              int32_t *ngroups) {
+  if (!p || !p->plan.finalized) return IEXA_ERR_STATE;
+  const Plan &P = p->plan;
+  std::vector<double> r, tmp;
+  if (which == 0) out[0] = 0.0;
+  if (which == 1) std::memset(out, 0, sizeof(double) * (size_t)P.nvar);
+  const int prog = (which == 0 || which == 2) ? 0 : (which == 1 || which == 3) ? 1 : 2;
+  if (ngroups) *ngroups = (int32_t)P.groups.size();
+  for (const Group &G : P.groups) {
+    bool want = G.is_obj ? (which == 0 || which == 1 || which == 4) : (which >= 2);
+    if (!want) continue;
+    const Program &pr = G.prog[prog];
+    tmp.assign(pr.nout > 0 ? pr.nout : 1, 0.0);
+    for (int64_t k = 0; k < G.K; ++k) {
+      run_group(P, G, pr, k, x, y, sigma, r, tmp.data());
+      for (size_t j = 0; j < G.outmap[prog].size(); ++j) {
+        int m = G.outmap[prog][j].first, c = G.outmap[prog][j].second;
+        const Generator &g = P.member(G, m);
+        switch (which) {
+          case 0: out[0] += tmp[j]; break;
+          case 1: out[g_index(P, G, G.jac_slot[m][c], k) - 1] += tmp[j]; break;
+          case 2: out[g.o0 + k] = tmp[j]; break;
+          case 3: out[g.o1 + k * g.c.o1step + c] = tmp[j]; break;
+          case 4: out[g.o2 + k * g.c.o2step + c] = tmp[j]; break;
+        }
+      }
+    }
+  }
   return IEXA_OK;
 }
 
