@@ -564,11 +564,20 @@ class CudaEngine : public Engine {
     for (int cb = 0; cb < CB__N; ++cb) {
       starts[cb] = items.size();
       if (!spec_->has(cb)) continue;
+      // Blocks of different groups are interleaved by their RELATIVE position in the support
+      // range: groups that walk the same supports (ODE rows, collocation rows, control rows of a
+      // time-indexed model) then touch the same part of x at about the same time, so the second
+      // reader hits in the 126 MB L2 instead of re-reading HBM.
+      struct Ord { double frac; int gi; int32_t b; };
+      std::vector<Ord> ord;
       for (int gi : spec_->groups_of(cb)) {
         const Group &G = plan_.groups[gi];
         int64_t n = G.k1 - G.k0;
-        for (int64_t b = 0; b * BLOCK < n; ++b) items.push_back(WorkItem{gi, (int32_t)b});
+        int64_t nb = (n + BLOCK - 1) / BLOCK;
+        for (int64_t b = 0; b < nb; ++b) ord.push_back(Ord{(b + 0.5) / (double)nb, gi, (int32_t)b});
       }
+      std::stable_sort(ord.begin(), ord.end(), [](const Ord &a, const Ord &b) { return a.frac < b.frac; });
+      for (const Ord &o : ord) items.push_back(WorkItem{o.gi, o.b});
     }
     starts[CB__N] = items.size();
     CK(gwork_.ensure(items.size() * sizeof(WorkItem) + 16));
