@@ -220,3 +220,61 @@ def farmer(num_scenarios: int = 1000, seed: int = 42) -> ExaCore:
     core.add_obj(ds.c * (beta[0] * y[0][i] + beta[1] * y[1][i] + (-lam[0]) * w[0][i] + (-lam[1]) * w[1][i]
                          + (-lam[2]) * w[2][i]), m)
     return core
+
+
+# ------------------------------------------------------------------------------------------------
+def rosenbrock_param(p1: float = 100.0, p2: float = 1.0, nt: int = 3):
+    """test/solve.jl:134-156 ("Parameter updates"): known answers 306.4999755050365 and, after the
+    in-place update p1=90, p2=1.3, 276.26497794903645.  Returns (core, P1, P2) with the finite
+    parameter handles (θ layout: one entry per finite parameter, transform.jl:120-131)."""
+    core = ExaCore(minimize=True)
+    ds = DataSource()
+    ts = np.linspace(0, 1, nt)
+    P1 = core.add_par([p1])
+    P2 = core.add_par([p2])
+    x1 = core.add_var(nt)
+    x2 = core.add_var(nt)
+    it = Itr(nt, {"group_idx1": np.arange(1, nt + 1)}, {"ip1": ts})
+    i = ds.group_idx1
+    core.add_con(x1[i], it, -np.inf, 0.5)
+    core.add_con(x2[i], it, -np.inf, 3.0)
+    core.add_con(x1[i] * x2[i], it, 1.0, np.inf)
+    core.add_con(abs2(x2[i]) + x1[i], it, 0.0, np.inf)
+    m = Itr(nt, {"group_idx1": np.arange(1, nt + 1)}, {"c": trapezoid_coeffs(ts), "ip1": ts})
+    # p1 * ∫((x2 − x1²)², t): quad term (p1, measure) -> coef·p1 moves inside (transform.jl:758-762)
+    core.add_obj(ds.c * (P1[1] * (((-1.0) * abs2(x1[i]) + x2[i]) ** 2)), m)
+    # ∫((p2 − x1)², t): affine² expands to p2² − 2·p2·x1 + x1²
+    core.add_obj(ds.c * (abs2(P2[1]) + (-2.0) * P2[1] * x1[i] + abs2(x1[i])), m)
+    return core, P1, P2
+
+
+def param_function_model(offset: float = 0.2, pf1=np.sin, nt: int = 3, ns: int = 3):
+    """test/solve.jl:158-209 ("Parameter function updates"): known answers 0.48292223509341475
+    (pf1 = sin, pf2 = sin(t)·s + 0.2) and 0.8155916466182952 (pf1 = cos, pf2 = sin(t)·s + 0.8).
+    Returns (core, PF1, PF2); θ layout is column-major, first group fastest
+    (test/transcription.jl:151-167, test/solve.jl:191)."""
+    core = ExaCore(minimize=True)
+    ds = DataSource()
+    ts = np.linspace(0, 1, nt)
+    ss = np.linspace(2, 3, ns)
+    it_t = Itr(nt, {"group_idx1": np.arange(1, nt + 1)}, {"ip1": ts})
+    it_s = Itr(ns, {"group_idx2": np.arange(1, ns + 1)}, {"ip2": ss})
+    both = Itr.product([it_t, it_s])
+    v = core.add_var(nt, lvar=0.0, uvar=100.0)
+    z = core.add_var(nt, ns, lvar=0.0, uvar=100.0)
+    PF1 = core.add_par(pf1(ts))
+    PF2 = core.add_par(np.sin(ts)[:, None] * ss[None, :] + offset)
+    i, j = ds.group_idx1, ds.group_idx2
+    core.add_con(v[i] + PF1[i], it_t, -np.inf, 100.0)                         # c1
+    core.add_con(PF1[i] * PF2[i, j] + 2.0 * v[i], both, -np.inf, 100.0)      # c2: quad term, then aff
+    core.add_con(v[i] + (-0.5) * PF2[i, j], both, 0.0, np.inf)               # c3
+    s25 = int(np.argmin(np.abs(ss - 2.5))) + 1                               # support_to_index[s = 2.5]
+    core.add_con(PF2[i, j] * PF1[i] + z[i, s25], both, -np.inf, 40.0)         # c4: semi-infinite z(t, 2.5)
+    mt = Itr(nt, {"group_idx1": np.arange(1, nt + 1)}, {"c": trapezoid_coeffs(ts), "ip1": ts})
+    core.add_obj(ds.c * (v[i] * PF1[i]), mt)
+    wt, ws = trapezoid_coeffs(ts), trapezoid_coeffs(ss)
+    K = nt * ns
+    m2 = Itr(K, {"group_idx1": np.tile(np.arange(1, nt + 1), ns), "group_idx2": np.repeat(np.arange(1, ns + 1), nt)},
+             {"c": np.outer(ws, wt).reshape(-1)})
+    core.add_obj(ds.c * (0.5 * z[i, j] * PF2[i, j]), m2)
+    return core, PF1, PF2
