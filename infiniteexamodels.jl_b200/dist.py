@@ -1,0 +1,126 @@
+"""Multi-GPU evaluation: one process per GPU, contiguous support-block sharding.
+
+Every generator is a map over its supports and its rows / COO slots are affine in the support
+index, so rank r of W evaluates ``k ∈ [K·r/W, K·(r+1)/W)`` of every generator and OWNS the matching
+slices of c, Jacobian values and Hessian values: ``cons!``, ``jac_coord!`` and ``hess_coord!`` need no
+communication at all.  x is replicated.  ``obj`` needs an all-reduce of one double and ``grad!`` an
+all-reduce of the slice of g that several ranks contribute to (finite / first-stage variables that
+every support's objective term references) — NCCL over NVLink through ``torch.distributed`` on
+GPUs, gloo in the CPU tests.  The KKT factorisation stays on one GPU (non-target cost).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import lib as _lib
+from . import model as _m
+from .core import ExaCore
+
+
+class ShardedExaModel:
+    """NLPModels callbacks over a model sharded across the ranks of a torch.distributed group."""
+
+    def __init__(self, core: ExaCore, device: Optional[int] = None, group=None, flags: int = _lib.IEXA_F_DEFAULT,
+                 library=None, evaluator=None):
+        import torch
+        import torch.distributed as dist
+        self.dist, self.torch, self.group = dist, torch, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.model = _m.ExaModel(core, device=0 if device is None else device, rank=self.rank, world=self.world,
+                                 flags=flags, library=library)
+        self.meta = self.model.meta
+        m = self.model
+        n = m.L.iexa_shared_vars(m.h, None, 0)
+        idx = np.zeros(max(n, 1), dtype=np.int64)
+        if n > 0:
+            m.L.iexa_shared_vars(m.h, idx.ctypes.data, n)
+        self.shared_idx = idx[:n] - 1  # 0-based variable indices whose gradient entries are partial sums
+        self._ev = evaluator  # tests inject a host evaluator; default: the CUDA engine
+        self._shared_t = None
+
+    # ---- layout ---------------------------------------------------------------------------------
+    def segments(self, which: int):
+        """[(global_start, local_start, length)] of rows (0), Jacobian slots (1), Hessian slots (2)."""
+        m = self.model
+        n = m.L.iexa_segments(m.h, which, None, 0)
+        segs = (_lib.Segment * max(n, 1))()
+        m.L.iexa_segments(m.h, which, segs, n)
+        return [(s.global_start, s.local_start, s.length) for s in segs[:n]]
+
+    def scatter_local(self, which: int, global_vec):
+        """this rank's slice of a GLOBAL vector (e.g. the multipliers y) in local layout"""
+        n = (self.model.loc_ncon, self.model.loc_nnzj, self.model.loc_nnzh)[which]
+        out = global_vec.new_zeros(max(n, 1)) if isinstance(global_vec, self.torch.Tensor) else np.zeros(max(n, 1))
+        for gs, ls, ln in self.segments(which):
+            out[ls:ls + ln] = global_vec[gs:gs + ln]
+        return out
+
+    def gather_global(self, which: int, local_vec):
+        """assemble the GLOBAL vector from every rank's local slice (tests / single-GPU consumers:
+        this gather is part of the non-target KKT cost)"""
+        torch, dist = self.torch, self.dist
+        total = (self.meta.ncon, self.meta.nnzj, self.meta.nnzh)[which]
+        t = torch.as_tensor(local_vec)
+        out = torch.zeros(total, dtype=t.dtype, device=t.device)
+        for gs, ls, ln in self.segments(which):
+            out[gs:gs + ln] = t[ls:ls + ln]
+        if self.world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)  # slices are disjoint
+        return out
+
+    # ---- callbacks ------------------------------------------------------------------------------
+    def _reduce_scalar(self, v: float, like=None) -> float:
+        if self.world == 1:
+            return v
+        torch, dist = self.torch, self.dist
+        dev = like.device if isinstance(like, torch.Tensor) else "cpu"
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())
+
+    def obj(self, x) -> float:
+        part = self._ev.obj(x) if self._ev else _m.obj(self.model, x)
+        return self._reduce_scalar(part, x)
+
+    def grad_(self, x, g):
+        """dense g; entries of shared variables are complete on every rank after the call, all other
+        entries hold this rank's (exclusive) contributions — zero where another rank owns the support."""
+        if self._ev:
+            self._ev.grad_(x, g)
+        else:
+            _m.grad_(self.model, x, g)
+        if self.world > 1 and len(self.shared_idx):
+            torch, dist = self.torch, self.dist
+            gt = g if isinstance(g, torch.Tensor) else torch.from_numpy(g)
+            if self._shared_t is None or self._shared_t.device != gt.device:
+                self._shared_t = torch.from_numpy(self.shared_idx).to(gt.device)
+            buf = gt[self._shared_t].contiguous()
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            gt[self._shared_t] = buf
+        return g
+
+    def grad_full_(self, x, g):
+        """dense g complete on every rank (all-reduce of the whole vector; for single-GPU consumers)"""
+        if self._ev:
+            self._ev.grad_(x, g)
+        else:
+            _m.grad_(self.model, x, g)
+        if self.world > 1:
+            gt = g if isinstance(g, self.torch.Tensor) else self.torch.from_numpy(g)
+            self.dist.all_reduce(gt, op=self.dist.ReduceOp.SUM, group=self.group)
+        return g
+
+    def cons_(self, x, c):
+        return self._ev.cons_(x, c) if self._ev else _m.cons_(self.model, x, c)
+
+    def jac_coord_(self, x, vals):
+        return self._ev.jac_coord_(x, vals) if self._ev else _m.jac_coord_(self.model, x, vals)
+
+    def hess_coord_(self, x, y_local, vals, obj_weight: float = 1.0):
+        if self._ev:
+            return self._ev.hess_coord_(x, y_local, vals, obj_weight)
+        return _m.hess_coord_(self.model, x, y_local, vals, obj_weight)

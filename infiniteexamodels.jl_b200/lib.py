@@ -90,6 +90,7 @@ def _declare(L):
     sig("iexa_csr_apply", _i32, _vp, _vp, _vp, _i32, _vp)
     # test-only entry points of tests/hostcheck (absent from the product library)
     sig("hostcheck_eval", _i32, _vp, _i32, _vp, _vp, _dbl, _vp)
+    sig("hostcheck_eval_local", _i32, _vp, _i32, _vp, _vp, _dbl, _vp)
     sig("hostcheck_eval_groups", _i32, _vp, _i32, _vp, _vp, _dbl, _vp, C.POINTER(_i32))
     sig("hostcheck_structure", _i32, _vp, _i32, _vp, _vp)
     sig("hostcheck_gen_stats", _i32, _vp, _i32, _i32, _vp)

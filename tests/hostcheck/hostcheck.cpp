@@ -103,6 +103,35 @@ int32_t hostcheck_eval(iexa_plan *p, int32_t which, const double *x, const doubl
   return IEXA_OK;
 }
 
+// this rank's shard only, LOCAL layout (what the CUDA engine produces when world > 1); y is local too.
+// which: 0 obj partial, 1 grad partial (dense nvar), 2 cons, 3 jac_coord, 4 hess_coord
+int32_t hostcheck_eval_local(iexa_plan *p, int32_t which, const double *x, const double *y, double sigma, double *out) {
+  if (!p || !p->plan.finalized) return IEXA_ERR_STATE;
+  const Plan &P = p->plan;
+  std::vector<double> r, tmp;
+  if (which == 0) out[0] = 0.0;
+  if (which == 1) std::memset(out, 0, sizeof(double) * (size_t)P.nvar);
+  auto each = [&](const Generator &g) {
+    const Program &pr = (which == 0 || which == 2) ? g.c.val : (which == 1 || which == 3) ? g.c.d1 : g.c.d2;
+    tmp.assign(pr.nout > 0 ? pr.nout : 1, 0.0);
+    for (int64_t k = g.k0; k < g.k1; ++k) {
+      const int64_t kl = k - g.k0;
+      double W = g.is_obj ? sigma : (y ? y[g.l0 + kl] : 0.0);
+      run_program(P, g, pr, k, x, W, r, tmp.data());
+      switch (which) {
+        case 0: out[0] += tmp[0]; break;
+        case 1: for (int c = 0; c < g.c.o1step; ++c) out[P.index_value(g, g.c.jac_slot[c], k) - 1] += tmp[c]; break;
+        case 2: out[g.l0 + kl] = tmp[0]; break;
+        case 3: for (int c = 0; c < g.c.o1step; ++c) out[g.l1 + kl * g.c.o1step + c] = tmp[c]; break;
+        case 4: for (int c = 0; c < g.c.o2step; ++c) out[g.l2 + kl * g.c.o2step + c] = tmp[c]; break;
+      }
+    }
+  };
+  if (which == 0 || which == 1 || which == 4) for (auto &g : P.objs) each(g);
+  if (which >= 2) for (auto &g : P.cons) each(g);
+  return IEXA_OK;
+}
+
 // same as hostcheck_eval but through the FUSED group programs; returns the number of groups via ngroups
 int32_t hostcheck_eval_groups(iexa_plan *p, int32_t which, const double *x, const double *y, double sigma, double *out,
                               int32_t *ngroups) {

@@ -137,3 +137,47 @@ def test_nan_propagates():
     c = torch.zeros(core.ncon, dtype=torch.float64, device="cuda")
     ex.cons_(m, x, c)
     assert torch.isnan(c).any() and not torch.isnan(c).all()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_plans_tile_the_model_on_one_gpu(world, oracle_cache):
+    """the CUDA path of every rank of a W-rank sharding, run one after the other on cuda:0: the local
+    slices assembled through iexa_segments reproduce the unsharded oracle result"""
+    import torch
+    core = models.quadrotor(101, "oc")
+    from oracle.oracle import OracleModel
+    om = OracleModel(core)
+    x, y = eval_point(core, seed=9)
+    xd = torch.from_numpy(x).cuda()
+    cg, jg, hg = np.zeros(om.ncon), np.zeros(om.nnzj), np.zeros(om.nnzh)
+    f, g = 0.0, np.zeros(om.nvar)
+    for rank in range(world):
+        m = ex.ExaModel(core, device=0, rank=rank, world=world)
+        segs = {}
+        for which in range(3):
+            arr = (ex.lib.Segment * 4096)()
+            n = m.L.iexa_segments(m.h, which, arr, 4096)
+            segs[which] = [(s.global_start, s.local_start, s.length) for s in arr[:n]]
+        yl = np.zeros(max(m.loc_ncon, 1))
+        for gs, ls, ln in segs[0]:
+            yl[ls:ls + ln] = y[gs:gs + ln]
+        c = torch.zeros(max(m.loc_ncon, 1), dtype=torch.float64, device="cuda")
+        jv = torch.zeros(max(m.loc_nnzj, 1), dtype=torch.float64, device="cuda")
+        hv = torch.zeros(max(m.loc_nnzh, 1), dtype=torch.float64, device="cuda")
+        gd = torch.zeros(om.nvar, dtype=torch.float64, device="cuda")
+        ex.cons_(m, xd, c); ex.jac_coord_(m, xd, jv); ex.hess_coord_(m, xd, torch.from_numpy(yl).cuda(), hv, 0.7)
+        f += ex.obj(m, xd); g += ex.grad_(m, xd, gd).cpu().numpy()
+        for (arrg, loc, which) in ((cg, c, 0), (jg, jv, 1), (hg, hv, 2)):
+            l = loc.cpu().numpy()
+            for gs, ls, ln in segs[which]:
+                arrg[gs:gs + ln] = l[ls:ls + ln]
+        # local structure: rows are global row numbers of the owned rows
+        r = torch.zeros(max(m.loc_nnzj, 1), dtype=torch.int64, device="cuda"); cc = torch.zeros_like(r)
+        ex.jac_structure_(m, r, cc)
+        ro, co = om.jac_structure()
+        rl, cl = r.cpu().numpy(), cc.cpu().numpy()
+        for gs, ls, ln in segs[1]:
+            assert (rl[ls:ls + ln] == ro[gs:gs + ln]).all() and (cl[ls:ls + ln] == co[gs:gs + ln]).all()
+    assert_close(cg, om.cons(x), "cons"); assert_close(jg, om.jac_coord(x), "jac"); assert_close(hg, om.hess_coord(x, y, 0.7), "hess")
+    assert abs(f - om.obj(x)) <= 1e-12 * abs(om.obj(x)) + 1e-14
+    assert np.allclose(g, om.grad(x), rtol=1e-12, atol=1e-14)
