@@ -211,6 +211,10 @@ int64_t iexa_algorithmic_bytes(const iexa_plan *p, int32_t which);
 /* number of kernel launches one call of callback `which` performs                      */
 int32_t iexa_launches_per_call(const iexa_plan *p, int32_t which);
 
+/* why run-time specialisation is not in use for this plan ("" when it is): NVRTC/driver missing,
+ * compile error, or the generated source exceeded the compile budget                      */
+const char *iexa_engine_note(const iexa_plan *p);
+
 /* ---- diagnostics: the CUDA translation unit that iexa_finalize specialises with NVRTC.
  *      _source returns its length (copies up to cap-1 bytes); _compile runs NVRTC for sm_100a
  *      without loading the image (works on a machine without a GPU).                       */

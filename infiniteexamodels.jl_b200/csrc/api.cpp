@@ -364,6 +364,8 @@ int32_t iexa_debug_codegen_compile(const iexa_plan *p, int64_t *cubin_bytes) {
   GUARD_END
 }
 
+const char *iexa_engine_note(const iexa_plan *p) { return (p && p->engine) ? p->engine->note() : ""; }
+
 int32_t iexa_launches_per_call(const iexa_plan *p, int32_t which) {
   if (!p || !p->engine) return 0;
   return p->engine->launches(which);

@@ -390,7 +390,7 @@ class CudaEngine : public Engine {
     return n;
   }
   int n_specialised() const override { return spec_ ? spec_->n_kernels() : 0; }
-  const std::string &spec_error() const { return spec_error_; }
+  const char *note() const override { return spec_error_.c_str(); }
 
  private:
   struct Table {

@@ -29,6 +29,7 @@ struct Engine {
   virtual int set_par(int64_t off, int64_t n, const double *vals, std::string &err) = 0;
   virtual int launches(int cb) const = 0;
   virtual int n_specialised() const = 0;
+  virtual const char *note() const = 0; // why specialisation was skipped, or ""
 };
 
 // engine.cu; returns nullptr and fills err when no CUDA device / kernel image is usable

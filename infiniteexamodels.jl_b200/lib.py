@@ -36,7 +36,7 @@ SYMBOLS = [
     "iexa_set_par", "iexa_get_par", "iexa_jac_structure", "iexa_hess_structure", "iexa_obj",
     "iexa_grad", "iexa_cons", "iexa_jac_coord", "iexa_hess_coord", "iexa_jprod", "iexa_jtprod",
     "iexa_hprod", "iexa_obj_device", "iexa_segments", "iexa_shared_vars", "iexa_algorithmic_bytes",
-    "iexa_launches_per_call", "iexa_debug_codegen_source", "iexa_debug_codegen_compile",
+    "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_codegen_compile",
     "iexa_csr_create", "iexa_csr_destroy", "iexa_csr_nnz", "iexa_csr_pattern", "iexa_csr_apply",
 ]
 
@@ -81,6 +81,7 @@ def _declare(L):
     sig("iexa_shared_vars", _i64, _vp, _vp, _i64)
     sig("iexa_algorithmic_bytes", _i64, _vp, _i32)
     sig("iexa_launches_per_call", _i32, _vp, _i32)
+    sig("iexa_engine_note", C.c_char_p, _vp)
     sig("iexa_debug_codegen_source", _i64, _vp, _vp, _i64)
     sig("iexa_debug_codegen_compile", _i32, _vp, C.POINTER(_i64))
     sig("iexa_csr_create", _i32, C.POINTER(_vp), _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32)

@@ -1,33 +1,67 @@
-"""scratch timing of the three callbacks at large N (not a test)."""
-import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
-import iexa_b200 as ex
-from iexa_b200 import models
+"""scratch timing of the callbacks on any config model (not a test).
 
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-t0 = time.time(); core = models.quadrotor(N, "oc"); t1 = time.time()
-m = ex.ExaModel(core, device=0, flags=flags); t2 = time.time()
-print(f"N={N} build core {t1-t0:.2f}s plan+finalize {t2-t1:.2f}s nvar={m.meta.nvar} ncon={m.meta.ncon} nnzj={m.meta.nnzj} nnzh={m.meta.nnzh} spec={m.cmeta.n_kernels_specialised}")
+usage: python tests/quick_bench.py <model> <size> [flags]
+  model: quad | quadfd | pandemic | pandemic128 | opf | opf30 | farmer
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import iexa_b200 as ex
+from iexa_b200 import models, opf
+from iexa_b200.transform import exa_core
+
+name = sys.argv[1] if len(sys.argv) > 1 else "quad"
+if name.isdigit():  # backwards compatible: quick_bench.py <N> [flags]
+    name, N, flags = "quad", int(sys.argv[1]), int(sys.argv[2]) if len(sys.argv) > 2 else 0
+else:
+    N = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+    flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+t0 = time.time()
+core = {"quad": lambda: models.quadrotor(N, "oc"), "quadfd": lambda: models.quadrotor(N, "fd"),
+        "pandemic": lambda: models.pandemic(N, 4), "pandemic128": lambda: models.pandemic(N, 128),
+        "opf": lambda: exa_core(opf.opf(None, num_supports=N))[0],
+        "opf30": lambda: exa_core(opf.opf(opf.synthetic_grid(30), num_supports=N))[0],
+        "farmer": lambda: models.farmer(N)}[name]()
+t1 = time.time()
+m = ex.ExaModel(core, device=0, flags=flags)
+t2 = time.time()
+print(f"{name} N={N} build core {t1-t0:.2f}s plan+finalize {t2-t1:.2f}s nvar={m.meta.nvar} ncon={m.meta.ncon} "
+      f"nnzj={m.meta.nnzj} nnzh={m.meta.nnzh} gens={m.cmeta.nobj_gen + m.cmeta.ncon_gen} spec={m.cmeta.n_kernels_specialised} "
+      f"note={m.L.iexa_engine_note(m.h).decode()[:80]!r}")
 rng = np.random.default_rng(0)
-x = torch.from_numpy(core.x0_vec + 0.1 * rng.uniform(-1, 1, core.nvar)).cuda()
+x0 = np.where(np.isfinite(core.x0_vec), core.x0_vec, 0.0)
+x = torch.from_numpy(x0 + 0.1 * rng.uniform(-1, 1, core.nvar)).cuda()
 y = torch.from_numpy(rng.uniform(-1, 1, core.ncon)).cuda()
-c = torch.zeros(m.meta.ncon, dtype=torch.float64, device="cuda")
-jv = torch.zeros(m.meta.nnzj, dtype=torch.float64, device="cuda")
-hv = torch.zeros(m.meta.nnzh, dtype=torch.float64, device="cuda")
+c = torch.zeros(max(m.meta.ncon, 1), dtype=torch.float64, device="cuda")
+jv = torch.zeros(max(m.meta.nnzj, 1), dtype=torch.float64, device="cuda")
+hv = torch.zeros(max(m.meta.nnzh, 1), dtype=torch.float64, device="cuda")
 g = torch.zeros(m.meta.nvar, dtype=torch.float64, device="cuda")
-def timeit(fn, n=10):
-    for _ in range(3): fn()
+
+
+def timeit(fn, n=20):
+    for _ in range(3):
+        fn()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(n): fn()
+    for _ in range(n):
+        fn()
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / n
+
+
 tb = time.time(); B = [ex.algorithmic_bytes(m, w) for w in range(5)]; print("bytes", B, f"({time.time()-tb:.1f}s)")
-for name, fn, w in (("cons", lambda: ex.cons_(m, x, c), 2), ("jac", lambda: ex.jac_coord_(m, x, jv), 3),
-                    ("hess", lambda: ex.hess_coord_(m, x, y, hv), 4), ("grad", lambda: ex.grad_(m, x, g), 1),
-                    ("obj", lambda: ex.obj(m, x), 0)):
+tot = 0.0
+for nm, fn, w in (("cons", lambda: ex.cons_(m, x, c), 2), ("jac", lambda: ex.jac_coord_(m, x, jv), 3),
+                  ("hess", lambda: ex.hess_coord_(m, x, y, hv), 4), ("grad", lambda: ex.grad_(m, x, g), 1),
+                  ("obj", lambda: ex.obj(m, x), 0)):
     ms = timeit(fn)
-    print(f"{name}: {ms:.3f} ms  {B[w]/ms/1e6:.1f} GB/s  frac_of_6552={B[w]/ms/1e6/6552:.3f}")
+    if w >= 2:
+        tot += ms
+    print(f"{nm}: {ms:.4f} ms  {B[w]/ms/1e6:.1f} GB/s  frac_of_6552={B[w]/ms/1e6/6552:.3f}")
+print(f"cons+jac+hess: {tot:.4f} ms -> {1e3/tot:.0f} evals/s, {sum(B[2:])/tot/1e6:.0f} GB/s ({sum(B[2:])/tot/1e6/6552:.3f} of 6552)")

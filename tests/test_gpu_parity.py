@@ -181,3 +181,37 @@ def test_sharded_plans_tile_the_model_on_one_gpu(world, oracle_cache):
     assert_close(cg, om.cons(x), "cons"); assert_close(jg, om.jac_coord(x), "jac"); assert_close(hg, om.hess_coord(x, y, 0.7), "hess")
     assert abs(f - om.obj(x)) <= 1e-12 * abs(om.obj(x)) + 1e-14
     assert np.allclose(g, om.grad(x), rtol=1e-12, atol=1e-14)
+
+
+def test_opf_case3_and_interpreter_budget_fallback(oracle_cache):
+    """BASELINE configs[3] (ESCAPE34/opf.jl, embedded 3-bus case) through the general lowering; and a
+    30-bus grid whose generated source exceeds the NVRTC budget: it must run on the AOT interpreter
+    kernels (GPU), say why, and still match the oracle."""
+    import torch
+    from iexa_b200 import opf
+    from iexa_b200.transform import exa_core
+    from oracle.oracle import OracleModel
+    for case, K, expect_spec in ((None, 64, True), (opf.synthetic_grid(30), 9, False)):
+        core, _ = exa_core(opf.opf(case, num_supports=K))
+        om = OracleModel(core)
+        m = ex.ExaModel(core, device=0)
+        note = m.L.iexa_engine_note(m.h).decode()
+        assert (m.cmeta.n_kernels_specialised > 0) == expect_spec, note
+        if not expect_spec:
+            assert "budget" in note
+        x, y = eval_point(core, seed=1)
+        x = np.where(np.isfinite(x), x, 0.0)
+        xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+        c = torch.zeros(om.ncon, dtype=torch.float64, device="cuda")
+        jv = torch.zeros(om.nnzj, dtype=torch.float64, device="cuda")
+        hv = torch.zeros(om.nnzh, dtype=torch.float64, device="cuda")
+        g = torch.zeros(om.nvar, dtype=torch.float64, device="cuda")
+        assert_close(ex.cons_(m, xd, c).cpu().numpy(), om.cons(x), "cons")
+        assert_close(ex.jac_coord_(m, xd, jv).cpu().numpy(), om.jac_coord(x), "jac")
+        assert_close(ex.hess_coord_(m, xd, yd, hv, 0.9).cpu().numpy(), om.hess_coord(x, y, 0.9), "hess")
+        assert_close(ex.grad_(m, xd, g).cpu().numpy(), om.grad(x), "grad")
+        assert_close(ex.obj(m, xd), om.obj(x), "obj")
+        r = torch.zeros(om.nnzh, dtype=torch.int32, device="cuda"); cc = torch.zeros_like(r)
+        ex.hess_structure_(m, r, cc)
+        ro, co = om.hess_structure()
+        assert (r.cpu().numpy() == ro).all() and (cc.cpu().numpy() == co).all()
