@@ -193,10 +193,15 @@ def main():
     jv = torch.empty(max(m.loc_nnzj, 1), dtype=torch.float64, device=dev)
     hv = torch.empty(max(m.loc_nnzh, 1), dtype=torch.float64, device=dev)
 
+    # buffers are bound once (raw pointers + stream), like a Julia ccall on CuArray pointers: every
+    # callback below is exactly one call into the C ABI
+    from iexa_b200.model import bind
+    f_cons = bind(m, "cons", x, c)
+    f_jac = bind(m, "jac_coord", x, jv)
+    f_hess = bind(m, "hess_coord", x, hv, y, 1.0)
+
     def step():
-        ex.cons_(m, x, c)
-        ex.jac_coord_(m, x, jv)
-        ex.hess_coord_(m, x, y, hv, 1.0)
+        f_cons(); f_jac(); f_hess()
 
     def barrier():
         if world > 1:
@@ -213,9 +218,9 @@ def main():
     barrier()
     t_wall = time.perf_counter()
     for i in range(args.steps):  # per-callback events on the launching (current torch) stream
-        ev[i][0].record(); ex.cons_(m, x, c)
-        ev[i][1].record(); ex.jac_coord_(m, x, jv)
-        ev[i][2].record(); ex.hess_coord_(m, x, y, hv, 1.0)
+        ev[i][0].record(); f_cons()
+        ev[i][1].record(); f_jac()
+        ev[i][2].record(); f_hess()
         ev[i][3].record()
     barrier()
     t_wall = time.perf_counter() - t_wall
@@ -237,8 +242,10 @@ def main():
         jp = torch.empty(max(m.loc_nnzj, 1), dtype=torch.float64).pin_memory()
         hp = torch.empty(max(m.loc_nnzh, 1), dtype=torch.float64).pin_memory()
 
+        h_cons, h_jac, h_hess = bind(m, "cons", xp, cp), bind(m, "jac_coord", xp, jp), bind(m, "hess_coord", xp, hp, yp, 1.0)
+
         def step_host():
-            ex.cons_(m, xp, cp); ex.jac_coord_(m, xp, jp); ex.hess_coord_(m, xp, yp, hp, 1.0)
+            h_cons(); h_jac(); h_hess()
 
         n_e2e = max(2, min(args.steps, 5))
         step_host()

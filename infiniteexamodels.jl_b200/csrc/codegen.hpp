@@ -30,6 +30,7 @@ struct GeneratedSource {
   size_t smem_bytes[5] = {0, 0, 0, 0, 0};
 };
 
+int spec_block(); // threads per block of the specialised kernels (env IEXA_BLOCK, default 128)
 GeneratedSource generate_source(const Plan &plan);
 bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string &err);
 

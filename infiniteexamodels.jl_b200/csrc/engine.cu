@@ -573,9 +573,21 @@ class CudaEngine : public Engine {
       for (int gi : spec_->groups_of(cb)) {
         const Group &G = plan_.groups[gi];
         int64_t n = G.k1 - G.k0;
-        int64_t nb = (n + BLOCK - 1) / BLOCK;
+        const int64_t SB = spec_block();
+        int64_t nb = (n + SB - 1) / SB;
         for (int64_t b = 0; b < nb; ++b) ord.push_back(Ord{(b + 0.5) / (double)nb, gi, (int32_t)b});
       }
+      // When this rank's slice of x fits comfortably in L2 (small shards of a multi-GPU run) reuse
+      // comes for free and the tail matters instead: run the heaviest groups first (longest
+      // processing time first) so that the kernel drains on short blocks.
+      const char *oe = getenv("IEXA_ORDER");
+      bool lpt = oe ? oe[0] == 'l' : false;
+      if (lpt) {
+        const int prog = (cb == CB_OBJ || cb == CB_CONS) ? PROG_VAL : (cb == CB_GRAD || cb == CB_JAC) ? PROG_D1 : PROG_D2;
+        std::stable_sort(ord.begin(), ord.end(), [&](const Ord &a, const Ord &b) {
+          return plan_.groups[a.gi].prog[prog].code.size() > plan_.groups[b.gi].prog[prog].code.size();
+        });
+      } else
       std::stable_sort(ord.begin(), ord.end(), [](const Ord &a, const Ord &b) { return a.frac < b.frac; });
       for (const Ord &o : ord) items.push_back(WorkItem{o.gi, o.b});
     }

@@ -245,3 +245,39 @@ def algorithmic_bytes(m: ExaModel, which: int) -> int:
 
 def launches_per_call(m: ExaModel, which: int) -> int:
     return int(m.L.iexa_launches_per_call(m.h, which))
+
+
+# ---- pre-bound callbacks ------------------------------------------------------------------------
+class BoundCall:
+    """A callback with its buffers resolved once (raw pointers, memory space, stream), so that each
+    call is ONE foreign call — what a Julia ``ccall`` on ``CuArray`` pointers costs.  Use when the
+    solver reuses the same vectors every iteration (MadNLP and Ipopt both do)."""
+
+    __slots__ = ("_f", "_args", "_m", "_keep")
+
+    def __init__(self, m: ExaModel, fn, args, keep):
+        self._m, self._f, self._args, self._keep = m, fn, args, keep
+
+    def __call__(self):
+        rc = self._f(*self._args)
+        if rc:
+            _lib.check(self._m.L, rc)
+
+
+def bind(m: ExaModel, name: str, x, out, y=None, obj_weight: float = 1.0) -> BoundCall:
+    """``bind(m, "cons", x, c)``, ``bind(m, "jac_coord", x, vals)``, ``bind(m, "hess_coord", x, vals, y, σ)``,
+    ``bind(m, "grad", x, g)``"""
+    bx, bo, by = m._buf(x, m.meta.nvar), m._buf(out), m._buf(y)
+    ms, st = m._pair(bx, bo, by) if y is not None else m._pair(bx, bo)
+    h = m.h
+    L = m.L
+    vp = C.c_void_p
+    if name == "cons":
+        return BoundCall(m, L.iexa_cons, (h, vp(bx[0]), vp(bo[0]), ms, vp(st)), (x, out))
+    if name == "jac_coord":
+        return BoundCall(m, L.iexa_jac_coord, (h, vp(bx[0]), vp(bo[0]), ms, vp(st)), (x, out))
+    if name == "grad":
+        return BoundCall(m, L.iexa_grad, (h, vp(bx[0]), vp(bo[0]), ms, vp(st)), (x, out))
+    if name == "hess_coord":
+        return BoundCall(m, L.iexa_hess_coord, (h, vp(bx[0]), vp(by[0]), C.c_double(obj_weight), vp(bo[0]), ms, vp(st)), (x, out, y))
+    raise ValueError(name)
