@@ -99,10 +99,11 @@ class ClockSampler:
 def cpu_eval_rate(sample_supports: int, full_supports: int, threads: int, reps: int = 2):
     """evals/s of the oracle (CPU restatement of the reference evaluator) on a bounded sample,
     scaled linearly to the full support count."""
-    os.environ["OMP_NUM_THREADS"] = str(threads)
     import iexa_b200 as ex  # noqa: F401  (models only; the oracle does the arithmetic)
     from iexa_b200 import models
+    from oracle import oracle as orc
     from oracle.oracle import OracleModel
+    orc.set_threads(threads)
     core = models.quadrotor(sample_supports, "oc")
     om = OracleModel(core)
     rng = np.random.default_rng(0)
@@ -123,11 +124,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     # each "step" is one eval of the bounded sample; K steps after W warm-ups
-    os.environ["OMP_NUM_THREADS"] = str(threads)
     from iexa_b200 import models
+    from oracle import oracle as orc
     from oracle.oracle import OracleModel
+    orc.set_threads(threads)
     ns = args.cpu_sample
     core = models.quadrotor(ns, "oc")
     om = OracleModel(core)

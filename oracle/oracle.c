@@ -29,6 +29,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -85,6 +88,22 @@ static int64_t idx_val(const ogen *g, int id, int64_t k) {
   int64_t v = e->base;
   for (int t = 0; t < e->nterms; ++t) v += e->coef[t] * g->ic[e->col[t]][k];
   return v;
+}
+
+/* thread count of the OpenMP loops over supports (1 = the sequential loops of ExaModels' CPU backend) */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n > 0 ? n : 1);
+#else
+  (void)n;
+#endif
+}
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
 }
 
 omodel *orc_create(void) { return (omodel *)calloc(1, sizeof(omodel)); }

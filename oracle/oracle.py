@@ -32,6 +32,8 @@ def lib():
         L = C.CDLL(build())
         vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
         L.orc_create.restype = vp
+        L.orc_set_threads.argtypes = [i32]
+        L.orc_max_threads.restype = i32
         L.orc_free.argtypes = [vp]
         L.orc_set_dims.argtypes = [vp, i64, i64, vp]
         L.orc_set_theta.argtypes = [vp, i64, i64, vp]
@@ -59,6 +61,16 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def set_threads(n: int) -> None:
+    """OpenMP threads of the oracle's loops over supports (omp_set_num_threads: works even when another
+    library initialised libgomp first)"""
+    lib().orc_set_threads(int(n))
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
 
 
 class OracleModel:
