@@ -14,7 +14,7 @@
  *   - indices handed to the caller (rows/cols, offsets) are 1-based like the Julia
  *     solvers expect; index expressions in tapes are 1-based as in transform.jl.
  *   - `memspace` says where the caller's buffers live (IEXA_MEM_HOST / IEXA_MEM_DEVICE).
- *     Host buffers are staged through pinned memory and copied inside the call.
+ *     Host buffers are copied inside the call (see iexa_host_register for page-locking).
  *   - `stream` is a cudaStream_t cast to void* (NULL = legacy default stream).  Device
  *     calls are asynchronous on that stream except where a scalar is returned (iexa_obj).
  *   - the engine never keeps caller pointers after a call returns.
@@ -191,6 +191,12 @@ int32_t iexa_hprod(iexa_plan *p, const double *x, const double *y, const double 
                    double obj_weight, double *Hv, int32_t memspace, void *stream);
 /* device-side objective partial (no host sync): writes 1 double to f_dev               */
 int32_t iexa_obj_device(iexa_plan *p, const double *x_dev, double *f_dev, void *stream);
+
+/* Optional page-locking of caller-owned HOST vectors that are reused on every iteration (the
+ * Ipopt-style path): host<->device copies then run at PCIe speed.  Explicit because only the
+ * caller knows the buffers' lifetime; unregister before freeing them.                       */
+int32_t iexa_host_register(iexa_plan *p, void *buf, int64_t bytes);
+int32_t iexa_host_unregister(iexa_plan *p, void *buf);
 
 /* ---- sharding queries (world > 1).  A segment maps a contiguous local range of rows /
  *      Jacobian slots / Hessian slots to its position in the global (unsharded) arrays. */

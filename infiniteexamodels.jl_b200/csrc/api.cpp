@@ -244,6 +244,13 @@ int32_t iexa_hprod(iexa_plan *p, const double *x, const double *y, const double 
   ENGINE_CALL(hprod(x, y, v, obj_weight, Hv, memspace, stream, err))
 }
 
+int32_t iexa_host_register(iexa_plan *p, void *buf, int64_t bytes) {
+  ENGINE_CALL(host_register(buf, (size_t)bytes, err))
+}
+int32_t iexa_host_unregister(iexa_plan *p, void *buf) {
+  ENGINE_CALL(host_unregister(buf, err))
+}
+
 // ---- sharding queries ----------------------------------------------------------------------------
 int64_t iexa_segments(const iexa_plan *p, int32_t which, iexa_segment *out, int64_t cap) {
   if (!p || !p->plan.finalized) return -1;

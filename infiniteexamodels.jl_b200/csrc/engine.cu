@@ -602,34 +602,41 @@ class CudaEngine : public Engine {
   }
 
   // ---- helpers -------------------------------------------------------------------------------
-  void try_register(const void *p, size_t bytes) {
-    // pin caller-owned host buffers once so the H2D/D2H copies run at PCIe speed; solvers reuse
-    // the same x / c / vals vectors on every iteration
-    if (!p || bytes < (1u << 16)) return;
-    auto it = registered_.find((void *)p);
-    if (it != registered_.end() && it->second >= bytes) return;
+  // Page-locking is EXPLICIT (iexa_host_register): the caller knows the lifetime of its vectors.  (Pinning
+  // behind the caller's back is unsafe: freed-and-remapped host memory would keep a stale registration.)
+ public:
+  int host_register(void *p, size_t bytes, std::string &err) override {
+    CK(cudaSetDevice(device_));
+    if (!p || bytes == 0) { err = "null buffer"; return IEXA_ERR_INVALID; }
+    if (registered_.count(p)) return IEXA_OK;
     cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return IEXA_OK; // already pinned
     cudaGetLastError();
-    if (it != registered_.end()) { cudaHostUnregister(it->first); registered_.erase(it); }
-    if (registered_.size() >= 32) return;
-    if (cudaHostRegister((void *)p, bytes, cudaHostRegisterDefault) == cudaSuccess) registered_[(void *)p] = bytes;
-    else cudaGetLastError();
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    registered_[p] = bytes;
+    return IEXA_OK;
+  }
+  int host_unregister(void *p, std::string &err) override {
+    CK(cudaSetDevice(device_));
+    auto it = registered_.find(p);
+    if (it == registered_.end()) return IEXA_OK;
+    CK(cudaHostUnregister(p));
+    registered_.erase(it);
+    return IEXA_OK;
   }
 
+ private:
   int in(const double *src, int64_t n, int memspace, DevBuf &stage, cudaStream_t st, const double *&dev,
          std::string &err) {
     if (!src) { dev = nullptr; return IEXA_OK; }
     if (memspace == IEXA_MEM_DEVICE) { dev = src; return IEXA_OK; }
     CK(stage.ensure((size_t)n * 8));
-    try_register(src, (size_t)n * 8);
     CK(cudaMemcpyAsync(stage.p, src, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     dev = stage.as<double>();
     return IEXA_OK;
   }
   int out(double *dst, const double *dev, int64_t n, int memspace, cudaStream_t st, std::string &err) {
     if (memspace == IEXA_MEM_DEVICE) return IEXA_OK;
-    try_register(dst, (size_t)n * 8);
     CK(cudaMemcpyAsync(dst, dev, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return IEXA_OK;

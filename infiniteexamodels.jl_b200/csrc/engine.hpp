@@ -27,6 +27,8 @@ struct Engine {
   virtual int hprod(const double *x, const double *y, const double *v, double sigma, double *Hv,
                     int memspace, void *stream, std::string &err) = 0;
   virtual int set_par(int64_t off, int64_t n, const double *vals, std::string &err) = 0;
+  virtual int host_register(void *p, size_t bytes, std::string &err) = 0;
+  virtual int host_unregister(void *p, std::string &err) = 0;
   virtual int launches(int cb) const = 0;
   virtual int n_specialised() const = 0;
   virtual const char *note() const = 0; // why specialisation was skipped, or ""
