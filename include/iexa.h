@@ -225,6 +225,8 @@ const char *iexa_engine_note(const iexa_plan *p);
  *      _source returns its length (copies up to cap-1 bytes); _compile runs NVRTC for sm_100a
  *      without loading the image (works on a machine without a GPU).                       */
 int64_t iexa_debug_codegen_source(const iexa_plan *p, char *buf, int64_t cap);
+/* regroup a host-only plan with (1) / without (0) shape canonicalisation before inspecting its source */
+int32_t iexa_debug_set_class_mode(iexa_plan *p, int32_t on);
 int32_t iexa_debug_codegen_compile(const iexa_plan *p, int64_t *cubin_bytes);
 
 /* ---- COO -> CSR value permutation feeding cuDSS (today MadNLPGPU's transfer! kernel,

@@ -359,6 +359,15 @@ int64_t iexa_debug_codegen_source(const iexa_plan *p, char *buf, int64_t cap) {
   }
   return (int64_t)src.size();
 }
+int32_t iexa_debug_set_class_mode(iexa_plan *p, int32_t on) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (!p->plan.finalized) return fail(IEXA_ERR_STATE, "plan not finalized");
+  if (p->engine) return fail(IEXA_ERR_STATE, "only for plans finalized with IEXA_F_NO_DEVICE");
+  p->plan.build_groups(on != 0);
+  return IEXA_OK;
+  GUARD_END
+}
 int32_t iexa_debug_codegen_compile(const iexa_plan *p, int64_t *cubin_bytes) {
   GUARD_BEGIN
   NEED_PLAN(p);

@@ -18,7 +18,7 @@
 namespace iexa {
 
 // entries of the generated kernels' __constant__ table (values are resolved per rank at load)
-enum { CI_K0 = 0, CI_K1, CI_IDX_BASE, CI_ICOL_PTR, CI_FCOL_PTR, CI_MEM_ROWLOC, CI_MEM_OUT };
+enum { CI_K0 = 0, CI_K1, CI_IDX_BASE, CI_ICOL_PTR, CI_FCOL_PTR, CI_MEM_ROWLOC, CI_MEM_OUT, CI_CLS_NBLK, CI_CLS_ITAB, CI_CLS_DTAB };
 struct CiEntry {
   int kind, group, a, b;
 };
@@ -39,7 +39,8 @@ class Specialiser {
   Specialiser();
   ~Specialiser();
   // col_dev_ptr[c]: device address of Plan::columns[c] (nullptr for iota columns)
-  bool build(const Plan &plan, const std::vector<const void *> &col_dev_ptr, std::string &err);
+  // may switch the plan to class mode (shape canonicalisation) when the source would exceed the budget
+  bool build(Plan &plan, const std::vector<const void *> &col_dev_ptr, std::string &err);
   bool has(int cb) const { return cb >= 0 && cb < 5 && fn_[cb] != nullptr; }
   const std::vector<int> &groups_of(int cb) const { return groups_of_[cb]; }
   bool launch(int cb, int nblocks, const WorkItem *work, const double *x, const double *theta,
@@ -50,6 +51,7 @@ class Specialiser {
 
  private:
   void *module_ = nullptr; // CUmodule
+  std::vector<unsigned long long> dev_allocs_; // instance tables of class groups
   void *fn_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t smem_[5] = {0, 0, 0, 0, 0};
   std::vector<int> groups_of_[5];

@@ -76,6 +76,8 @@ class GenCompiler {
   }
 
   GenCompiled g;
+  // shape classes: tape node -> per-instance constant parameter index (or -1 = literal); see plan.hpp
+  const std::vector<int32_t> *cpar_of_node = nullptr;
 
   // symbolic AD into the Dag; afterwards val_root()/slot1()/slot2() name the outputs
   void differentiate() {
@@ -265,7 +267,9 @@ class GenCompiler {
       const iexa_node &nd = g.tape[i];
       Info &in = info_[i];
       switch (nd.op) {
-        case IEXA_OP_CONST: val_[i] = d.cnst(nd.c); continue;
+        case IEXA_OP_CONST:
+          val_[i] = (cpar_of_node && (*cpar_of_node)[i] >= 0) ? d.cpar((*cpar_of_node)[i]) : d.cnst(nd.c);
+          continue;
         case IEXA_OP_FIELD: val_[i] = d.field(ctx_.fcolslot[nd.a]); continue;
         case IEXA_OP_VAR: val_[i] = d.loadx(g.idx_map[nd.a]); continue;
         case IEXA_OP_PAR: val_[i] = d.loadp(g.idx_map[nd.a]); continue;

@@ -9,6 +9,7 @@
 // o2_g + o2step_g*k + c with all OBJECTIVE generators first.
 #pragma once
 #include <cmath>
+#include <cstring>
 #include <limits>
 #include <memory>
 #include <string>
@@ -64,6 +65,14 @@ struct Group {
   std::vector<std::vector<int32_t>> jac_slot;         // per member: group index slot of each first-order slot
   std::vector<uint8_t> x_slots[3];
   size_t dag_nodes = 0;
+  // Shape class (build_groups(class_mode = true)): ONE member program shared by many generators of
+  // identical shape — same tape structure, columns and index-term structure; they differ only in
+  // literal constants, index bases and output offsets, which become per-instance table entries.
+  // This is what turns the reference's "one generator per bus / branch constraint" launch storm
+  // (ESCAPE34/opf.jl:150-283) into a handful of kernel bodies with an instance axis.
+  bool is_class = false;
+  std::vector<int32_t> inst_gens;   // generator index of every instance (members[0] == inst_gens[0])
+  std::vector<int32_t> cpar_nodes;  // tape node ids whose literal differs between instances
 };
 
 struct Plan {
@@ -223,39 +232,103 @@ struct Plan {
     finalized = true;
   }
 
-  // fuse generators that share (kind, iterator); a group is closed when it grows past the caps
-  void build_groups(size_t max_dag_nodes = 6000, int max_slots = 96) {
+  // shape key of a generator: everything except literal values, index bases and bounds
+  static std::string shape_key(const Generator &g) {
+    std::string k;
+    auto put = [&](int64_t v) { k.append(reinterpret_cast<const char *>(&v), sizeof v); };
+    put(g.itr); put((int64_t)g.c.tape.size());
+    for (const iexa_node &n : g.c.tape) { put(n.op); if (n.op != IEXA_OP_CONST && n.op != IEXA_OP_VAR && n.op != IEXA_OP_PAR) { put(n.a); put(n.b); } }
+    // leaves: which index SLOT each VAR/PAR leaf uses (identity pattern) and each slot's term structure
+    for (const iexa_node &n : g.c.tape) if (n.op == IEXA_OP_VAR || n.op == IEXA_OP_PAR) put(g.c.idx_map[n.a]);
+    for (const IndexExpr &e : g.c.uidx) { put((int64_t)e.terms.size()); for (auto &t : e.terms) { put(t.first); put(t.second); } }
+    for (int32_t c : g.c.int_cols) put(c);
+    for (int32_t c : g.c.fp_cols) put(c);
+    for (int32_t s : g.c.jac_slot) put(s);
+    for (auto &pr : g.c.hess_slot) { put(pr.first); put(pr.second); }
+    return k;
+  }
+
+  // Fuse generators that share (kind, iterator); a group is closed when it grows past the caps.
+  // class_mode: generators of identical SHAPE (>= min_inst of them) become one class group first.
+  void build_groups(bool class_mode = false, size_t min_inst = 4, size_t max_dag_nodes = 6000, int max_slots = 96) {
     groups.clear();
     for (int pass = 0; pass < 2; ++pass) {
       std::vector<Generator> &gens = pass == 0 ? objs : cons;
+      std::vector<uint8_t> taken(gens.size(), 0);
+      if (class_mode) {
+        std::map<std::string, std::vector<int32_t>> classes;
+        std::vector<std::string> order;
+        for (size_t gi = 0; gi < gens.size(); ++gi) {
+          std::string key = shape_key(gens[gi]);
+          if (!classes.count(key)) order.push_back(key);
+          classes[key].push_back((int32_t)gi);
+        }
+        for (const std::string &key : order) {
+          const std::vector<int32_t> &inst = classes[key];
+          if (inst.size() < min_inst) continue;
+          const Generator &g0 = gens[inst[0]];
+          const Iterator &it = itrs[g0.itr];
+          groups.emplace_back();
+          Group &G = groups.back();
+          G.is_obj = pass == 0; G.itr = g0.itr; G.K = g0.K; G.k0 = g0.k0; G.k1 = g0.k1;
+          G.is_class = true; G.inst_gens = inst; G.members.push_back(inst[0]);
+          // literals that differ between instances become parameters
+          std::vector<int32_t> cpar(g0.c.tape.size(), -1);
+          for (size_t n = 0; n < g0.c.tape.size(); ++n) {
+            if (g0.c.tape[n].op != IEXA_OP_CONST) continue;
+            bool same = true;
+            for (int32_t gi : inst) if (std::memcmp(&gens[gi].c.tape[n].c, &g0.c.tape[n].c, 8) != 0) { same = false; break; }
+            if (!same) { cpar[n] = (int32_t)G.cpar_nodes.size(); G.cpar_nodes.push_back((int32_t)n); }
+          }
+          Dag dag;
+          GenCompiler gc(g0.c.tape.data(), (int32_t)g0.c.tape.size(), g0.c.raw_idx.data(), (int32_t)g0.c.raw_idx.size(),
+                         (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size(), G.ctx, dag, 0);
+          gc.cpar_of_node = &cpar;
+          gc.differentiate();
+          // a parameter that happens to be 0/1 in g0 must not have been folded: slot counts must match
+          if ((int)gc.slot1().size() != g0.c.o1step || (int)gc.slot2().size() != g0.c.o2step)
+            throw std::logic_error("shape class: sparsity of the parametrised program differs from its instances");
+          G.jac_slot.push_back(gc.g.jac_slot);
+          std::vector<int> o0{gc.val_root()};
+          G.outmap[0].push_back({0, 0});
+          for (size_t c = 0; c < gc.slot1().size(); ++c) G.outmap[1].push_back({0, (int32_t)c});
+          for (size_t c = 0; c < gc.slot2().size(); ++c) G.outmap[2].push_back({0, (int32_t)c});
+          G.prog[0] = schedule(dag, o0, G.ctx.uidx.size(), G.x_slots[0]);
+          G.prog[1] = schedule(dag, gc.slot1(), G.ctx.uidx.size(), G.x_slots[1]);
+          G.prog[2] = schedule(dag, gc.slot2(), G.ctx.uidx.size(), G.x_slots[2]);
+          G.dag_nodes = dag.nodes.size();
+          for (int32_t gi : inst) taken[gi] = 1;
+        }
+      }
       std::map<int32_t, int> open; // itr -> group index
       std::vector<std::unique_ptr<Dag>> dags;
       std::vector<std::vector<int>> outs[3];
       std::vector<int> slots1, slots2;
-      size_t first_group = groups.size();
+      std::vector<int> gid_of_local; // local dag index -> group index
       for (size_t gi = 0; gi < gens.size(); ++gi) {
+        if (taken[gi]) continue;
         Generator &g = gens[gi];
         const Iterator &it = itrs[g.itr];
-        int gid = -1;
+        int li = -1;
         auto f = open.find(g.itr);
         if (f != open.end()) {
-          size_t li = f->second - first_group;
+          int cand = f->second;
           int s1 = g.c.o1step > 1 ? (g.c.o1step | 1) : 0, s2 = g.c.o2step > 1 ? (g.c.o2step | 1) : 0;
-          if (dags[li]->nodes.size() < max_dag_nodes && slots1[li] + s1 <= max_slots && slots2[li] + s2 <= max_slots)
-            gid = f->second;
+          if (dags[cand]->nodes.size() < max_dag_nodes && slots1[cand] + s1 <= max_slots && slots2[cand] + s2 <= max_slots)
+            li = cand;
         }
-        if (gid < 0) {
-          gid = (int)groups.size();
+        if (li < 0) {
+          li = (int)dags.size();
           groups.emplace_back();
           Group &G = groups.back();
           G.is_obj = pass == 0; G.itr = g.itr; G.K = g.K; G.k0 = g.k0; G.k1 = g.k1;
           dags.emplace_back(new Dag());
           for (auto &o : outs) o.emplace_back();
           slots1.push_back(0); slots2.push_back(0);
-          open[g.itr] = gid;
+          gid_of_local.push_back((int)groups.size() - 1);
+          open[g.itr] = li;
         }
-        size_t li = gid - first_group;
-        Group &G = groups[gid];
+        Group &G = groups[gid_of_local[li]];
         int mpos = (int)G.members.size();
         GenCompiler gc(g.c.tape.data(), (int32_t)g.c.tape.size(), g.c.raw_idx.data(), (int32_t)g.c.raw_idx.size(),
                        (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size(), G.ctx, *dags[li], mpos);
@@ -270,12 +343,14 @@ struct Plan {
         slots2[li] += g.c.o2step > 1 ? (g.c.o2step | 1) : 0;
       }
       for (size_t li = 0; li < dags.size(); ++li) {
-        Group &G = groups[first_group + li];
+        Group &G = groups[gid_of_local[li]];
         for (int p = 0; p < 3; ++p) G.prog[p] = schedule(*dags[li], outs[p][li], G.ctx.uidx.size(), G.x_slots[p]);
         G.dag_nodes = dags[li]->nodes.size();
       }
     }
+    class_mode_ = class_mode;
   }
+  bool class_mode_ = false;
 
   const Generator &member(const Group &G, int mpos) const { return (G.is_obj ? objs : cons)[G.members[mpos]]; }
 };

@@ -36,7 +36,7 @@ SYMBOLS = [
     "iexa_set_par", "iexa_get_par", "iexa_jac_structure", "iexa_hess_structure", "iexa_obj",
     "iexa_grad", "iexa_cons", "iexa_jac_coord", "iexa_hess_coord", "iexa_jprod", "iexa_jtprod",
     "iexa_hprod", "iexa_obj_device", "iexa_host_register", "iexa_host_unregister", "iexa_segments", "iexa_shared_vars", "iexa_algorithmic_bytes",
-    "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_codegen_compile",
+    "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_set_class_mode", "iexa_debug_codegen_compile",
     "iexa_csr_create", "iexa_csr_destroy", "iexa_csr_nnz", "iexa_csr_pattern", "iexa_csr_apply",
 ]
 
@@ -86,6 +86,7 @@ def _declare(L):
     sig("iexa_engine_note", C.c_char_p, _vp)
     sig("iexa_debug_codegen_source", _i64, _vp, _vp, _i64)
     sig("iexa_debug_codegen_compile", _i32, _vp, C.POINTER(_i64))
+    sig("iexa_debug_set_class_mode", _i32, _vp, _i32)
     sig("iexa_csr_create", _i32, C.POINTER(_vp), _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32)
     sig("iexa_csr_destroy", _i32, _vp)
     sig("iexa_csr_nnz", _i64, _vp)
@@ -95,6 +96,7 @@ def _declare(L):
     sig("hostcheck_eval", _i32, _vp, _i32, _vp, _vp, _dbl, _vp)
     sig("hostcheck_eval_local", _i32, _vp, _i32, _vp, _vp, _dbl, _vp)
     sig("hostcheck_eval_groups", _i32, _vp, _i32, _vp, _vp, _dbl, _vp, C.POINTER(_i32))
+    sig("hostcheck_set_class_mode", _i32, _vp, _i32)
     sig("hostcheck_structure", _i32, _vp, _i32, _vp, _vp)
     sig("hostcheck_gen_stats", _i32, _vp, _i32, _i32, _vp)
     return L

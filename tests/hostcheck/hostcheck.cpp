@@ -45,22 +45,23 @@ static int64_t g_int_col(const Plan &P, const Group &G, int32_t slot, int64_t k)
   const HostColumn &c = P.columns[r.col];
   return c.iota ? j + 1 : (int64_t)c.ivals[j];
 }
-static int64_t g_index(const Plan &P, const Group &G, int32_t islot, int64_t k) {
+static int64_t g_index(const Plan &P, const Group &G, int32_t islot, int64_t k, const Generator *inst = nullptr) {
   const IndexExpr &e = G.ctx.uidx[islot];
-  int64_t v = e.base;
+  int64_t v = inst ? inst->c.uidx[islot].base : e.base; // shape class: the instance's own base
   for (auto &t : e.terms) v += t.second * g_int_col(P, G, t.first, k);
   return v;
 }
 static void run_group(const Plan &P, const Group &G, const Program &pr, int64_t k, const double *x, const double *y,
-                      double sigma, std::vector<double> &r, double *out) {
+                      double sigma, std::vector<double> &r, double *out, const Generator *inst = nullptr) {
   r.resize(pr.nreg > 0 ? pr.nreg : 1);
   for (const Instr &I : pr.code) {
     switch (I.op) {
       case D_FIELD: { const ColRef &c = P.itrs[G.itr].fp_cols[G.ctx.fp_cols[I.a]]; r[I.dst] = P.columns[c.col].fvals[(k / c.div) % c.mod]; break; }
-      case D_LOADX: r[I.dst] = x[g_index(P, G, I.a, k) - 1]; break;
-      case D_LOADP: r[I.dst] = P.theta[g_index(P, G, I.a, k) - 1]; break;
-      case D_W: r[I.dst] = G.is_obj ? sigma : (y ? y[P.member(G, I.a).o0 + k] : 0.0); break;
-      case D_SEL2: r[I.dst] = g_index(P, G, I.a, k) == g_index(P, G, I.b, k) ? 2.0 : 1.0; break;
+      case D_LOADX: r[I.dst] = x[g_index(P, G, I.a, k, inst) - 1]; break;
+      case D_LOADP: r[I.dst] = P.theta[g_index(P, G, I.a, k, inst) - 1]; break;
+      case D_W: r[I.dst] = G.is_obj ? sigma : (y ? y[(inst ? *inst : P.member(G, I.a)).o0 + k] : 0.0); break;
+      case D_SEL2: r[I.dst] = g_index(P, G, I.a, k, inst) == g_index(P, G, I.b, k, inst) ? 2.0 : 1.0; break;
+      case D_CPAR: r[I.dst] = inst->c.tape[G.cpar_nodes[I.a]].c; break;
       case D_OUT: out[I.dst] = I.a >= 0 ? r[I.a] : pr.cpool[~I.a]; break;
       default: {
         double a = I.a >= 0 ? r[I.a] : pr.cpool[~I.a];
@@ -133,6 +134,12 @@ int32_t hostcheck_eval_local(iexa_plan *p, int32_t which, const double *x, const
 }
 
 // same as hostcheck_eval but through the FUSED group programs; returns the number of groups via ngroups
+int32_t hostcheck_set_class_mode(iexa_plan *p, int32_t on) {
+  if (!p || !p->plan.finalized) return IEXA_ERR_STATE;
+  try { p->plan.build_groups(on != 0); } catch (const std::exception &e) { return IEXA_ERR_INVALID; }
+  return IEXA_OK;
+}
+
 int32_t hostcheck_eval_groups(iexa_plan *p, int32_t which, const double *x, const double *y, double sigma, double *out,
                               int32_t *ngroups) {
   if (!p || !p->plan.finalized) return IEXA_ERR_STATE;
@@ -147,14 +154,18 @@ int32_t hostcheck_eval_groups(iexa_plan *p, int32_t which, const double *x, cons
     if (!want) continue;
     const Program &pr = G.prog[prog];
     tmp.assign(pr.nout > 0 ? pr.nout : 1, 0.0);
+    const std::vector<Generator> &gens = G.is_obj ? P.objs : P.cons;
+    const size_t ninst = G.is_class ? G.inst_gens.size() : 1;
+    for (size_t ii = 0; ii < ninst; ++ii)
     for (int64_t k = 0; k < G.K; ++k) {
-      run_group(P, G, pr, k, x, y, sigma, r, tmp.data());
+      const Generator *inst = G.is_class ? &gens[G.inst_gens[ii]] : nullptr;
+      run_group(P, G, pr, k, x, y, sigma, r, tmp.data(), inst);
       for (size_t j = 0; j < G.outmap[prog].size(); ++j) {
         int m = G.outmap[prog][j].first, c = G.outmap[prog][j].second;
-        const Generator &g = P.member(G, m);
+        const Generator &g = inst ? *inst : P.member(G, m);
         switch (which) {
           case 0: out[0] += tmp[j]; break;
-          case 1: out[g_index(P, G, G.jac_slot[m][c], k) - 1] += tmp[j]; break;
+          case 1: out[g_index(P, G, G.jac_slot[m][c], k, inst) - 1] += tmp[j]; break;
           case 2: out[g.o0 + k] = tmp[j]; break;
           case 3: out[g.o1 + k * g.c.o1step + c] = tmp[j]; break;
           case 4: out[g.o2 + k * g.c.o2step + c] = tmp[j]; break;

@@ -183,15 +183,21 @@ def test_sharded_plans_tile_the_model_on_one_gpu(world, oracle_cache):
     assert np.allclose(g, om.grad(x), rtol=1e-12, atol=1e-14)
 
 
-def test_opf_case3_and_interpreter_budget_fallback(oracle_cache):
-    """BASELINE configs[3] (ESCAPE34/opf.jl, embedded 3-bus case) through the general lowering; and a
-    30-bus grid whose generated source exceeds the NVRTC budget: it must run on the AOT interpreter
-    kernels (GPU), say why, and still match the oracle."""
+def test_opf_shape_classes_and_budget_fallback(oracle_cache, monkeypatch):
+    """BASELINE configs[3] (ESCAPE34/opf.jl) through the general lowering: the embedded 3-bus case (fused
+    groups), a 30-bus grid with 722 generators (its fused source exceeds the NVRTC budget -> generators
+    of identical shape are canonicalised into class kernels with an instance axis), and the same grid
+    with a tiny budget (-> AOT interpreter kernels, with the reason reported).  All match the oracle."""
     import torch
     from iexa_b200 import opf
     from iexa_b200.transform import exa_core
     from oracle.oracle import OracleModel
-    for case, K, expect_spec in ((None, 64, True), (opf.synthetic_grid(30), 9, False)):
+    for case, K, budget, expect_spec in ((None, 64, None, True), (opf.synthetic_grid(30), 9, None, True),
+                                         (opf.synthetic_grid(30), 9, "1000", False)):
+        if budget:
+            monkeypatch.setenv("IEXA_CODEGEN_MAX_BYTES", budget)
+        else:
+            monkeypatch.delenv("IEXA_CODEGEN_MAX_BYTES", raising=False)
         core, _ = exa_core(opf.opf(case, num_supports=K))
         om = OracleModel(core)
         m = ex.ExaModel(core, device=0)

@@ -143,3 +143,24 @@ def test_bad_tapes_are_rejected(hostcheck_lib):
     rc = L.iexa_add_con(h, nodes.ctypes.data, 1, None, 0, 0, 0.0, 0.0, C.byref(off))
     assert rc != 0
     L.iexa_plan_destroy(h)
+
+
+def test_shape_classes_match_oracle(hostcheck_lib):
+    """class mode: generators of identical shape share one parametrised program (plan.hpp::build_groups)"""
+    from oracle.oracle import OracleModel
+    from iexa_b200 import opf
+    from iexa_b200.transform import exa_core
+    L = hostcheck_lib
+    core, _ = exa_core(opf.opf(opf.synthetic_grid(12), num_supports=4))
+    om = OracleModel(core)
+    m = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L)
+    n_fused = L.iexa_debug_codegen_source(m.h, None, 0)
+    assert L.iexa_debug_set_class_mode(m.h, 1) == 0
+    n_class = L.iexa_debug_codegen_source(m.h, None, 0)
+    assert n_class < n_fused / 3, (n_class, n_fused)
+    x, y = eval_point(core)
+    x = np.where(np.isfinite(x), x, 0.0)
+    for which, ref in ((0, [om.obj(x)]), (1, om.grad(x)), (2, om.cons(x)), (3, om.jac_coord(x)), (4, om.hess_coord(x, y, 0.7))):
+        assert_close(_hc(L, m, "hostcheck_eval_groups", which, len(ref), x, y, 0.7 if which == 4 else 1.0), np.asarray(ref), str(which))
+    nb = C.c_int64()
+    assert L.iexa_debug_codegen_compile(m.h, C.byref(nb)) == 0, L.iexa_last_error().decode()
