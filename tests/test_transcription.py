@@ -132,3 +132,28 @@ def test_lowering_matches_hand_transcription(name):
     Ha = np.zeros((oa.nvar, oa.nvar)); np.add.at(Ha, (ha[0] - 1, ha[1] - 1), oa.hess_coord(x, y, 0.7))
     Hb = np.zeros((ob.nvar, ob.nvar)); np.add.at(Hb, (hb[0] - 1, hb[1] - 1), ob.hess_coord(x, y, 0.7))
     assert np.allclose(Ha, Hb, rtol=1e-13, atol=1e-14)
+
+
+def test_constrained_measure_is_expanded_inline_with_a_warning():
+    """transform.jl:430-435: a measure inside a constraint is expanded into the explicit weighted sum
+    (point variables), with the reference's warning; values checked against a hand-written model."""
+    import iexa_b200 as ex
+    from oracle.oracle import OracleModel
+    m = io.InfiniteModel()
+    t = m.infinite_parameter(0, 1, num_supports=5)
+    y = m.variable(t, start=1.0)
+    z = m.variable(start=2.0)
+    m.constraint(m.integral(y ** 2, t) + z, "<=", 3.0)
+    m.objective("Min", z)
+    with pytest.warns(UserWarning, match="Constrained measures can lead to poor performance"):
+        core, data = exa_core(m)
+    assert core.ncon == 1 and core.cons[0].itr.K == 1                      # a finite constraint over [(;)]
+    om = OracleModel(core)
+    assert om.nnzj == 6                                                    # z + the 5 point variables y(t_k)
+    x = np.array([2.0, 0.3, -0.5, 0.7, 1.1, -0.2])
+    w = np.array([0.125, 0.25, 0.25, 0.25, 0.125])
+    assert abs(om.cons(x)[0] - (np.dot(w, x[1:] ** 2) + x[0])) < 1e-14
+    assert om.lcon[0] == -np.inf and om.ucon[0] == 3.0
+    r, c = om.jac_structure()
+    J = np.zeros(6); np.add.at(J, c - 1, om.jac_coord(x))
+    assert np.allclose(J, np.r_[1.0, 2 * w * x[1:]], atol=1e-14)
