@@ -74,8 +74,10 @@ interp_kernel(const GenD *__restrict__ gens, const WorkItem *__restrict__ work, 
         } else if (sink == SINK_SUM) {
           if (active) acc += v;
         } else {
-          const int islot = g.jac_slot[dst];
-          if (g.idx[islot].nterms == 0) { // shared variable: warp-shuffle reduce, one atomic per warp
+          int islot = g.jac_slot[dst];
+          if (islot < 0) { // single writer (Plan::analyse_grad): plain store, the range is not zero-filled
+            if (active) out[idx_eval(g, ~islot, k) - 1] = v;
+          } else if (g.idx[islot].nterms == 0) { // shared variable: warp-shuffle reduce, one atomic per warp
             double s = active ? v : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
@@ -139,7 +141,11 @@ interp_kernel_big(const GenD *__restrict__ gens, const WorkItem *__restrict__ wo
         const double v = I.a >= 0 ? r[I.a * nthr] : P.cpool[~I.a];
         if (sink == SINK_DENSE) { if (active) out[obase + I.dst] = v; }
         else if (sink == SINK_SUM) { if (active) acc += v; }
-        else if (active) atomicAdd(out + (idx_eval(g, g.jac_slot[I.dst], k) - 1), v);
+        else if (active) {
+          const int is_ = g.jac_slot[I.dst];
+          if (is_ < 0) out[idx_eval(g, ~is_, k) - 1] = v;
+          else atomicAdd(out + (idx_eval(g, is_, k) - 1), v);
+        }
         break;
       }
       default: {
@@ -349,7 +355,8 @@ class CudaEngine : public Engine {
     if (rc) return rc;
     double *gd = g;
     if (memspace == IEXA_MEM_HOST) { CK(stage_out_.ensure((size_t)plan_.nvar * 8)); gd = stage_out_.as<double>(); }
-    CK(cudaMemsetAsync(gd, 0, (size_t)plan_.nvar * 8, st));
+    // only the entries that are not written by a single-writer slot need zero-filling
+    for (auto &zr : plan_.grad_zero_ranges) CK(cudaMemsetAsync(gd + zr.first, 0, (size_t)zr.second * 8, st));
     rc = launch(CB_GRAD, PROG_D1, SINK_SCATTER, xd, nullptr, 1.0, gd, st, err);
     if (rc) return rc;
     return out(g, gd, plan_.nvar, memspace, st, err);
@@ -443,7 +450,9 @@ class CudaEngine : public Engine {
         offs[gi].code[p] = A.add(pr[p]->code.data(), pr[p]->code.size() * sizeof(Instr));
         offs[gi].cpool[p] = A.add(pr[p]->cpool.data(), pr[p]->cpool.size() * 8);
       }
-      offs[gi].jac_slot = A.add(g.c.jac_slot.data(), g.c.jac_slot.size() * 4);
+      std::vector<int32_t> js(g.c.jac_slot);
+      if (g.is_obj) for (size_t c = 0; c < js.size(); ++c) if (c < g.grad_direct.size() && g.grad_direct[c]) js[c] = ~js[c];
+      offs[gi].jac_slot = A.add(js.data(), js.size() * 4);
       std::vector<int32_t> hs;
       for (auto &pr2 : g.c.hess_slot) { hs.push_back(pr2.first); hs.push_back(pr2.second); }
       offs[gi].hess_slot = A.add(hs.data(), hs.size() * 4);

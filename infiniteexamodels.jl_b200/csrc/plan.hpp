@@ -47,6 +47,9 @@ struct Generator {
   // this rank's support range and local layout
   int64_t k0 = 0, k1 = 0;
   int64_t l0 = 0, l1 = 0, l2 = 0;
+  // objective generators: first-order slots that are the ONLY writer of their gradient entries
+  // (plain store instead of an atomic, and no zero-fill of that range) — Plan::analyse_grad
+  std::vector<uint8_t> grad_direct;
 };
 
 // Generators over the SAME iterator are fused into one program: one thread evaluates every
@@ -229,6 +232,7 @@ struct Plan {
       g.l2 = loc_nnzh; loc_nnzh += (g.k1 - g.k0) * g.c.o2step;
     }
     build_groups();
+    analyse_grad();
     finalized = true;
   }
 
@@ -351,6 +355,66 @@ struct Plan {
     class_mode_ = class_mode;
   }
   bool class_mode_ = false;
+
+  // ---- grad!: which sparse-gradient slots can be written without atomics ------------------------------
+  // A slot whose index is  base ± (k+1)  over an unrestricted support index walks a contiguous block of
+  // g exactly once; if no other objective slot touches that block, every entry has a single writer:
+  // the kernel stores it directly and grad! does not have to zero the block first.  Everything else
+  // (finite / shared variables, restricted or product iterators) keeps the warp-reduce + atomic path.
+  std::vector<std::pair<int64_t, int64_t>> grad_zero_ranges; // 0-based [start, start+len) that grad! must zero
+  void analyse_grad() {
+    struct Iv { int64_t lo, hi; int gen, slot; bool simple; int coef; };
+    std::vector<Iv> ivs;
+    bool complex_any = false;
+    for (size_t gi = 0; gi < objs.size(); ++gi) {
+      Generator &g = objs[gi];
+      g.grad_direct.assign(g.c.jac_slot.size(), 0);
+      const Iterator &it = itrs[g.itr];
+      for (size_t c = 0; c < g.c.jac_slot.size(); ++c) {
+        const IndexExpr &e = g.c.uidx[g.c.jac_slot[c]];
+        if (e.terms.empty()) { ivs.push_back(Iv{e.base, e.base, (int)gi, (int)c, false, 0}); continue; }
+        bool ok = e.terms.size() == 1 && (e.terms[0].second == 1 || e.terms[0].second == -1);
+        if (ok) {
+          const ColRef &r = it.int_cols[g.c.int_cols[e.terms[0].first]];
+          ok = columns[r.col].iota && r.div == 1 && r.mod == g.K && g.K > 0;
+        }
+        if (!ok) { complex_any = true; continue; }
+        int64_t a = e.base + e.terms[0].second * 1, b = e.base + e.terms[0].second * g.K;
+        ivs.push_back(Iv{std::min(a, b), std::max(a, b), (int)gi, (int)c, true, (int)e.terms[0].second});
+      }
+    }
+    grad_zero_ranges.clear();
+    if (!complex_any) {
+      std::vector<size_t> order(ivs.size());
+      for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+      std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ivs[a].lo < ivs[b].lo; });
+      std::vector<uint8_t> clash(ivs.size(), 0);
+      int64_t reach = INT64_MIN; size_t reach_i = 0;
+      for (size_t q = 0; q < order.size(); ++q) {
+        size_t i = order[q];
+        if (q > 0 && ivs[i].lo <= reach) { clash[i] = 1; clash[reach_i] = 1; }
+        if (ivs[i].hi > reach) { reach = ivs[i].hi; reach_i = i; }
+      }
+      for (size_t i = 0; i < ivs.size(); ++i)
+        if (ivs[i].simple && !clash[i] && ivs[i].lo >= 1 && ivs[i].hi <= nvar) objs[ivs[i].gen].grad_direct[ivs[i].slot] = 1;
+    }
+    // zero ranges: the complement (in [0, nvar)) of the blocks this RANK stores directly
+    std::vector<std::pair<int64_t, int64_t>> direct;
+    for (size_t i = 0; i < ivs.size() && !complex_any; ++i) {
+      const Generator &g = objs[ivs[i].gen];
+      if (!g.grad_direct[ivs[i].slot] || g.k1 <= g.k0) continue;
+      const IndexExpr &e = g.c.uidx[g.c.jac_slot[ivs[i].slot]];
+      int64_t a = e.base + ivs[i].coef * (g.k0 + 1), b = e.base + ivs[i].coef * g.k1; // 1-based, inclusive
+      direct.push_back({std::min(a, b) - 1, std::max(a, b)});                           // 0-based [lo, hi)
+    }
+    std::sort(direct.begin(), direct.end());
+    int64_t pos = 0;
+    for (auto &d : direct) {
+      if (d.first > pos) grad_zero_ranges.push_back({pos, d.first - pos});
+      pos = std::max(pos, d.second);
+    }
+    if (pos < nvar) grad_zero_ranges.push_back({pos, nvar - pos});
+  }
 
   const Generator &member(const Group &G, int mpos) const { return (G.is_obj ? objs : cons)[G.members[mpos]]; }
 };

@@ -99,6 +99,7 @@ def _declare(L):
     sig("hostcheck_set_class_mode", _i32, _vp, _i32)
     sig("hostcheck_structure", _i32, _vp, _i32, _vp, _vp)
     sig("hostcheck_gen_stats", _i32, _vp, _i32, _i32, _vp)
+    sig("hostcheck_grad_stats", _i32, _vp, _vp)
     return L
 
 

@@ -201,6 +201,15 @@ int32_t hostcheck_structure(iexa_plan *p, int32_t which, int64_t *rows, int64_t 
   return IEXA_OK;
 }
 
+// grad! analysis: out[0] = number of single-writer slots, out[1] = entries grad! must zero-fill
+int32_t hostcheck_grad_stats(iexa_plan *p, int64_t *out) {
+  if (!p || !p->plan.finalized) return IEXA_ERR_STATE;
+  out[0] = out[1] = 0;
+  for (auto &g : p->plan.objs) for (uint8_t d : g.grad_direct) out[0] += d;
+  for (auto &z : p->plan.grad_zero_ranges) out[1] += z.second;
+  return IEXA_OK;
+}
+
 // per-generator compile statistics: out[8] = {o1step, o2step, n_occ1, n_occ2, nreg_val, nreg_d1, nreg_d2, ncode_d2}
 int32_t hostcheck_gen_stats(iexa_plan *p, int32_t is_obj, int32_t i, int64_t *out) {
   if (!p) return IEXA_ERR_INVALID;
