@@ -255,6 +255,8 @@ struct Plan {
   // Fuse generators that share (kind, iterator); a group is closed when it grows past the caps.
   // class_mode: generators of identical SHAPE (>= min_inst of them) become one class group first.
   void build_groups(bool class_mode = false, size_t min_inst = 4, size_t max_dag_nodes = 6000, int max_slots = 96) {
+    if (const char *e = getenv("IEXA_GROUP_MAX_SLOTS")) max_slots = atoi(e);       // tuning knobs
+    if (const char *e = getenv("IEXA_GROUP_MAX_NODES")) max_dag_nodes = (size_t)atoll(e);
     groups.clear();
     for (int pass = 0; pass < 2; ++pass) {
       std::vector<Generator> &gens = pass == 0 ? objs : cons;
