@@ -570,16 +570,19 @@ class CudaEngine : public Engine {
   int build_group_tables(std::string &err) {
     std::vector<WorkItem> items;
     size_t starts[CB__N + 1];
+    int64_t nclosed[CB__N] = {0, 0, 0, 0, 0};
     for (int cb = 0; cb < CB__N; ++cb) {
       starts[cb] = items.size();
       if (!spec_->has(cb)) continue;
-      // Blocks of different groups are interleaved by their RELATIVE position in the support
-      // range: groups that walk the same supports (ODE rows, collocation rows, control rows of a
-      // time-indexed model) then touch the same part of x at about the same time, so the second
-      // reader hits in the 126 MB L2 instead of re-reading HBM.
+      // Big groups are scheduled arithmetically (CbSchedule, codegen.hpp); the table holds the rest.
+      // Table blocks of different groups are interleaved by their RELATIVE position in the support
+      // range: groups that walk the same supports then touch the same part of x at about the same
+      // time, so the second reader hits in the 126 MB L2 instead of re-reading HBM.
+      const CbSchedule &S = spec_->schedule(cb);
+      nclosed[cb] = S.nclosed();
       struct Ord { double frac; int gi; int32_t b; };
       std::vector<Ord> ord;
-      for (int gi : spec_->groups_of(cb)) {
+      for (int gi : S.small) {
         const Group &G = plan_.groups[gi];
         int64_t n = G.k1 - G.k0;
         const int64_t SB = spec_block();
@@ -588,12 +591,9 @@ class CudaEngine : public Engine {
         for (int64_t q = 0; q < ninst; ++q)
           for (int64_t b = 0; b < nb; ++b) ord.push_back(Ord{(b + 0.5) / (double)nb, gi, (int32_t)(q * nb + b)});
       }
-      // When this rank's slice of x fits comfortably in L2 (small shards of a multi-GPU run) reuse
-      // comes for free and the tail matters instead: run the heaviest groups first (longest
-      // processing time first) so that the kernel drains on short blocks.
       const char *oe = getenv("IEXA_ORDER");
       bool lpt = oe ? oe[0] == 'l' : false;
-      if (lpt) {
+      if (lpt) { // heaviest groups first (longest processing time first): the kernel drains on short blocks
         const int prog = (cb == CB_OBJ || cb == CB_CONS) ? PROG_VAL : (cb == CB_GRAD || cb == CB_JAC) ? PROG_D1 : PROG_D2;
         std::stable_sort(ord.begin(), ord.end(), [&](const Ord &a, const Ord &b) {
           return plan_.groups[a.gi].prog[prog].code.size() > plan_.groups[b.gi].prog[prog].code.size();
@@ -607,7 +607,8 @@ class CudaEngine : public Engine {
     if (!items.empty()) CK(cudaMemcpy(gwork_.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
     for (int cb = 0; cb < CB__N; ++cb) {
       gtable_[cb].work = gwork_.as<WorkItem>() + starts[cb];
-      gtable_[cb].nblocks = (int)(starts[cb + 1] - starts[cb]);
+      if (nclosed[cb] + (int64_t)(starts[cb + 1] - starts[cb]) > 0x7fffffffll) { err = "too many blocks for one launch"; return IEXA_ERR_INVALID; }
+      gtable_[cb].nblocks = (int)(nclosed[cb] + (int64_t)(starts[cb + 1] - starts[cb])); // grid size: closed-form blocks first
     }
     return IEXA_OK;
   }

@@ -98,11 +98,9 @@ struct Plan {
   int64_t add_var(int64_t n, const double *s, const double *l, const double *u) {
     int64_t off = nvar;
     const double inf = std::numeric_limits<double>::infinity();
-    for (int64_t i = 0; i < n; ++i) {
-      x0.push_back(s ? s[i] : 0.0);
-      lvar.push_back(l ? l[i] : -inf);
-      uvar.push_back(u ? u[i] : inf);
-    }
+    if (s) x0.insert(x0.end(), s, s + n); else x0.resize(x0.size() + n, 0.0);
+    if (l) lvar.insert(lvar.end(), l, l + n); else lvar.resize(lvar.size() + n, -inf);
+    if (u) uvar.insert(uvar.end(), u, u + n); else uvar.resize(uvar.size() + n, inf);
     nvar += n;
     return off;
   }
@@ -179,7 +177,7 @@ struct Plan {
     g.is_obj = false; g.lcon = lc; g.ucon = uc;
     g.o0 = ncon;
     ncon += g.K;
-    for (int64_t k = 0; k < g.K; ++k) { lcon.push_back(lc); ucon.push_back(uc); y0.push_back(0.0); }
+    lcon.resize(lcon.size() + g.K, lc); ucon.resize(ucon.size() + g.K, uc); y0.resize(y0.size() + g.K, 0.0);
     cons.push_back(std::move(g));
     return cons.back().o0;
   }
