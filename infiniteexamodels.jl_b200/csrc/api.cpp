@@ -324,7 +324,7 @@ int64_t iexa_algorithmic_bytes(const iexa_plan *pc, int32_t which) {
     }
     auto touch_col = [&](const iexa::ColRef &r, int esz) {
       const iexa::HostColumn &c = P.columns[r.col];
-      if (c.is_int && c.iota) return;
+      if (c.is_int && c.affine) return; // index arithmetic, nothing is loaded
       auto &seen = colseen[r.col];
       if (seen.empty()) seen.assign((size_t)c.K, false);
       // entries reached by the local support range

@@ -20,7 +20,7 @@ namespace iexa {
 // entries of the generated kernels' __constant__ table (values are resolved per rank at load)
 enum { CI_K0 = 0, CI_K1, CI_IDX_BASE, CI_ICOL_PTR, CI_FCOL_PTR, CI_MEM_ROWLOC, CI_MEM_OUT, CI_CLS_NBLK, CI_CLS_ITAB, CI_CLS_DTAB,
        CI_SB,         // supports per block of (group, callback a)
-       CI_SCHED };    // group = -1, a = callback, b = 0: #closed-form blocks, 1: #big groups, 2 + j: group id of slot j
+       CI_SCHED };    // group = -1, a = callback, b = 0: NB (arithmetic grid rows), 1: #work-table items, 2 + j: group id of slot j
 struct CiEntry {
   int kind, group, a, b;
 };
@@ -36,8 +36,10 @@ struct CiEntry {
 // blocks were already covering it.  IEXA_SCHED=t keeps everything on the table.
 struct CbSchedule {
   std::vector<int> big, sb, small;
-  int64_t NB = 0;
-  int64_t nclosed() const { return NB * (int64_t)big.size(); }
+  int64_t NB = 0;      // blocks per big group (= grid rows walked arithmetically)
+  int64_t ntable = 0;  // work-table items (small and shape-class groups)
+  int64_t gx = 1, gy = 0; // launch grid: x = big-group slot (fastest in dispatch order), y = block row
+  int64_t nblocks() const { return gx * gy; }
 };
 CbSchedule make_schedule(const Plan &plan, const std::vector<int> &groups);
 
@@ -63,7 +65,7 @@ class Specialiser {
   bool has(int cb) const { return cb >= 0 && cb < 5 && fn_[cb] != nullptr; }
   const std::vector<int> &groups_of(int cb) const { return groups_of_[cb]; }
   const CbSchedule &schedule(int cb) const { return sched_[cb]; }
-  bool launch(int cb, int nblocks, const WorkItem *work, const double *x, const double *theta,
+  bool launch(int cb, const WorkItem *work, const double *x, const double *theta,
               const double *y, double sigma, double *out, double *partials, cudaStream_t st,
               std::string &err);
   int n_kernels() const { return n_kernels_; }

@@ -432,7 +432,7 @@ class CudaEngine : public Engine {
     auto need_col = [&](int32_t c) {
       if (col_off[c] != (size_t)-1) return;
       const HostColumn &hc = P.columns[c];
-      if (hc.is_int) { if (!hc.iota) col_off[c] = A.add(hc.ivals.data(), hc.ivals.size() * 4); }
+      if (hc.is_int) { if (!hc.affine) col_off[c] = A.add(hc.ivals.data(), hc.ivals.size() * 4); }
       else col_off[c] = A.add(hc.fvals.data(), hc.fvals.size() * 8);
     };
     std::vector<Generator *> all;
@@ -473,11 +473,12 @@ class CudaEngine : public Engine {
       std::vector<ColD> ic, fc;
       for (int32_t s : g.c.int_cols) {
         const ColRef &r = it.int_cols[s];
-        ic.push_back(ColD{P.columns[r.col].iota ? nullptr : (const void *)(lb + col_off[r.col]), r.div, r.mod});
+        const HostColumn &hc = P.columns[r.col];
+        ic.push_back(ColD{hc.affine ? nullptr : (const void *)(lb + col_off[r.col]), r.div, r.mod, hc.aa, hc.ab, hc.ac, hc.ad});
       }
       for (int32_t s : g.c.fp_cols) {
         const ColRef &r = it.fp_cols[s];
-        fc.push_back(ColD{(const void *)(lb + col_off[r.col]), r.div, r.mod});
+        fc.push_back(ColD{(const void *)(lb + col_off[r.col]), r.div, r.mod, 0, 0, 1, 0});
       }
       std::vector<IdxD> ix;
       for (auto &e : g.c.uidx) {
@@ -570,7 +571,6 @@ class CudaEngine : public Engine {
   int build_group_tables(std::string &err) {
     std::vector<WorkItem> items;
     size_t starts[CB__N + 1];
-    int64_t nclosed[CB__N] = {0, 0, 0, 0, 0};
     for (int cb = 0; cb < CB__N; ++cb) {
       starts[cb] = items.size();
       if (!spec_->has(cb)) continue;
@@ -579,7 +579,6 @@ class CudaEngine : public Engine {
       // range: groups that walk the same supports then touch the same part of x at about the same
       // time, so the second reader hits in the 126 MB L2 instead of re-reading HBM.
       const CbSchedule &S = spec_->schedule(cb);
-      nclosed[cb] = S.nclosed();
       struct Ord { double frac; int gi; int32_t b; };
       std::vector<Ord> ord;
       for (int gi : S.small) {
@@ -607,8 +606,11 @@ class CudaEngine : public Engine {
     if (!items.empty()) CK(cudaMemcpy(gwork_.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
     for (int cb = 0; cb < CB__N; ++cb) {
       gtable_[cb].work = gwork_.as<WorkItem>() + starts[cb];
-      if (nclosed[cb] + (int64_t)(starts[cb + 1] - starts[cb]) > 0x7fffffffll) { err = "too many blocks for one launch"; return IEXA_ERR_INVALID; }
-      gtable_[cb].nblocks = (int)(nclosed[cb] + (int64_t)(starts[cb + 1] - starts[cb])); // grid size: closed-form blocks first
+      if (!spec_->has(cb)) { gtable_[cb].nblocks = 0; continue; }
+      const CbSchedule &S = spec_->schedule(cb);
+      if ((int64_t)(starts[cb + 1] - starts[cb]) != S.ntable) { err = "work table does not match the block schedule"; return IEXA_ERR_INVALID; }
+      if (S.gy > 65535 || S.nblocks() > 0x7fffffffll) { err = "too many blocks for one launch"; return IEXA_ERR_INVALID; }
+      gtable_[cb].nblocks = (int)S.nblocks(); // whole grid (arithmetic rows + table rows): one objective partial per block
     }
     return IEXA_OK;
   }
@@ -663,7 +665,7 @@ class CudaEngine : public Engine {
     if (spec_ && spec_->has(cb)) {
       const Table &GT = gtable_[cb];
       if (GT.nblocks == 0) return IEXA_OK;
-      if (!spec_->launch(cb, GT.nblocks, GT.work, xd, th, yd, sigma, outd, part, st, err)) return IEXA_ERR_CUDA;
+      if (!spec_->launch(cb, GT.work, xd, th, yd, sigma, outd, part, st, err)) return IEXA_ERR_CUDA;
       return IEXA_OK;
     }
     if (T.max_nreg <= 32)

@@ -49,8 +49,9 @@ IEXA_HD double eval_arith(int32_t op, double a, double b) {
 
 // ---- device descriptors ---------------------------------------------------------------
 struct ColD {
-  const void *ptr; // int32* / double* table; nullptr = iota (value = j + 1)
+  const void *ptr; // int32* / double* table; nullptr = affine int column, value = aa + ab*(j / ac) + ad*(j % ac)
   long long div, mod; // j = (k / div) % mod
+  long long aa, ab, ac, ad; // (1, 1, 1, 0) = iota: value = j + 1
 };
 struct IdxD {
   long long base;
@@ -84,7 +85,7 @@ struct GenD {
 
 IEXA_HD long long col_int(const ColD &c, long long k) {
   long long j = (k / c.div) % c.mod;
-  return c.ptr ? (long long)((const int32_t *)c.ptr)[j] : j + 1;
+  return c.ptr ? (long long)((const int32_t *)c.ptr)[j] : c.aa + c.ab * (j / c.ac) + c.ad * (j % c.ac);
 }
 IEXA_HD double col_fp(const ColD &c, long long k) {
   long long j = (k / c.div) % c.mod;

@@ -9,6 +9,7 @@
 // o2_g + o2step_g*k + c with all OBJECTIVE generators first.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -22,8 +23,28 @@ struct HostColumn {
   int64_t K = 0;
   bool is_int = false;
   bool iota = false;            // int column equal to 1..K: never stored
+  // int column that is an affine pattern of its position,  v(j) = aa + ab*(j / ac) + ad*(j % ac):  never stored or
+  // loaded either — index arithmetic instead of a column load followed by a dependent x load.  Covers what the
+  // reference's transcription produces besides 1..K (transform.jl:27-31): restricted / shifted support indices
+  // 2..T of finite-difference rows (:535-538), the (lower bound, node) pairs of orthogonal collocation (:485-505)
+  // and the (upper bound, internal node) pairs of the collocation restrictions (:582-584).
+  bool affine = false;
+  int64_t aa = 0, ab = 0, ac = 1, ad = 0;
   std::vector<int32_t> ivals;   // int column (narrowed; x/theta indices fit in int32)
   std::vector<double> fvals;
+  int64_t ival(int64_t j) const { return affine ? aa + ab * (j / ac) + ad * (j % ac) : (int64_t)ivals[j]; }
+  // v(j) = a + b*(j/c) + d*(j%c) for some period c <= 8?
+  bool detect_affine(const int64_t *v, int64_t n) {
+    if (getenv("IEXA_NO_AFFINE")) return false;
+    if (n <= 0) { affine = true; aa = 1; ab = 1; ac = 1; ad = 0; return true; }
+    for (int64_t c = 1; c <= 8 && (c == 1 || c < n); ++c) {
+      const int64_t a = v[0], d = (c > 1 && n > 1) ? v[1] - v[0] : 0, b = n > c ? v[c] - v[0] : 0;
+      bool ok = true;
+      for (int64_t k = 0; k < n && ok; ++k) ok = v[k] == a + b * (k / c) + d * (k % c);
+      if (ok) { affine = true; aa = a; ab = b; ac = c; ad = d; return true; }
+    }
+    return false;
+  }
 };
 
 struct ColRef {
@@ -121,7 +142,9 @@ struct Plan {
       c.K = K; c.is_int = true; c.iota = true;
       for (int64_t k = 0; k < K; ++k)
         if (ic[j][k] != k + 1) { c.iota = false; break; }
-      if (!c.iota) {
+      if (c.iota) { c.affine = true; c.aa = 1; c.ab = 1; c.ac = 1; c.ad = 0; }
+      else c.detect_affine(ic[j], K);
+      if (!c.affine) {
         c.ivals.resize(K);
         for (int64_t k = 0; k < K; ++k) {
           int64_t v = ic[j][k];
@@ -192,7 +215,7 @@ struct Plan {
     const ColRef &r = itrs[g.itr].int_cols[g.c.int_cols[slot]];
     int64_t j = (k / r.div) % r.mod;
     const HostColumn &c = columns[r.col];
-    return c.iota ? j + 1 : (int64_t)c.ivals[j];
+    return c.ival(j);
   }
   double fp_col_value(const Generator &g, int32_t slot, int64_t k) const {
     const ColRef &r = itrs[g.itr].fp_cols[g.c.fp_cols[slot]];

@@ -43,7 +43,7 @@ static int64_t g_int_col(const Plan &P, const Group &G, int32_t slot, int64_t k)
   const ColRef &r = P.itrs[G.itr].int_cols[G.ctx.int_cols[slot]];
   int64_t j = (k / r.div) % r.mod;
   const HostColumn &c = P.columns[r.col];
-  return c.iota ? j + 1 : (int64_t)c.ivals[j];
+  return c.ival(j);
 }
 static int64_t g_index(const Plan &P, const Group &G, int32_t islot, int64_t k, const Generator *inst = nullptr) {
   const IndexExpr &e = G.ctx.uidx[islot];
