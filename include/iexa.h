@@ -45,7 +45,15 @@ enum {
   IEXA_ERR_NOMEM = 6
 };
 
-enum { IEXA_MEM_HOST = 0, IEXA_MEM_DEVICE = 1 };
+enum {
+  IEXA_MEM_HOST = 0,
+  IEXA_MEM_DEVICE = 1,
+  /* host buffers, and x is bit-identical to the x of the previous host-memory call on this plan: the engine
+   * reuses the device copy of x it already holds instead of uploading it again.  This is Ipopt's `new_x == false`
+   * (every Ipopt callback — eval_g, eval_jac_g, eval_h, … — receives that flag; NLPModelsIpopt drops it, the binding in
+   * INTEGRATION.md forwards it).  Falls back to a plain upload when the engine holds no copy yet. */
+  IEXA_MEM_HOST_SAME_X = 2
+};
 
 /* ---- tape operators ---------------------------------------------------------------
  * One entry per operator of the reference's table src/operators.jl:2-46 plus the four

@@ -334,6 +334,7 @@ class CudaEngine : public Engine {
 
   int obj(const double *x, double *f_host, int memspace, void *stream, std::string &err) override {
     CK(cudaSetDevice(device_));
+    memspace = host_mode(memspace);
     cudaStream_t st = (cudaStream_t)stream;
     const double *xd = nullptr;
     int rc = in(x, plan_.nvar, memspace, stage_x_, st, xd, err);
@@ -349,6 +350,7 @@ class CudaEngine : public Engine {
 
   int grad(const double *x, double *g, int memspace, void *stream, std::string &err) override {
     CK(cudaSetDevice(device_));
+    memspace = host_mode(memspace);
     cudaStream_t st = (cudaStream_t)stream;
     const double *xd = nullptr;
     int rc = in(x, plan_.nvar, memspace, stage_x_, st, xd, err);
@@ -644,11 +646,20 @@ class CudaEngine : public Engine {
          std::string &err) {
     if (!src) { dev = nullptr; return IEXA_OK; }
     if (memspace == IEXA_MEM_DEVICE) { dev = src; return IEXA_OK; }
+    const bool is_x = &stage == &stage_x_;
+    if (is_x && same_x_ && stage_x_valid_ && stage.bytes >= (size_t)n * 8) { dev = stage.as<double>(); return IEXA_OK; } // new_x == false
     CK(stage.ensure((size_t)n * 8));
     CK(cudaMemcpyAsync(stage.p, src, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    if (is_x) stage_x_valid_ = true;
     dev = stage.as<double>();
     return IEXA_OK;
   }
+  // IEXA_MEM_HOST_SAME_X is IEXA_MEM_HOST plus the promise that x has not changed since the last host call
+  int host_mode(int memspace) {
+    same_x_ = memspace == IEXA_MEM_HOST_SAME_X;
+    return same_x_ ? (int)IEXA_MEM_HOST : memspace;
+  }
+  bool same_x_ = false, stage_x_valid_ = false;
   int out(double *dst, const double *dev, int64_t n, int memspace, cudaStream_t st, std::string &err) {
     if (memspace == IEXA_MEM_DEVICE) return IEXA_OK;
     CK(cudaMemcpyAsync(dst, dev, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
@@ -686,6 +697,7 @@ class CudaEngine : public Engine {
   int dense_cb(int cb, int prog, const double *x, const double *y, double sigma, double *o, int64_t n,
                int memspace, void *stream, std::string &err) {
     CK(cudaSetDevice(device_));
+    memspace = host_mode(memspace);
     cudaStream_t st = (cudaStream_t)stream;
     const double *xd = nullptr, *yd = nullptr;
     int rc = in(x, plan_.nvar, memspace, stage_x_, st, xd, err);
@@ -717,6 +729,7 @@ class CudaEngine : public Engine {
   int prod(int mode, const double *x, const double *y, const double *v, double sigma, double *o, int memspace,
            void *stream, std::string &err) {
     CK(cudaSetDevice(device_));
+    memspace = host_mode(memspace);
     cudaStream_t st = (cudaStream_t)stream;
     const int which = mode == 2 ? 1 : 0;
     const int64_t nnz = which == 0 ? plan_.loc_nnzj : plan_.loc_nnzh;

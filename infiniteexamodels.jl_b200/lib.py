@@ -7,7 +7,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-IEXA_MEM_HOST, IEXA_MEM_DEVICE = 0, 1
+IEXA_MEM_HOST, IEXA_MEM_DEVICE, IEXA_MEM_HOST_SAME_X = 0, 1, 2
 IEXA_F_DEFAULT, IEXA_F_NO_SPECIALISE, IEXA_F_NO_DEVICE = 0, 1, 2
 CB_OBJ, CB_GRAD, CB_CONS, CB_JAC, CB_HESS = range(5)
 

@@ -264,11 +264,14 @@ class BoundCall:
             _lib.check(self._m.L, rc)
 
 
-def bind(m: ExaModel, name: str, x, out, y=None, obj_weight: float = 1.0) -> BoundCall:
+def bind(m: ExaModel, name: str, x, out, y=None, obj_weight: float = 1.0, new_x: bool = True) -> BoundCall:
     """``bind(m, "cons", x, c)``, ``bind(m, "jac_coord", x, vals)``, ``bind(m, "hess_coord", x, vals, y, σ)``,
-    ``bind(m, "grad", x, g)``"""
+    ``bind(m, "grad", x, g)``.  ``new_x=False`` (host buffers only) is Ipopt's ``new_x`` flag: x is the x of the
+    previous host call on this model, so the engine reuses its device copy (IEXA_MEM_HOST_SAME_X)."""
     bx, bo, by = m._buf(x, m.meta.nvar), m._buf(out), m._buf(y)
     ms, st = m._pair(bx, bo, by) if y is not None else m._pair(bx, bo)
+    if not new_x and ms == _lib.IEXA_MEM_HOST:
+        ms = _lib.IEXA_MEM_HOST_SAME_X
     h = m.h
     L = m.L
     vp = C.c_void_p

@@ -15,6 +15,7 @@ const LIB = get(ENV, "IEXA_B200_LIB", "libiexa_b200.so")
 
 const MEM_HOST = Int32(0)
 const MEM_DEVICE = Int32(1)
+const MEM_HOST_SAME_X = Int32(2)   # host buffers, x unchanged since the previous host call (Ipopt's new_x == false)
 
 # ---- mirrors of the C structs ------------------------------------------------------------------
 struct IexaNode            # iexa_node (24 bytes)

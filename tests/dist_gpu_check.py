@@ -1,0 +1,71 @@
+"""Multi-GPU parity check of the sharded path on real GPUs (NCCL over NVLink), one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
+        tests/dist_gpu_check.py
+
+Every rank evaluates its support blocks with the CUDA engine; obj and the shared-variable slice of grad! go through an
+NCCL all-reduce; the global c / Jacobian / Hessian values are assembled from the ranks' slices and compared with the
+oracle on rank 0 (tolerance 1e-12 relative / 1e-14 absolute).  Not a pytest file: the driver's `-m gpu` run has one GPU
+(the single-GPU sharding test lives in tests/test_gpu_parity.py, the host logic in tests/test_dist_gloo.py)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import iexa_b200 as ex
+    from iexa_b200 import models
+    from iexa_b200.dist import ShardedExaModel
+    from conftest import assert_close, eval_point
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    cases = {"ode_5x5": models.ode_5x5, "quadrotor_oc_1000": lambda: models.quadrotor(1000, "oc"),
+             "pandemic_200x8": lambda: models.pandemic(200, 8), "farmer_5000": lambda: models.farmer(5000)}
+    ok = True
+    for name, build in cases.items():
+        core = build()
+        sm = ShardedExaModel(core, device=local)
+        assert sm.model.cmeta.n_kernels_specialised > 0
+        x, y = eval_point(core, seed=4)
+        xd, yd = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)
+        f = sm.obj(xd)
+        g = sm.grad_(xd, torch.zeros(core.nvar, dtype=torch.float64, device=dev))
+        gfull = sm.grad_full_(xd, torch.zeros(core.nvar, dtype=torch.float64, device=dev))
+        c = sm.cons_(xd, torch.zeros(max(sm.model.loc_ncon, 1), dtype=torch.float64, device=dev))
+        jv = sm.jac_coord_(xd, torch.zeros(max(sm.model.loc_nnzj, 1), dtype=torch.float64, device=dev))
+        yl = sm.scatter_local(0, yd)
+        hv = sm.hess_coord_(xd, yl, torch.zeros(max(sm.model.loc_nnzh, 1), dtype=torch.float64, device=dev), 0.7)
+        cg, jg, hg = sm.gather_global(0, c), sm.gather_global(1, jv), sm.gather_global(2, hv)
+        if rank == 0:
+            from oracle.oracle import OracleModel
+            om = OracleModel(core)
+            try:
+                assert_close(f, om.obj(x), "obj (all-reduce)")
+                ref = om.grad(x)
+                assert np.allclose(gfull.cpu().numpy(), ref, rtol=1e-12, atol=1e-13), "grad (full all-reduce)"
+                sh = sm.shared_idx
+                assert np.allclose(g.cpu().numpy()[sh], ref[sh], rtol=1e-12, atol=1e-13), "grad (shared slice)"
+                assert_close(cg.cpu().numpy(), om.cons(x), "cons")
+                assert_close(jg.cpu().numpy(), om.jac_coord(x), "jac_coord")
+                assert_close(hg.cpu().numpy(), om.hess_coord(x, y, 0.7), "hess_coord")
+                print(f"{name}: world={world} OK  (rank0 owns {sm.model.loc_ncon}/{om.ncon} rows, "
+                      f"{len(sh)} shared gradient entries)", flush=True)
+            except AssertionError as e:
+                ok = False
+                print(f"{name}: world={world} FAILED: {e}", flush=True)
+        dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,27 @@ def test_callbacks_host_buffers(name, oracle_cache):
     assert (r == ro).all() and (c == co).all()
 
 
+def test_host_buffers_same_x_flag(oracle_cache):
+    """IEXA_MEM_HOST_SAME_X (Ipopt's new_x == false): the device copy of x is reused by the calls that say so, and a
+    call with new_x picks up a changed x."""
+    from iexa_b200.model import bind
+    core, om = _oracle(oracle_cache, "quadrotor_oc_40")
+    m = ex.ExaModel(core, device=0)
+    x, y = eval_point(core)
+    xb = x.copy()
+    c, jv, hv = np.zeros(om.ncon), np.zeros(om.nnzj), np.zeros(om.nnzh)
+    f_cons = bind(m, "cons", xb, c)
+    f_jac = bind(m, "jac_coord", xb, jv, new_x=False)
+    f_hess = bind(m, "hess_coord", xb, hv, y, 0.7, new_x=False)
+    f_jac()                                   # nothing uploaded yet: falls back to a plain upload
+    assert_close(jv, om.jac_coord(x), "jac_coord before any upload")
+    for trial in range(2):
+        f_cons(); f_jac(); f_hess()
+        assert_close(c, om.cons(xb), "cons"); assert_close(jv, om.jac_coord(xb), "jac_coord (same x)")
+        assert_close(hv, om.hess_coord(xb, y, 0.7), "hess_coord (same x)")
+        xb += 0.05 * np.cos(np.arange(xb.size))   # next iterate: cons! is called with new_x and re-uploads
+
+
 def test_parameter_update_in_place(oracle_cache):
     """set_parameter! semantics (infiniteopt_backend.jl:511-548): θ changes, no plan rebuild."""
     import torch
