@@ -43,7 +43,7 @@ hv = torch.zeros(max(m.meta.nnzh, 1), dtype=torch.float64, device="cuda")
 g = torch.zeros(m.meta.nvar, dtype=torch.float64, device="cuda")
 
 
-def timeit(fn, n=20):
+def timeit(fn, n=50):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -57,8 +57,9 @@ def timeit(fn, n=20):
 
 tb = time.time(); B = [ex.algorithmic_bytes(m, w) for w in range(5)]; print("bytes", B, f"({time.time()-tb:.1f}s)")
 tot = 0.0
-for nm, fn, w in (("cons", lambda: ex.cons_(m, x, c), 2), ("jac", lambda: ex.jac_coord_(m, x, jv), 3),
-                  ("hess", lambda: ex.hess_coord_(m, x, y, hv), 4), ("grad", lambda: ex.grad_(m, x, g), 1),
+from iexa_b200.model import bind  # pre-bound calls: one foreign call each, like a Julia ccall (the un-bound Python wrappers cost ~10 us)
+for nm, fn, w in (("cons", bind(m, "cons", x, c), 2), ("jac", bind(m, "jac_coord", x, jv), 3),
+                  ("hess", bind(m, "hess_coord", x, hv, y, 1.0), 4), ("grad", bind(m, "grad", x, g), 1),
                   ("obj", lambda: ex.obj(m, x), 0)):
     ms = timeit(fn)
     if w >= 2:

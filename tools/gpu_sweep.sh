@@ -1,5 +1,5 @@
-set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/s10_pytest.log
-python bench.py > gpurun_out/s10_bench.json 2> gpurun_out/s10_bench.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/s10_ref.json 2> gpurun_out/s10_ref.err
+for cfg in "quad 16000" "pandemic 100000" "pandemic128 10000" "opf 100000" "opf30 10000" "farmer 100000"; do
+  set -- $cfg
+  python tests/quick_bench.py $1 $2 > gpurun_out/s14_$1_$2.log 2>&1
+done
