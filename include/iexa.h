@@ -217,6 +217,12 @@ int64_t iexa_segments(const iexa_plan *p, int32_t which, iexa_segment *out, int6
  * one rank (finite / shared variables and shard-boundary halos): the slice that must be
  * all-reduced after iexa_grad.  Returns the count; fills up to cap.                    */
 int64_t iexa_shared_vars(const iexa_plan *p, int64_t *out, int64_t cap);
+/* the parts of x this rank's callbacks READ: its own supports of every variable block, the replicated finite /
+ * shared variables and the halo of shifted references (y[i-1] of finite differences, the lower-bound / internal
+ * nodes of collocation elements) at the shard boundaries — merged, sorted ranges (global_start == local_start,
+ * 0-based; a conservative cover).  A distributed solver keeps only these ranges of x current on this rank
+ * (halo exchange instead of a broadcast of the whole iterate).  Returns the count; fills up to cap.            */
+int64_t iexa_x_ranges(const iexa_plan *p, iexa_segment *out, int64_t cap);
 
 /* ---- byte accounting used by bench.py's roofline: ALGORITHMIC bytes of
  *      one call of each callback, computed from the finalised plan.

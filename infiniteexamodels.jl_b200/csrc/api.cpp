@@ -288,6 +288,57 @@ int64_t iexa_shared_vars(const iexa_plan *p, int64_t *out, int64_t cap) {
   return (int64_t)v.size();
 }
 
+int64_t iexa_x_ranges(const iexa_plan *p, iexa_segment *out, int64_t cap) {
+  if (!p || !p->plan.finalized) return -1;
+  const iexa::Plan &P = p->plan;
+  std::vector<std::pair<int64_t, int64_t>> iv; // [lo, hi] 1-based, inclusive
+  auto scan = [&](const iexa::Generator &g) {
+    if (g.k1 <= g.k0) return;
+    const iexa::Iterator &it = P.itrs[g.itr];
+    std::vector<uint8_t> used(g.c.uidx.size(), 0);
+    for (size_t s = 0; s < used.size(); ++s)
+      used[s] = (s < g.c.x_slots_val.size() && g.c.x_slots_val[s]) || (s < g.c.x_slots_d1.size() && g.c.x_slots_d1[s]) ||
+                (s < g.c.x_slots_d2.size() && g.c.x_slots_d2[s]);
+    for (int32_t s : g.c.jac_slot) used[s] = 1;
+    for (auto &pr : g.c.hess_slot) { used[pr.first] = 1; used[pr.second] = 1; }
+    for (size_t s = 0; s < used.size(); ++s) {
+      if (!used[s]) continue;
+      const iexa::IndexExpr &e = g.c.uidx[s];
+      int64_t lo = e.base, hi = e.base;
+      for (auto &t : e.terms) {
+        const iexa::ColRef &r = it.int_cols[g.c.int_cols[t.first]];
+        const iexa::HostColumn &c = P.columns[r.col];
+        // positions j = (k / div) % mod visited by k in [k0, k1)
+        int64_t q0 = g.k0 / r.div, q1 = (g.k1 - 1) / r.div, j0 = 0, j1 = r.mod - 1;
+        if (q1 - q0 + 1 < r.mod && q0 % r.mod <= q1 % r.mod) { j0 = q0 % r.mod; j1 = q1 % r.mod; }
+        int64_t vmin, vmax;
+        if (c.affine) {
+          const int64_t a0 = c.ab * (j0 / c.ac), a1 = c.ab * (j1 / c.ac), dm = c.ad * (c.ac - 1);
+          vmin = c.aa + std::min(a0, a1) + std::min<int64_t>(0, dm);
+          vmax = c.aa + std::max(a0, a1) + std::max<int64_t>(0, dm);
+        } else {
+          vmin = vmax = c.ivals[j0];
+          for (int64_t j = j0; j <= j1; ++j) { vmin = std::min<int64_t>(vmin, c.ivals[j]); vmax = std::max<int64_t>(vmax, c.ivals[j]); }
+        }
+        lo += t.second >= 0 ? t.second * vmin : t.second * vmax;
+        hi += t.second >= 0 ? t.second * vmax : t.second * vmin;
+      }
+      lo = std::max<int64_t>(lo, 1); hi = std::min<int64_t>(hi, P.nvar);
+      if (lo <= hi) iv.emplace_back(lo, hi);
+    }
+  };
+  for (auto &g : P.objs) scan(g);
+  for (auto &g : P.cons) scan(g);
+  std::sort(iv.begin(), iv.end());
+  std::vector<std::pair<int64_t, int64_t>> m;
+  for (auto &r : iv) {
+    if (!m.empty() && r.first <= m.back().second + 1) m.back().second = std::max(m.back().second, r.second);
+    else m.push_back(r);
+  }
+  for (size_t i = 0; i < m.size() && (int64_t)i < cap && out; ++i) out[i] = iexa_segment{m[i].first - 1, m[i].first - 1, m[i].second - m[i].first + 1};
+  return (int64_t)m.size();
+}
+
 // ---- algorithmic bytes --------------------------------------------------------
 int64_t iexa_algorithmic_bytes(const iexa_plan *pc, int32_t which) {
   if (!pc || !pc->plan.finalized || which < 0 || which > 4) return -1;

@@ -51,6 +51,16 @@ class ShardedExaModel:
         m.L.iexa_segments(m.h, which, segs, n)
         return [(s.global_start, s.local_start, s.length) for s in segs[:n]]
 
+    def x_ranges(self):
+        """[(start, length)] (0-based) of the parts of x this rank's callbacks read: its own supports of every
+        variable block, the replicated finite / shared variables and the shard-boundary halos.  A distributed
+        solver keeps only these current on this rank (halo exchange instead of a broadcast of the iterate)."""
+        m = self.model
+        n = m.L.iexa_x_ranges(m.h, None, 0)
+        segs = (_lib.Segment * max(n, 1))()
+        m.L.iexa_x_ranges(m.h, segs, n)
+        return [(s.global_start, s.length) for s in segs[:n]]
+
     def scatter_local(self, which: int, global_vec):
         """this rank's slice of a GLOBAL vector (e.g. the multipliers y) in local layout"""
         n = (self.model.loc_ncon, self.model.loc_nnzj, self.model.loc_nnzh)[which]

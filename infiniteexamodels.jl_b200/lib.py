@@ -35,7 +35,7 @@ SYMBOLS = [
     "iexa_add_obj", "iexa_finalize", "iexa_get_meta", "iexa_get_vector", "iexa_set_vector",
     "iexa_set_par", "iexa_get_par", "iexa_jac_structure", "iexa_hess_structure", "iexa_obj",
     "iexa_grad", "iexa_cons", "iexa_jac_coord", "iexa_hess_coord", "iexa_jprod", "iexa_jtprod",
-    "iexa_hprod", "iexa_obj_device", "iexa_host_register", "iexa_host_unregister", "iexa_segments", "iexa_shared_vars", "iexa_algorithmic_bytes",
+    "iexa_hprod", "iexa_obj_device", "iexa_host_register", "iexa_host_unregister", "iexa_segments", "iexa_shared_vars", "iexa_x_ranges", "iexa_algorithmic_bytes",
     "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_set_class_mode", "iexa_debug_codegen_compile",
     "iexa_csr_create", "iexa_csr_destroy", "iexa_csr_nnz", "iexa_csr_pattern", "iexa_csr_apply",
 ]
@@ -81,6 +81,7 @@ def _declare(L):
     sig("iexa_host_unregister", _i32, _vp, _vp)
     sig("iexa_segments", _i64, _vp, _i32, _vp, _i64)
     sig("iexa_shared_vars", _i64, _vp, _vp, _i64)
+    sig("iexa_x_ranges", _i64, _vp, _vp, _i64)
     sig("iexa_algorithmic_bytes", _i64, _vp, _i32)
     sig("iexa_launches_per_call", _i32, _vp, _i32)
     sig("iexa_engine_note", C.c_char_p, _vp)

@@ -44,6 +44,15 @@ def main():
         yl = sm.scatter_local(0, yd)
         hv = sm.hess_coord_(xd, yl, torch.zeros(max(sm.model.loc_nnzh, 1), dtype=torch.float64, device=dev), 0.7)
         cg, jg, hg = sm.gather_global(0, c), sm.gather_global(1, jv), sm.gather_global(2, hv)
+        # x outside iexa_x_ranges is never read by this rank: poison it and evaluate again (bit-identical results)
+        xp = torch.full_like(xd, float("nan"))
+        cover = 0
+        for s0, ln in sm.x_ranges():
+            xp[s0:s0 + ln] = xd[s0:s0 + ln]; cover += ln
+        c2 = sm.cons_(xp, torch.zeros_like(c)); jv2 = sm.jac_coord_(xp, torch.zeros_like(jv))
+        hv2 = sm.hess_coord_(xp, yl, torch.zeros_like(hv), 0.7)
+        assert torch.equal(c2, c) and torch.equal(jv2, jv) and torch.equal(hv2, hv), f"rank {rank} read x outside its ranges"
+        frac = cover / core.nvar
         if rank == 0:
             from oracle.oracle import OracleModel
             om = OracleModel(core)
@@ -57,7 +66,7 @@ def main():
                 assert_close(jg.cpu().numpy(), om.jac_coord(x), "jac_coord")
                 assert_close(hg.cpu().numpy(), om.hess_coord(x, y, 0.7), "hess_coord")
                 print(f"{name}: world={world} OK  (rank0 owns {sm.model.loc_ncon}/{om.ncon} rows, "
-                      f"{len(sh)} shared gradient entries)", flush=True)
+                      f"{len(sh)} shared gradient entries, reads {100 * frac:.1f}% of x)", flush=True)
             except AssertionError as e:
                 ok = False
                 print(f"{name}: world={world} FAILED: {e}", flush=True)

@@ -62,6 +62,17 @@ def _worker(rank, world, port, case, q):
         cg = sm.gather_global(0, c).numpy()
         jg = sm.gather_global(1, jv).numpy()
         hg = sm.gather_global(2, hv).numpy()
+        # x outside iexa_x_ranges is never read by this rank: poison it and evaluate again
+        xp = np.full_like(x, np.nan)
+        cover = 0
+        for s0, ln in sm.x_ranges():
+            xp[s0:s0 + ln] = x[s0:s0 + ln]; cover += ln
+        assert world == 1 or case == "ode_5x5" or cover < core.nvar, "x ranges are not a proper subset"
+        c2 = sm.cons_(xp, np.zeros(max(sm.model.loc_ncon, 1)))
+        jv2 = sm.jac_coord_(xp, np.zeros(max(sm.model.loc_nnzj, 1)))
+        hv2 = sm.hess_coord_(xp, yl, np.zeros(max(sm.model.loc_nnzh, 1)), 0.7)
+        assert np.array_equal(c2, c) and np.array_equal(jv2, jv) and np.array_equal(hv2, hv), "a rank read x outside its ranges"
+        assert sm._ev.obj(xp) == sm._ev.obj(x)
         # owned gradient entries: sum over ranks of the per-rank g must double-count ONLY the shared slice
         gsum = torch.from_numpy(g.copy()); dist.all_reduce(gsum)
         if rank == 0:
