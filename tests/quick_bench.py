@@ -65,4 +65,14 @@ for nm, fn, w in (("cons", bind(m, "cons", x, c), 2), ("jac", bind(m, "jac_coord
     if w >= 2:
         tot += ms
     print(f"{nm}: {ms:.4f} ms  {B[w]/ms/1e6:.1f} GB/s  frac_of_6552={B[w]/ms/1e6/6552:.3f}")
+if os.environ.get("IEXA_GRAPH"):  # the three callbacks captured into one CUDA graph and replayed
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        fc, fj, fh = bind(m, "cons", x, c), bind(m, "jac_coord", x, jv), bind(m, "hess_coord", x, hv, y, 1.0)
+        fc(); fj(); fh()
+    st.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr, stream=st):
+        fc(); fj(); fh()
+    print(f"cons+jac+hess as ONE CUDA graph replay: {timeit(gr.replay):.4f} ms")
 print(f"cons+jac+hess: {tot:.4f} ms -> {1e3/tot:.0f} evals/s, {sum(B[2:])/tot/1e6:.0f} GB/s ({sum(B[2:])/tot/1e6/6552:.3f} of 6552)")

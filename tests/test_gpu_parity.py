@@ -125,6 +125,38 @@ def test_host_buffers_same_x_flag(oracle_cache):
         xb += 0.05 * np.cos(np.arange(xb.size))   # next iterate: cons! is called with new_x and re-uploads
 
 
+@pytest.mark.parametrize("mode", list(MODES))
+def test_callbacks_capture_into_a_cuda_graph(mode, oracle_cache):
+    """Device-memory callbacks only enqueue kernels on the caller's stream (no allocation, no synchronisation), so a
+    solver can capture an iteration's cons! + jac_coord! + hess_coord! into a CUDA graph and replay it: the replay
+    must see the CURRENT contents of x / y and reproduce the oracle."""
+    import torch
+    from iexa_b200.model import bind
+    core, om = _oracle(oracle_cache, "quadrotor_oc_40")
+    m = ex.ExaModel(core, device=0, flags=MODES[mode])
+    x, y = eval_point(core, seed=11)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    c = torch.zeros(om.ncon, dtype=torch.float64, device="cuda")
+    jv = torch.zeros(om.nnzj, dtype=torch.float64, device="cuda")
+    hv = torch.zeros(om.nnzh, dtype=torch.float64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):  # bound on the capture stream
+        f_c, f_j, f_h = bind(m, "cons", xd, c), bind(m, "jac_coord", xd, jv), bind(m, "hess_coord", xd, hv, yd, 0.7)
+        f_c(); f_j(); f_h()     # warm-up outside the capture
+    s.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        f_c(); f_j(); f_h()
+    for trial in range(2):
+        c.zero_(); jv.zero_(); hv.zero_()
+        g.replay(); torch.cuda.synchronize()
+        xh = xd.cpu().numpy()
+        assert_close(c.cpu().numpy(), om.cons(xh), "cons (graph replay)")
+        assert_close(jv.cpu().numpy(), om.jac_coord(xh), "jac_coord (graph replay)")
+        assert_close(hv.cpu().numpy(), om.hess_coord(xh, y, 0.7), "hess_coord (graph replay)")
+        xd += 0.01 * torch.cos(torch.arange(xd.numel(), device="cuda", dtype=torch.float64))  # next iterate, same buffers
+
+
 def test_parameter_update_in_place(oracle_cache):
     """set_parameter! semantics (infiniteopt_backend.jl:511-548): θ changes, no plan rebuild."""
     import torch
