@@ -250,6 +250,16 @@ typedef struct iexa_csr iexa_csr;
 int32_t iexa_csr_create(iexa_csr **out, int64_t nrows, int64_t ncols, int64_t nnz,
                         const void *rows, const void *cols, int32_t idx_bytes,
                         int32_t memspace, int32_t device);
+/* Same, with a locality key per COO entry (entries with nearby keys are evaluated from nearby supports): the
+ * apply pass then walks the CSR entries grouped by key, so that every consumer of a COO tile runs while the
+ * tile is in cache.  iexa_coo_locality fills the keys of the Jacobian (which = 0) / Hessian (which = 1) slots of a
+ * plan (relative position of the slot's 128-support bucket in its generator, scaled to [0, 2^20)); a caller that
+ * concatenates COO blocks into a KKT pattern (MadNLP) concatenates the keys the same way and gives any
+ * constant to the entries it adds itself.  keys == NULL is iexa_csr_create.                             */
+int32_t iexa_csr_create_keyed(iexa_csr **out, int64_t nrows, int64_t ncols, int64_t nnz,
+                              const void *rows, const void *cols, int32_t idx_bytes,
+                              const int32_t *keys, int32_t memspace, int32_t device);
+int32_t iexa_coo_locality(iexa_plan *p, int32_t which, int32_t *keys, int32_t memspace, void *stream);
 int32_t iexa_csr_destroy(iexa_csr *h);
 int64_t iexa_csr_nnz(const iexa_csr *h);
 /* rowptr: nrows+1 entries, colind: csr_nnz entries, 0-based int32 (cuDSS convention)    */

@@ -214,6 +214,10 @@ int32_t iexa_jac_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_byt
 int32_t iexa_hess_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_bytes, int32_t memspace, void *stream) {
   ENGINE_CALL(structure(1, rows, cols, idx_bytes, memspace, stream, err))
 }
+int32_t iexa_coo_locality(iexa_plan *p, int32_t which, int32_t *keys, int32_t memspace, void *stream) {
+  if (which != 0 && which != 1) return fail(IEXA_ERR_INVALID, "which must be 0 (Jacobian) or 1 (Hessian)");
+  ENGINE_CALL(structure(2 + which, keys, nullptr, 4, memspace, stream, err))
+}
 int32_t iexa_obj(iexa_plan *p, const double *x, double *f_host, int32_t memspace, void *stream) {
   ENGINE_CALL(obj(x, f_host, memspace, stream, err))
 }

@@ -191,6 +191,17 @@ structure_kernel(const GenD *__restrict__ gens, const WorkItem *__restrict__ wor
   const GenD &g = gens[w.gen];
   const long long k = g.k0 + (long long)w.blk * BLOCK + threadIdx.x;
   if (k >= g.k1) return;
+  if (which >= 2) { // locality key of every COO slot: relative position of its support in the generator's range
+    const int pr = which == 2 ? PROG_D1 : PROG_D2;
+    const int n = g.ostep[pr];
+    const long long base = g.out_local[pr] + (k - g.k0) * n;
+    // buckets of 128 supports: long enough that a bucket's entries of one generator are a contiguous run of the COO
+    // array, short enough that the runs of all generators of a bucket sit in cache together
+    const long long nbk = (g.K + 127) >> 7;
+    const IT key = (IT)(((k >> 7) << 20) / (nbk > 0 ? nbk : 1));
+    for (int c = 0; c < n; ++c) rows[base + c] = key;
+    return;
+  }
   if (which == 0) {
     const int n = g.ostep[PROG_D1];
     const long long base = g.out_local[PROG_D1] + (k - g.k0) * n;
@@ -294,15 +305,16 @@ class CudaEngine : public Engine {
                 std::string &err) override {
     CK(cudaSetDevice(device_));
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n = which == 0 ? plan_.loc_nnzj : plan_.loc_nnzh;
+    const bool locality = which >= 2; // 2 / 3: locality keys of the Jacobian / Hessian slots into `rows` (cols unused)
+    const int64_t n = (which & 1) == 0 ? plan_.loc_nnzj : plan_.loc_nnzh;
     if (idx_bytes != 4 && idx_bytes != 8) { err = "idx_bytes must be 4 or 8"; return IEXA_ERR_INVALID; }
     void *dr = rows, *dc = cols;
     if (memspace == IEXA_MEM_HOST) {
       CK(stage_a_.ensure((size_t)n * idx_bytes));
-      CK(stage_b_.ensure((size_t)n * idx_bytes));
+      if (!locality) CK(stage_b_.ensure((size_t)n * idx_bytes));
       dr = stage_a_.p; dc = stage_b_.p;
     }
-    const Table &T = table_[which == 0 ? CB_JAC : CB_HESS];
+    const Table &T = table_[(which & 1) == 0 ? CB_JAC : CB_HESS];
     if (T.nblocks > 0) {
       if (idx_bytes == 4)
         structure_kernel<int32_t><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, which, 0, (int32_t *)dr, (int32_t *)dc);
@@ -312,7 +324,7 @@ class CudaEngine : public Engine {
     }
     if (memspace == IEXA_MEM_HOST) {
       CK(cudaMemcpyAsync(rows, dr, (size_t)n * idx_bytes, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(cols, dc, (size_t)n * idx_bytes, cudaMemcpyDeviceToHost, st));
+      if (!locality) CK(cudaMemcpyAsync(cols, dc, (size_t)n * idx_bytes, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
     }
     return IEXA_OK;

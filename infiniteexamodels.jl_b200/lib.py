@@ -37,7 +37,7 @@ SYMBOLS = [
     "iexa_grad", "iexa_cons", "iexa_jac_coord", "iexa_hess_coord", "iexa_jprod", "iexa_jtprod",
     "iexa_hprod", "iexa_obj_device", "iexa_host_register", "iexa_host_unregister", "iexa_segments", "iexa_shared_vars", "iexa_x_ranges", "iexa_algorithmic_bytes",
     "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_set_class_mode", "iexa_debug_codegen_compile",
-    "iexa_csr_create", "iexa_csr_destroy", "iexa_csr_nnz", "iexa_csr_pattern", "iexa_csr_apply",
+    "iexa_csr_create", "iexa_csr_create_keyed", "iexa_coo_locality", "iexa_csr_destroy", "iexa_csr_nnz", "iexa_csr_pattern", "iexa_csr_apply",
 ]
 
 _vp, _i64, _i32, _dbl, _u32 = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_uint32
@@ -89,6 +89,8 @@ def _declare(L):
     sig("iexa_debug_codegen_compile", _i32, _vp, C.POINTER(_i64))
     sig("iexa_debug_set_class_mode", _i32, _vp, _i32)
     sig("iexa_csr_create", _i32, C.POINTER(_vp), _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32)
+    sig("iexa_csr_create_keyed", _i32, C.POINTER(_vp), _i64, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _i32)
+    sig("iexa_coo_locality", _i32, _vp, _i32, _vp, _i32, _vp)
     sig("iexa_csr_destroy", _i32, _vp)
     sig("iexa_csr_nnz", _i64, _vp)
     sig("iexa_csr_pattern", _i32, _vp, _vp, _vp, _i32)

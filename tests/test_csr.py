@@ -45,6 +45,23 @@ def test_csr_matches_scipy(idx_dtype):
     torch.cuda.synchronize()
     assert torch.equal(o1, o2) and np.array_equal(o1.cpu().numpy(), out)
     L.iexa_csr_destroy(h)
+    # locality-keyed work order (iexa_coo_locality): same pattern, bit-identical values
+    rd, cd = torch.from_numpy(r.astype(np.int32)).cuda(), torch.from_numpy(c.astype(np.int32)).cuda()
+    keys = torch.zeros(nh, dtype=torch.int32, device="cuda")
+    assert L.iexa_coo_locality(m.h, 1, keys.data_ptr(), 1, st) == 0, L.iexa_last_error()
+    torch.cuda.synchronize()
+    assert int(keys.min()) >= 0 and int(keys.max()) < (1 << 20)
+    hk = C.c_void_p()
+    assert L.iexa_csr_create_keyed(C.byref(hk), n, n, nh, rd.data_ptr(), cd.data_ptr(), 4, keys.data_ptr(), 1, 0) == 0, L.iexa_last_error()
+    assert L.iexa_csr_nnz(hk) == nnz
+    rp2 = np.zeros(n + 1, dtype=np.int32); ci2 = np.zeros(nnz, dtype=np.int32)
+    assert L.iexa_csr_pattern(hk, rp2.ctypes.data, ci2.ctypes.data, 0) == 0
+    assert (rp2 == rowptr).all() and (ci2 == colind).all()
+    o3 = torch.zeros(nnz, dtype=torch.float64, device="cuda")
+    assert L.iexa_csr_apply(hk, vd.data_ptr(), o3.data_ptr(), 1, st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(o3, o1)
+    L.iexa_csr_destroy(hk)
 
 
 def test_csr_empty_pattern():

@@ -1,6 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "graph or same_x" 2>&1 | tail -3 > gpurun_out/s20_pytest.log
-for cfg in "quad 16000" "pandemic 100000" "farmer 100000" "opf 100000"; do
-  set -- $cfg
-  IEXA_GRAPH=1 python tests/quick_bench.py $1 $2 2>&1 | tail -2 > gpurun_out/s20_$1.log
-done
+python -m pytest tests/test_csr.py tests/test_full_size.py -m gpu -x -q -k "csr" 2>&1 | tail -3 > gpurun_out/s21_pytest.log
+python tests/quick_csr.py > gpurun_out/s21_csr.log 2>&1
