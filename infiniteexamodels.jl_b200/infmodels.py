@@ -22,6 +22,37 @@ def ode_5x5() -> InfiniteModel:
     return m
 
 
+def solve_test_problem(variant: int = -1) -> InfiniteModel:
+    """test/solve.jl:2-14 ("Test Problem 1", ``variant=-1``: point variable, DomainRestriction, derivative of a
+    semi-infinite variable) and :48-59 / :72-77 ("Test Problem 2", ``variant=0`` and its alternative objectives 1..4).
+    The reference checks these differentially against JuMP's TranscriptionBackend (solve.jl:19-26, 61-68, 79-93)."""
+    m = InfiniteModel()
+    t = m.infinite_parameter(0, 1, num_supports=5)
+    x = m.infinite_parameter(-1, 1, num_supports=5)
+    y = m.variable(t, x, lb=0.0)
+    z = m.variable(start=10.0)
+    inner = m.integral(y ** 2, t)
+    if variant == -1:
+        m.objective("Min", m.integral(m.integral(y ** 2, t), x) + 2 * y(0, 1))
+    elif variant == 0:
+        m.objective("Min", m.integral(inner + 2 * z, x) + 2 * y(0, 1))
+    elif variant == 1:
+        m.objective("Min", m.integral(inner + 2 * z ** 2, x) + 2 * y(0, 1))
+    elif variant == 2:
+        m.objective("Min", m.integral(inner + sin(z ** 2), x))
+    elif variant == 3:
+        m.objective("Min", m.integral(inner * cos(z), x))
+    else:
+        m.objective("Min", m.integral(z * (inner + z ** 3), x))
+    m.constraint(m.deriv(y, t), "==", sin(y) + z + 1.2)
+    if variant == -1:
+        m.constraint(y + z, "<=", 42 + t, restriction=lambda s: 0 <= s <= 0.5, restriction_prefs=(t,))
+    else:
+        m.constraint(y + z, "<=", 42 + t)
+    m.constraint(m.deriv(y(0, x), x), "==", 5)
+    return m
+
+
 def rosenbrock_param(p1v=100.0, p2v=1.0):
     """test/solve.jl:134-143"""
     m = InfiniteModel()

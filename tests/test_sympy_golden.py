@@ -58,6 +58,21 @@ BUILDERS = {
 }
 
 
+def _solve_problem(variant):
+    from iexa_b200 import infmodels
+    from iexa_b200.transform import exa_core
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")      # the slow-path measure expansion warns like the reference (transform.jl:683,716)
+        return exa_core(infmodels.solve_test_problem(variant))[0]
+
+
+BUILDERS["solve_tp1"] = lambda: _solve_problem(-1)
+for _v in range(5):
+    BUILDERS[f"solve_tp2_v{_v}"] = (lambda v: (lambda: _solve_problem(v)))(_v)
+ROW_MATCHED = {n for n in BUILDERS if n.startswith("solve_")}   # fixture rows are in the generator script's order
+
+
 def load(name):
     return dict(np.load(os.path.join(G, f"sympy_{name}.npz")))
 
@@ -77,8 +92,21 @@ def close(a, b, scale, what):
     assert not bad.any(), f"{what}: {int(bad.sum())} entries differ, worst {np.abs(a - b)[bad].max():.3e}"
 
 
-def check(d, nvar, ncon, obj, grad, cons, jr, jc, jv, hr, hc, hv, obj_scale=None):
+def match_rows(cons, gold):
+    """row permutation between the engine's constraint order and the fixture's, recovered from the (distinct) values"""
+    a, b = np.argsort(cons), np.argsort(gold)
+    assert np.all(np.abs(np.sort(cons) - np.sort(gold)) <= 1e-14 + 1e-12 * np.abs(np.sort(gold))), "constraint VALUES differ as multisets"
+    assert np.min(np.diff(np.sort(gold))) > 1e-9, "fixture rows are not distinguishable by value"
+    perm = np.empty(len(cons), dtype=np.int64)
+    perm[a] = b          # engine row i  <->  fixture row perm[i]
+    return perm
+
+
+def check(d, nvar, ncon, obj, grad, cons, jr, jc, jv, hr, hc, hv, obj_scale=None, perm=None):
     assert (nvar, ncon) == (int(d["nvar"]), int(d["ncon"]))
+    if perm is not None:   # bring the fixture's rows into the engine's order
+        inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
+        d = dict(d); d["cons"] = d["cons"][perm]; d["jr"] = inv[d["jr"]]
     close(obj, d["obj"], np.abs(d["cons"]).sum() if obj_scale is None else obj_scale, "obj")
     close(grad, d["grad"], 0.0, "grad")
     close(cons, d["cons"], np.abs(d["x"]).max(), "cons")
@@ -91,16 +119,25 @@ def check(d, nvar, ncon, obj, grad, cons, jr, jc, jv, hr, hc, hv, obj_scale=None
     close(H, Hg, HM, "hessian of the Lagrangian")
 
 
+def rows_and_multipliers(name, d, cons):
+    """(multipliers in the engine's row order, row permutation or None)"""
+    if name not in ROW_MATCHED:
+        return np.ascontiguousarray(d["y"]), None
+    perm = match_rows(np.asarray(cons), d["cons"])
+    return np.ascontiguousarray(d["y"][perm]), perm
+
+
 @pytest.mark.parametrize("name", list(BUILDERS))
 def test_oracle_against_sympy(name):
     from oracle.oracle import OracleModel
     d = load(name)
     core = BUILDERS[name]()
     om = OracleModel(core)
-    x, y, s = d["x"], d["y"], float(d["sigma"])
+    x, s = d["x"], float(d["sigma"])
+    y, perm = rows_and_multipliers(name, d, om.cons(x))
     jr, jc = om.jac_structure()
     hr, hc = om.hess_structure()
-    check(d, om.nvar, om.ncon, om.obj(x), om.grad(x), om.cons(x), jr, jc, om.jac_coord(x), hr, hc, om.hess_coord(x, y, s))
+    check(d, om.nvar, om.ncon, om.obj(x), om.grad(x), om.cons(x), jr, jc, om.jac_coord(x), hr, hc, om.hess_coord(x, y, s), perm=perm)
 
 
 @pytest.mark.parametrize("name", list(BUILDERS))
@@ -109,7 +146,7 @@ def test_compiled_programs_against_sympy(name, hostcheck_lib):
     d = load(name)
     core = BUILDERS[name]()
     m = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L)
-    x, y, s = np.ascontiguousarray(d["x"]), np.ascontiguousarray(d["y"]), float(d["sigma"])
+    x, s = np.ascontiguousarray(d["x"]), float(d["sigma"])
 
     def hc_(which, n, yy=None, sg=1.0):
         out = np.zeros(max(n, 1))
@@ -121,8 +158,9 @@ def test_compiled_programs_against_sympy(name, hostcheck_lib):
     jr, jc = om.jac_structure()
     hr, hcol = om.hess_structure()
     obj = hc_(0, 1)[0]
+    y, perm = rows_and_multipliers(name, d, hc_(2, m.meta.ncon))
     check(d, m.meta.nvar, m.meta.ncon, obj, hc_(1, m.meta.nvar), hc_(2, m.meta.ncon), jr, jc, hc_(3, m.meta.nnzj),
-          hr, hcol, hc_(4, m.meta.nnzh, y, s))
+          hr, hcol, hc_(4, m.meta.nnzh, y, s), perm=perm)
 
 
 @pytest.mark.gpu
@@ -137,7 +175,7 @@ def test_cuda_engine_against_sympy(name, interp):
     if not interp:
         assert m.cmeta.n_kernels_specialised > 0, m.L.iexa_engine_note(m.h).decode()
     dev = "cuda"
-    x, y, s = torch.from_numpy(d["x"]).to(dev), torch.from_numpy(d["y"]).to(dev), float(d["sigma"])
+    x, s = torch.from_numpy(d["x"]).to(dev), float(d["sigma"])
     n, mc = m.meta.nvar, m.meta.ncon
     c = torch.zeros(max(mc, 1), dtype=torch.float64, device=dev)
     g = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -145,9 +183,12 @@ def test_cuda_engine_against_sympy(name, interp):
     hv = torch.zeros(max(m.meta.nnzh, 1), dtype=torch.float64, device=dev)
     jr = torch.zeros(max(m.meta.nnzj, 1), dtype=torch.int64, device=dev); jc = torch.zeros_like(jr)
     hr = torch.zeros(max(m.meta.nnzh, 1), dtype=torch.int64, device=dev); hc = torch.zeros_like(hr)
-    ex.cons_(m, x, c); ex.grad_(m, x, g); ex.jac_coord_(m, x, jv); ex.hess_coord_(m, x, y, hv, s)
+    ex.cons_(m, x, c)
+    yh, perm = rows_and_multipliers(name, d, c.cpu().numpy()[:mc])
+    y = torch.from_numpy(yh).to(dev)
+    ex.grad_(m, x, g); ex.jac_coord_(m, x, jv); ex.hess_coord_(m, x, y, hv, s)
     ex.jac_structure_(m, jr, jc); ex.hess_structure_(m, hr, hc)
     f = ex.obj(m, x)
     cpu = lambda t, k: t.cpu().numpy()[:k]
     check(d, n, mc, f, cpu(g, n), cpu(c, mc), cpu(jr, m.meta.nnzj), cpu(jc, m.meta.nnzj), cpu(jv, m.meta.nnzj),
-          cpu(hr, m.meta.nnzh), cpu(hc, m.meta.nnzh), cpu(hv, m.meta.nnzh))
+          cpu(hr, m.meta.nnzh), cpu(hc, m.meta.nnzh), cpu(hv, m.meta.nnzh), perm=perm)
