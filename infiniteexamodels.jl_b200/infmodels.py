@@ -85,6 +85,28 @@ def param_function_model(offset=0.2, pf1=np.sin):
     return m, f1, f2
 
 
+def param_function_problem(ti: float = 0.2) -> InfiniteModel:
+    """test/solve.jl:97-131 ("Parameter Function Problem"), including c5 — a measure of a parameter function inside a
+    constraint, which the reference expands inline with a warning (transform.jl:430-435)"""
+    def param_func2(t, s):
+        return np.cos(t) * s - ti if t <= 0.5 else np.sin(t) * s + ti
+
+    m = InfiniteModel()
+    t = m.infinite_parameter(0, 1, num_supports=5)
+    s = m.infinite_parameter(2, 3, num_supports=5)
+    v = m.variable(t, lb=0, ub=100)
+    z = m.variable(t, s, lb=0, ub=100)
+    pf = m.parameter_function(lambda tt: np.sin(tt), t)
+    pf2 = m.parameter_function(param_func2, t, s)
+    m.constraint(v + pf, "<=", 100)
+    m.constraint(v * 2 + pf * pf2, "<=", 100)
+    m.constraint(v, ">=", 0.2 * pf2)
+    m.constraint(z(t, 2.5) + pf2 * pf, "<=", 40)
+    m.constraint(v * m.integral(pf2, s), "<=", 100)
+    m.objective("Min", m.integral(v * pf, t) + m.integral(m.integral(0.5 * z * pf2, t), s))
+    return m
+
+
 def pandemic(num_supports=100, num_scenarios=4, seed=0) -> InfiniteModel:
     """ESCAPE34/pandemic.jl:4-34"""
     gamma, beta, N = 0.303, 0.727, 1e5

@@ -566,7 +566,9 @@ def expand_measures(ex, data):
                 if isinstance(v, io.ParameterFunction) and any(p in sval for p in v.prefs):
                     if all(p in sval for p in v.prefs):
                         return float(v.func(*[sval[p] for p in v.prefs]))
-                    raise NotImplementedError("partially evaluated parameter function inside an expanded measure")
+                    # partially evaluated: a semi-infinite parameter function (transform.jl:207-211 maps it to
+                    # the parameter function's θ block with the fixed support's index; test/solve.jl:120)
+                    return v.model._semi(v, {i: sval[p] for i, p in enumerate(v.prefs) if p in sval})
                 return v
             total = total + float(coeffs[k]) * io.map_expression(at, inner)
         return total

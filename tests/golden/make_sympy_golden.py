@@ -337,7 +337,33 @@ def solve_tests():
         P.dump(x=rng.uniform(0.2, 1.5, len(P.vars)))
 
 
+def param_function_problem():
+    """test/solve.jl:97-131 ("Parameter Function Problem"): parameter functions pf(t), pf2(t, s) (piecewise), a semi-
+    infinite variable z(t, 2.5) inside a constraint, and a measure of a parameter function inside a constraint
+    (c5: v*∫(pf2, s) <= 100, expanded inline — transform.jl:430-435).  Layout: v(t), z(t, s) (t fastest)."""
+    nt = ns = 5
+    ts, ss = np.linspace(0, 1, nt), np.linspace(2, 3, ns)
+    wt, ws = trapezoid(ts), trapezoid(ss)
+    ti = 0.2
+    pf = np.sin(ts)
+    pf2 = np.array([[np.cos(t) * s - ti if t <= 0.5 else np.sin(t) * s + ti for s in ss] for t in ts])   # [i_t, i_s]
+    P = NLP("param_function_problem")
+    v = P.var("v", nt)
+    z = np.array(P.var("z", nt * ns)).reshape(ns, nt).T
+    s25 = int(np.argmin(np.abs(ss - 2.5)))
+    P.cons += [v[i] + R(pf[i]) for i in range(nt)]                                              # c1
+    P.cons += [2 * v[i] + R(pf[i]) * R(pf2[i, j]) for j in range(ns) for i in range(nt)]      # c2
+    P.cons += [v[i] - R(0.2) * R(pf2[i, j]) for j in range(ns) for i in range(nt)]            # c3
+    P.cons += [z[i, s25] + R(pf2[i, j]) * R(pf[i]) for j in range(ns) for i in range(nt)]     # c4
+    P.cons += [v[i] * sum(R(ws[j]) * R(pf2[i, j]) for j in range(ns)) for i in range(nt)]      # c5
+    P.obj = sum(R(wt[i]) * v[i] * R(pf[i]) for i in range(nt)) + sum(
+        R(ws[j]) * R(wt[i]) * R(0.5) * z[i, j] * R(pf2[i, j]) for j in range(ns) for i in range(nt))
+    rng = np.random.default_rng(33)
+    P.dump(x=rng.uniform(0.5, 5.0, len(P.vars)))
+
+
 if __name__ == "__main__":
+    param_function_problem()
     solve_tests()
     ode_5x5()
     quadrotor("fd", 5)
