@@ -280,6 +280,54 @@ def main():
         e2e = {"value": 1.0 / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": n_e2e, "note": "host (pinned) buffers through iexa_cons/iexa_jac_coord/iexa_hess_coord; PCIe copies inside the timed region; x uploaded once per eval (new_x), y once, c + Jacobian + Hessian values downloaded"}
 
+    # ---- NON-TARGET cost, reported separately: getting a new iterate to the ranks when the solver lives
+    #      on GPU 0.  (a) NCCL broadcast of the whole x; (b) only the ranges each rank READS (iexa_x_ranges: its own
+    #      supports of every variable block + shared variables + halos), packed, sent point to point, unpacked.
+    xdist = None
+    if world > 1:
+        n = m.L.iexa_x_ranges(m.h, None, 0)
+        segs = (ex.lib.Segment * max(n, 1))()
+        m.L.iexa_x_ranges(m.h, segs, n)
+        mine = [(s.global_start, s.length) for s in segs[:n]]
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+
+        def timed(fn, reps=10):
+            for _ in range(2):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        def scatter_ranges():
+            if rank == 0:
+                ops = []
+                for r in range(1, world):
+                    buf = torch.cat([x[s0:s0 + ln] for s0, ln in allr[r]])
+                    ops.append(dist.P2POp(dist.isend, buf, r))
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            else:
+                tot = sum(ln for _, ln in mine)
+                buf = torch.empty(tot, dtype=torch.float64, device=dev)
+                for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, buf, 0)]):
+                    w.wait()
+                o = 0
+                for s0, ln in mine:
+                    x[s0:s0 + ln] = buf[o:o + ln]; o += ln
+
+        xdist = {"broadcast_whole_x_ms": timed(lambda: dist.broadcast(x, src=0)),
+                 "scatter_read_ranges_ms": timed(scatter_ranges),
+                 "x_bytes": int(8 * m.meta.nvar), "read_fraction_per_rank": sum(ln for _, ln in mine) / m.meta.nvar,
+                 "note": "non-target cost of a solver that lives on GPU 0; a distributed solver exchanges halos only"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -333,7 +381,7 @@ def main():
                    "nnzj": int(m.meta.nnzj), "nnzh": int(m.meta.nnzh), "sharding": f"contiguous support blocks x{world}",
                    "l2": "inputs larger than L2 (x = %.0f MB, outputs %.1f GB per eval)" % (m.meta.nvar * 8 / 1e6, (m.loc_nnzj + m.loc_nnzh + m.loc_ncon) * 8 / 1e9),
                    "kernels": "interpreter" if args.interp else f"nvrtc-specialised ({m.cmeta.n_kernels_specialised})"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "x_distribution": xdist,
         "gpu_launches": int(args.steps * sum(ex.launches_per_call(m, w) for w in which)),
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }
