@@ -20,7 +20,7 @@ import numpy as np
 from . import infopt as io
 from . import lib as _lib
 from .model import ExaModel
-from .transform import ExaMappingData, _support_values, exa_core
+from .transform import ExaMappingData, _evaluate_parameter_function, _support_values, exa_core
 
 
 @dataclass
@@ -79,9 +79,7 @@ class ExaTranscriptionBackend:
             pref.func = value
             groups = pref.groups
             dims = tuple(self.data.base_itrs[g - 1].K for g in groups)
-            vals = np.empty(dims)
-            for idx in itertools.product(*[range(d) for d in dims]):
-                vals[idx] = value(*_support_values(self.data, groups, idx))
+            vals = _evaluate_parameter_function(value, self.data, groups, dims)
         self.model.set_parameter(block, vals)
         th = self.core.theta_vec
         th[block.offset:block.offset + block.length] = np.asarray(vals).reshape(-1, order="F")

@@ -41,6 +41,7 @@ class ExaMappingData:
     base_itrs: List[Itr] = field(default_factory=list)
     support_to_index: Dict = field(default_factory=dict)     # (group, support) -> index
     support_labels: List = field(default_factory=list)
+    deriv_data_cache: Dict = field(default_factory=dict)
     has_internal_supps: List[bool] = field(default_factory=list)
     semivar_info: Dict = field(default_factory=dict)
     supports: List[np.ndarray] = field(default_factory=list)  # per group, after generative supports
@@ -66,16 +67,14 @@ def _build_base_iterators(data: ExaMappingData, inf_model: io.InfiniteModel) -> 
         data.supports.append(supps)
         data.internal.append(internal)
         K = supps.shape[-1]
+        # support_to_index[(g, s)] = i (transform.jl:27-29) is answered on demand by _nearest_index (a binary search in
+        # the sorted supports of an independent parameter) instead of a dictionary with one entry per support
         if dependent:
-            for i in range(K):
-                data.support_to_index[(g, tuple(supps[:, i]))] = i + 1
             fps = OrderedDict((a, supps[j]) for j, a in enumerate(aliases))
         else:
-            for i in range(K):
-                data.support_to_index[(g, float(supps[i]))] = i + 1
             fps = OrderedDict([(aliases[0], supps)])
         data.base_itrs.append(Itr(K, {itr_sym: np.arange(1, K + 1)}, fps))
-        data.support_labels.append(["internal" if b else "public" for b in internal])
+        data.support_labels.append(internal)          # True = internal collocation node, False = public support
         data.has_internal_supps.append(bool(internal.any()))
 
 
@@ -89,12 +88,16 @@ def _lobatto_nodes(n: int) -> np.ndarray:
 
 def _add_generative_supports(pub: np.ndarray, num_nodes: int):
     nodes = _lobatto_nodes(num_nodes)[1:-1]
-    out, internal = [pub[0]], [False]
-    for lo, hi in zip(pub[:-1], pub[1:]):
-        for z in nodes:
-            out.append(lo + (z + 1) / 2 * (hi - lo)); internal.append(True)
-        out.append(hi); internal.append(False)
-    return np.asarray(out), np.asarray(internal)
+    n = len(nodes)
+    lo, hi = pub[:-1], pub[1:]
+    T = len(pub) + n * (len(pub) - 1)
+    out = np.empty(T)
+    internal = np.ones(T, dtype=bool)
+    out[0::n + 1] = pub
+    internal[0::n + 1] = False
+    for j, z in enumerate(nodes):
+        out[1 + j::n + 1] = lo + (z + 1) / 2 * (hi - lo)
+    return out, internal
 
 
 # ---- transform.jl:41-101 ---------------------------------------------------------------------------
@@ -158,25 +161,48 @@ def _support_values(data, groups, idx):
     return supp
 
 
+def _evaluate_parameter_function(func, data, group_idxs, dims) -> np.ndarray:
+    """table of a parameter function at every support combination (transform.jl:174-177 calls the closure once per
+    combination).  First try ONE call on broadcast support arrays — exact for functions written with numpy ufuncs —
+    and verify it against per-combination calls on a few entries; fall back to the per-combination loop otherwise
+    (e.g. functions that branch on their arguments, test/solve.jl:99-105)."""
+    if all(data.supports[g - 1].ndim == 1 for g in group_idxs) and int(np.prod(dims)) > 64:
+        try:
+            grids = np.meshgrid(*[data.supports[g - 1] for g in group_idxs], indexing="ij")
+            vals = np.asarray(func(*grids), dtype=np.float64)
+            if vals.shape == tuple(dims):
+                rng = np.random.default_rng(0)
+                probes = [tuple(int(rng.integers(0, d)) for d in dims) for _ in range(8)] + [tuple(0 for _ in dims), tuple(d - 1 for d in dims)]
+                if all(vals[i] == float(func(*_support_values(data, group_idxs, i))) for i in probes):
+                    return vals
+        except Exception:
+            pass
+    vals = np.empty(dims)
+    for idx in itertools.product(*[range(d) for d in dims]):
+        vals[idx] = func(*_support_values(data, group_idxs, idx))
+    return vals
+
+
 def _add_parameter_functions(core: ExaCore, data, inf_model):
     for pfref in inf_model.param_funcs:
         group_idxs = pfref.groups
         dims = tuple(data.base_itrs[g - 1].K for g in group_idxs)
-        vals = np.empty(dims)
-        for idx in itertools.product(*[range(d) for d in dims]):
-            vals[idx] = pfref.func(*_support_values(data, group_idxs, idx))
-        data.param_mappings[pfref] = core.add_par(vals)
+        data.param_mappings[pfref] = core.add_par(_evaluate_parameter_function(pfref.func, data, group_idxs, dims))
     return core
 
 
 # ---- transform.jl:186-287 --------------------------------------------------------------------------------
 def _nearest_index(data, g, value):
+    """``data.support_to_index[g, value]`` (transform.jl:27-29, used by :199,:202,:266)"""
     s = data.supports[g - 1]
-    key = (g, float(value))
-    if key in data.support_to_index:
-        return data.support_to_index[key]
-    i = int(np.argmin(np.abs(s - value)))
-    if abs(s[i] - value) > 1e-12 * max(1.0, abs(value)):
+    if s.ndim == 1 and len(s) > 1:                   # supports of an independent parameter come sorted (transform.jl:528)
+        j = int(np.searchsorted(s, value))
+        cand = [c for c in (j - 1, j) if 0 <= c < len(s)]
+        i = min(cand, key=lambda c: abs(s[c] - value))
+    else:
+        i = int(np.argmin(np.abs(s - value))) if s.ndim == 1 else int(np.argmin(np.abs(s - np.asarray(value).reshape(-1, 1)).sum(axis=0)))
+    ref = s[i] if s.ndim == 1 else s[:, i]
+    if np.max(np.abs(ref - value)) > 1e-12 * max(1.0, float(np.max(np.abs(value)))):
         raise KeyError(f"support {value} of parameter group {g} does not exist")
     return i + 1
 
@@ -358,17 +384,19 @@ def derivative_expr_data(pref, supps: np.ndarray, internal: np.ndarray, method):
     #   y(t_j) − y(lb) = Σ_k M[j,k]·dy(t_k),  M = M2·inv(M1),  M1[j,k] = k (t_j−lb)^(k−1),  M2[j,k] = (t_j−lb)^k
     n = method.num_nodes - 1
     pub = np.flatnonzero(~internal)
-    lbs, nodes, Ms = [], [], [[] for _ in range(n)]
-    for a, b in zip(pub[:-1], pub[1:]):
-        tj = supps[a + 1:b + 1] - supps[a]
-        k = np.arange(1, n + 1)
-        M1 = k[None, :] * tj[:, None] ** (k[None, :] - 1)
-        M2 = tj[:, None] ** k[None, :]
-        M = M2 @ np.linalg.inv(M1)
-        for j in range(n):
-            lbs.append(a + 1); nodes.append(a + 2 + j)
-            for kk in range(n): Ms[kk].append(M[j, kk])
-    return {"idx": np.asarray(nodes), "d_lb": np.asarray(lbs)}, {f"d_arg{kk + 1}": np.asarray(Ms[kk]) for kk in range(n)}
+    a = pub[:-1]                                                     # 0-based position of every interval's lower bound
+    if len(a) == 0:
+        return {"idx": np.zeros(0, dtype=np.int64), "d_lb": np.zeros(0, dtype=np.int64)}, {f"d_arg{kk + 1}": np.zeros(0) for kk in range(n)}
+    assert np.all(np.diff(pub) == n), "every interval carries the same number of collocation nodes"
+    # all intervals at once (the reference loops over supports; at 10^6 supports that loop is the build time)
+    tj = supps[a[:, None] + 1 + np.arange(n)[None, :]] - supps[a][:, None]          # (intervals, n)
+    k = np.arange(1, n + 1)
+    M1 = k[None, None, :] * tj[:, :, None] ** (k[None, None, :] - 1)
+    M2 = tj[:, :, None] ** k[None, None, :]
+    M = M2 @ np.linalg.inv(M1)                                                      # (intervals, n, n)
+    lbs = np.repeat(a + 1, n)
+    nodes = (a[:, None] + 2 + np.arange(n)[None, :]).reshape(-1)
+    return {"idx": nodes, "d_lb": lbs}, {f"d_arg{kk + 1}": np.ascontiguousarray(M[:, :, kk].reshape(-1)) for kk in range(n)}
 
 
 def make_indexed_derivative_expr(dref, vref, pref, data_src, data, method, group_alias):
@@ -396,7 +424,9 @@ def _add_derivative_approximations(core: ExaCore, data, inf_model):
         pref_group = pref.group
         base_itr = data.base_itrs[pref_group - 1]
         supps = data.supports[pref_group - 1]
-        ints, fps = derivative_expr_data(pref, supps, data.internal[pref_group - 1], method)
+        if (pref, id(method)) not in data.deriv_data_cache:   # the same rows for every variable differentiated along pref
+            data.deriv_data_cache[(pref, id(method))] = derivative_expr_data(pref, supps, data.internal[pref_group - 1], method)
+        ints, fps = (dict(d) for d in data.deriv_data_cache[(pref, id(method))])
         galias = data.group_alias[pref_group - 1]
         idxs = ints.pop("idx")
         cols_i = OrderedDict([(galias, idxs)]); cols_i.update(ints)
@@ -418,7 +448,7 @@ def _add_collocation_restrictions(core: ExaCore, data, inf_model):
         num_nodes = pref.derivative_method.num_nodes - 2
         num_supps = len(data.supports[g - 1])
         ubs = np.repeat(np.arange(2 + num_nodes, num_supps + 1, num_nodes + 1), num_nodes)
-        pts = np.array([i for i in range(2, num_supps) if i not in set(ubs.tolist())])
+        pts = np.setdiff1d(np.arange(2, num_supps), ubs)
         pref_itr = Itr(len(ubs), {"i1": ubs, "i2": pts}, {})
         pref_alias = data.group_alias[g - 1]
         for vref in vrefs:

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_csr.py tests/test_full_size.py -m gpu -x -q -k "csr" 2>&1 | tail -3 > gpurun_out/s21_pytest.log
-python tests/quick_csr.py > gpurun_out/s21_csr.log 2>&1
+( time python -m pytest tests -m gpu -x -q ) > gpurun_out/s22_pytest.log 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s22_smoke.log 2>&1
+python bench.py > gpurun_out/s22_bench.json 2> gpurun_out/s22_bench.err
