@@ -132,6 +132,29 @@ def test_config3_world2_sharding_tiles_the_full_model_bit_for_bit():
     assert abs(fsum - f) <= 1e-12 * max(1.0, abs(f))
 
 
+def test_config3_general_lowering_builds_the_same_plan_at_full_size():
+    """the model STATEMENTS of ESCAPE34/quadrotor.jl lowered by transform.py (the restatement of src/transform.jl) at 10^6
+    supports give the same plan dimensions, x0 and θ bit for bit, and the same evaluations within the north-star tolerance
+    as the hand transcription the benchmark uses (the collocation coefficients differ in the last bit: M2·inv(M1) evaluated
+    numerically vs the closed form 0.75h, -0.25h, h, 0)"""
+    import torch
+    from iexa_b200 import infmodels
+    from iexa_b200.transform import exa_core
+    hand = models.quadrotor(1_000_000, "oc")
+    x, y = eval_point(hand, seed=6)
+    m1 = ex.ExaModel(hand, device=0)
+    ref = [t.clone() for t in _eval_all(m1, x, y, 0.7)[2:]]
+    dims = (m1.meta.nvar, m1.meta.ncon, m1.meta.nnzj, m1.meta.nnzh)
+    del m1
+    general, _ = exa_core(infmodels.quadrotor(1_000_000, "oc"))
+    assert np.array_equal(general.x0_vec, hand.x0_vec) and np.array_equal(general.theta_vec, hand.theta_vec)
+    m2 = ex.ExaModel(general, device=0)
+    assert (m2.meta.nvar, m2.meta.ncon, m2.meta.nnzj, m2.meta.nnzh) == dims
+    got = _eval_all(m2, x, y, 0.7)[2:]
+    for name, a, b in zip(("cons", "jac_coord", "hess_coord"), got, ref):
+        assert_close(a.cpu().numpy(), b.cpu().numpy(), name)
+
+
 def test_config2_pandemic_1e5_time_supports_parity():
     """ESCAPE34/pandemic.jl, 10^5 time supports (+10 extra), 4 scenarios (BASELINE configs[1])"""
     _parity(models.pandemic(100_000, 4), seed=2)

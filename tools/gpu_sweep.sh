@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-( time python -m pytest tests -m gpu -x -q ) > gpurun_out/s22_pytest.log 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s22_smoke.log 2>&1
-python bench.py > gpurun_out/s22_bench.json 2> gpurun_out/s22_bench.err
+( time python -m pytest tests/test_full_size.py tests/test_sympy_golden.py -m gpu -x -q --durations=5 ) > gpurun_out/s23_pytest.log 2>&1
