@@ -292,19 +292,19 @@ def main():
         allr = [None] * world
         dist.all_gather_object(allr, mine)
 
-        def timed(fn, reps=10):
-            for _ in range(2):
+        def timed(fn, reps=11):
+            for _ in range(4):          # first calls set up NCCL point-to-point channels
                 fn()
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
+            ts = []
             for _ in range(reps):
-                fn()
-            b.record()
-            barrier()
-            t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                barrier()
+                t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ts.append(float(t.item()))
+            return float(np.median(ts))
 
         def scatter_ranges():
             if rank == 0:
