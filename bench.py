@@ -323,10 +323,16 @@ def main():
                 for s0, ln in mine:
                     x[s0:s0 + ln] = buf[o:o + ln]; o += ln
 
+        from iexa_b200.dist import ShardedExaModel
+        sm = ShardedExaModel.wrap(m)
+        _, recv, _ = sm.x_partition()
+        halo = torch.tensor([sum(hi - lo for v in recv.values() for lo, hi in v)], device=dev)
+        dist.all_reduce(halo)
         xdist = {"broadcast_whole_x_ms": timed(lambda: dist.broadcast(x, src=0)),
                  "scatter_read_ranges_ms": timed(scatter_ranges),
+                 "halo_exchange_ms": timed(lambda: sm.exchange_x(x)), "halo_entries_all_ranks": int(halo.item()),
                  "x_bytes": int(8 * m.meta.nvar), "read_fraction_per_rank": sum(ln for _, ln in mine) / m.meta.nvar,
-                 "note": "non-target cost of a solver that lives on GPU 0; a distributed solver exchanges halos only"}
+                 "note": "non-target: a solver that lives on GPU 0 broadcasts x or scatters the ranges each rank reads; a distributed solver (each rank owns its part of x, ShardedExaModel.exchange_x) exchanges the shared slice and the shard-boundary halos only"}
 
     if rank != 0:
         if world > 1:

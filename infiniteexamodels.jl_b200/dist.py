@@ -42,6 +42,23 @@ class ShardedExaModel:
         self._ev = evaluator  # tests inject a host evaluator; default: the CUDA engine
         self._shared_t = None
 
+    @classmethod
+    def wrap(cls, model: "_m.ExaModel", group=None) -> "ShardedExaModel":
+        """the sharded view of an ExaModel that was already built with (rank, world)"""
+        import torch
+        import torch.distributed as dist
+        self = cls.__new__(cls)
+        self.dist, self.torch, self.group = dist, torch, group
+        self.rank, self.world = model.rank, model.world
+        self.model, self.meta = model, model.meta
+        n = model.L.iexa_shared_vars(model.h, None, 0)
+        idx = np.zeros(max(n, 1), dtype=np.int64)
+        if n > 0:
+            model.L.iexa_shared_vars(model.h, idx.ctypes.data, n)
+        self.shared_idx = idx[:n] - 1
+        self._ev, self._shared_t = None, None
+        return self
+
     # ---- layout ---------------------------------------------------------------------------------
     def segments(self, which: int):
         """[(global_start, local_start, length)] of rows (0), Jacobian slots (1), Hessian slots (2)."""
@@ -60,6 +77,93 @@ class ShardedExaModel:
         segs = (_lib.Segment * max(n, 1))()
         m.L.iexa_x_ranges(m.h, segs, n)
         return [(s.global_start, s.length) for s in segs[:n]]
+
+    # ---- distributed iterate: who owns which part of x, and the halo exchange ----------------------
+    @staticmethod
+    def _intersect(a, b):
+        """intersection of two sorted lists of disjoint half-open intervals [(lo, hi)]"""
+        out, i, j = [], 0, 0
+        while i < len(a) and j < len(b):
+            lo, hi = max(a[i][0], b[j][0]), min(a[i][1], b[j][1])
+            if lo < hi:
+                out.append((lo, hi))
+            if a[i][1] < b[j][1]:
+                i += 1
+            else:
+                j += 1
+        return out
+
+    @staticmethod
+    def _subtract(a, b):
+        """a \\ b for sorted lists of disjoint half-open intervals"""
+        out, j = [], 0
+        for lo, hi in a:
+            cur = lo
+            while j < len(b) and b[j][1] <= cur:
+                j += 1
+            k = j
+            while k < len(b) and b[k][0] < hi:
+                if b[k][0] > cur:
+                    out.append((cur, b[k][0]))
+                cur = max(cur, b[k][1])
+                k += 1
+            if cur < hi:
+                out.append((cur, hi))
+        return out
+
+    def x_partition(self):
+        """(owned, recv, send): every entry of x that some rank reads is OWNED by the lowest rank that reads it (shared
+        variables by rank 0; a shard-boundary halo by the lower neighbour).  ``owned``: this rank's half-open intervals;
+        ``recv[q]`` / ``send[r]``: the intervals this rank needs from owner q / owes to reader r.  Computed once."""
+        if getattr(self, "_partition", None) is not None:
+            return self._partition
+        mine = [(s0, s0 + ln) for s0, ln in self.x_ranges()]
+        reads = [mine]
+        if self.world > 1:
+            reads = [None] * self.world
+            self.dist.all_gather_object(reads, mine, group=self.group)
+        owned_all, seen = [], []
+        for r in range(self.world):
+            owned_all.append(self._subtract(reads[r], seen))
+            seen = sorted(seen + owned_all[r])
+            merged = []
+            for lo, hi in seen:                      # keep `seen` a list of disjoint, merged intervals
+                if merged and lo <= merged[-1][1]:
+                    merged[-1] = (merged[-1][0], max(merged[-1][1], hi))
+                else:
+                    merged.append((lo, hi))
+            seen = merged
+        recv = {q: self._intersect(reads[self.rank], owned_all[q]) for q in range(self.world) if q != self.rank}
+        send = {r: self._intersect(reads[r], owned_all[self.rank]) for r in range(self.world) if r != self.rank}
+        self._partition = (owned_all[self.rank], {q: v for q, v in recv.items() if v}, {r: v for r, v in send.items() if v})
+        return self._partition
+
+    def exchange_x(self, x):
+        """make every range of x this rank READS current, given that each rank holds current values on the ranges it
+        OWNS: point-to-point sends of the shared slice and the shard-boundary halos (NCCL over NVLink on GPUs) — the
+        distributed solver's alternative to broadcasting the whole iterate."""
+        if self.world == 1:
+            return x
+        torch, dist = self.torch, self.dist
+        _, recv, send = self.x_partition()
+        xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(x)
+        key = str(xt.device)
+        if getattr(self, "_xidx", {}).get("dev") != key:   # index tensors of the packed ranges, built once per device
+            mk = lambda ivs: torch.cat([torch.arange(lo, hi, dtype=torch.int64) for lo, hi in ivs]).to(xt.device)
+            self._xidx = {"dev": key, "send": {r: mk(v) for r, v in sorted(send.items())},
+                          "recv": {q: mk(v) for q, v in sorted(recv.items())}}
+        ops, inbox = [], {}
+        for r, idx in self._xidx["send"].items():           # one gather kernel per reader
+            ops.append(dist.P2POp(dist.isend, xt[idx], r, group=self.group))
+        for q, idx in self._xidx["recv"].items():
+            inbox[q] = torch.empty(idx.numel(), dtype=xt.dtype, device=xt.device)
+            ops.append(dist.P2POp(dist.irecv, inbox[q], q, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for q, idx in self._xidx["recv"].items():           # one scatter kernel per owner
+            xt[idx] = inbox[q]
+        return x
 
     def scatter_local(self, which: int, global_vec):
         """this rank's slice of a GLOBAL vector (e.g. the multipliers y) in local layout"""

@@ -53,6 +53,17 @@ def main():
         hv2 = sm.hess_coord_(xp, yl, torch.zeros_like(hv), 0.7)
         assert torch.equal(c2, c) and torch.equal(jv2, jv) and torch.equal(hv2, hv), f"rank {rank} read x outside its ranges"
         frac = cover / core.nvar
+        # distributed iterate: current values on the OWNED ranges only, then the halo exchange over NCCL point-to-point
+        owned, recv, send = sm.x_partition()
+        xo = torch.full_like(xd, float("nan"))
+        for lo, hi in owned:
+            xo[lo:hi] = xd[lo:hi]
+        sm.exchange_x(xo)
+        c3 = sm.cons_(xo, torch.zeros_like(c)); hv3 = sm.hess_coord_(xo, yl, torch.zeros_like(hv), 0.7)
+        assert torch.equal(c3, c) and torch.equal(hv3, hv), f"rank {rank}: halo exchange left a read range stale"
+        halo_t = torch.tensor([sum(hi - lo for v in recv.values() for lo, hi in v)], device=dev)
+        dist.all_reduce(halo_t)
+        halo = int(halo_t.item())
         if rank == 0:
             from oracle.oracle import OracleModel
             om = OracleModel(core)
@@ -66,7 +77,7 @@ def main():
                 assert_close(jg.cpu().numpy(), om.jac_coord(x), "jac_coord")
                 assert_close(hg.cpu().numpy(), om.hess_coord(x, y, 0.7), "hess_coord")
                 print(f"{name}: world={world} OK  (rank0 owns {sm.model.loc_ncon}/{om.ncon} rows, "
-                      f"{len(sh)} shared gradient entries, reads {100 * frac:.1f}% of x)", flush=True)
+                      f"{len(sh)} shared gradient entries, reads {100 * frac:.1f}% of x, {halo} entries cross ranks in the halo exchange)", flush=True)
             except AssertionError as e:
                 ok = False
                 print(f"{name}: world={world} FAILED: {e}", flush=True)

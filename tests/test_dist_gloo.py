@@ -73,6 +73,18 @@ def _worker(rank, world, port, case, q):
         hv2 = sm.hess_coord_(xp, yl, np.zeros(max(sm.model.loc_nnzh, 1)), 0.7)
         assert np.array_equal(c2, c) and np.array_equal(jv2, jv) and np.array_equal(hv2, hv), "a rank read x outside its ranges"
         assert sm._ev.obj(xp) == sm._ev.obj(x)
+        # distributed iterate: every rank starts with current values on the ranges it OWNS only; after exchange_x the
+        # ranges it reads are current and the evaluation is unchanged
+        owned, recv, send = sm.x_partition()
+        xo = np.full_like(x, np.nan)
+        for lo, hi in owned:
+            xo[lo:hi] = x[lo:hi]
+        n_owned = torch.tensor([sum(hi - lo for lo, hi in owned)]); dist.all_reduce(n_owned)
+        assert int(n_owned) <= core.nvar                         # ownership is disjoint
+        sm.exchange_x(xo)
+        c3 = sm.cons_(xo, np.zeros(max(sm.model.loc_ncon, 1)))
+        jv3 = sm.jac_coord_(xo, np.zeros(max(sm.model.loc_nnzj, 1)))
+        assert np.array_equal(c3, c) and np.array_equal(jv3, jv), "halo exchange left a read range stale"
         # owned gradient entries: sum over ranks of the per-rank g must double-count ONLY the shared slice
         gsum = torch.from_numpy(g.copy()); dist.all_reduce(gsum)
         if rank == 0:
