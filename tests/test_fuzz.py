@@ -1,0 +1,144 @@
+"""Seeded random models against the oracle: random expression trees over the reference's operator table, random
+iterators (1..K, shifted / strided / paired integer columns that the engine turns into index arithmetic, arbitrary
+integer columns that it must load, product iterators), several generators per iterator (fusion), shared variables,
+parameters, ragged support counts around the block size.
+
+  * CPU: the plan compiler's register programs (tests/hostcheck) vs the oracle — structure bit-exact, values within
+    1e-12 relative / 1e-14 absolute;
+  * GPU (`-m gpu`): the NVRTC-specialised kernels and the AOT interpreter kernels through the C ABI vs the oracle.
+
+This is the net under the code generator's special cases (affine columns, 32-bit index arithmetic, loads issued first,
+sincos pairing, arithmetic block schedule, staged tile write-out)."""
+import numpy as np
+import pytest
+
+import iexa_b200 as ex
+from conftest import assert_close, has_gpu
+
+UNARY = [ex.sin, ex.cos, ex.tanh, ex.abs2, lambda a: ex.exp(0.3 * a), lambda a: ex.sqrt(1.5 + ex.abs2(a)),
+         lambda a: ex.log(2.0 + ex.abs2(a)), lambda a: ex.tan(0.4 * a), lambda a: ex.atan(a), lambda a: a ** 2, lambda a: a ** 3.0]
+
+
+def random_model(seed, K1=None, K2=None):
+    rng = np.random.default_rng(seed)
+    K1 = int(rng.choice([1, 3, 37, 64, 130, 257, 300])) if K1 is None else int(K1)
+    K2 = int(rng.choice([1, 1, 4])) if K2 is None else int(K2)
+    core = ex.ExaCore()
+    ds = ex.DataSource()
+    a, b = core.add_var(K1), core.add_var(K1)
+    c = core.add_var(K1, K2)
+    z = core.add_var(1, start=0.3)
+    th = core.add_par(rng.uniform(0.5, 1.5, K1))
+    iota = np.arange(1, K1 + 1)
+    perm = rng.permutation(K1) + 1                                   # arbitrary (non-affine) integer column
+    t1 = ex.Itr(K1, {"i": iota, "p": perm}, {"w": rng.uniform(0.2, 1.0, K1), "s": rng.uniform(-1, 1, K1)})
+    t2 = ex.Itr(K2, {"j": np.arange(1, K2 + 1)}, {"q": rng.uniform(0.5, 2.0, K2)})
+    both = ex.Itr.product([t1, t2])
+    iters = [("t1", t1), ("both", both)]
+    if K1 >= 3:                                                       # shifted / paired / strided affine columns
+        sh = ex.Itr(K1 - 1, {"i": np.arange(2, K1 + 1)}, {"w": rng.uniform(0.2, 1.0, K1 - 1), "s": rng.uniform(-1, 1, K1 - 1)})
+        n2 = (K1 - 1) // 2
+        pr = ex.Itr(2 * n2, {"i": np.repeat(np.arange(1, 2 * n2, 2), 2), "p": np.arange(2, 2 * n2 + 2)},
+                    {"w": rng.uniform(0.2, 1.0, 2 * n2), "s": rng.uniform(-1, 1, 2 * n2)}) if n2 >= 1 else None
+        iters += [("sh", sh)] + ([("pr", pr)] if pr is not None else [])
+
+    def leaf(kind):
+        i, p = ds.i, ds.p
+        pool = [lambda: a[i], lambda: b[i], lambda: z[1], lambda: th[i], lambda: ds.w, lambda: ds.s,
+                lambda: float(rng.uniform(-2, 2))]
+        if kind in ("t1", "pr"):
+            pool += [lambda: a[p], lambda: b[p]]
+        if kind == "both":
+            pool += [lambda: c[i, ds.j], lambda: ds.q, lambda: c[p, ds.j]]
+        if kind == "sh":
+            pool += [lambda: a[i.idx() - 1], lambda: b[i.idx() - 1]]
+        if kind == "pr":
+            pool += [lambda: a[i.idx() + 1], lambda: b[i.idx() + 2] if K1 >= 2 * ((K1 - 1) // 2) + 2 else b[i]]
+        return pool[int(rng.integers(len(pool)))]()
+
+    def tree(kind, depth):
+        if depth == 0 or rng.random() < 0.2:
+            return leaf(kind)
+        r = rng.random()
+        if r < 0.35:
+            return UNARY[int(rng.integers(len(UNARY)))](tree(kind, depth - 1))
+        l, rr = tree(kind, depth - 1), tree(kind, depth - 1)
+        op = int(rng.integers(4))
+        if op == 0: return l + rr
+        if op == 1: return l - rr
+        if op == 2: return l * rr
+        return l / (2.0 + ex.abs2(rr))
+
+    ngen = int(rng.integers(3, 8))
+    for _ in range(ngen):
+        kind, itr = iters[int(rng.integers(len(iters)))]
+        e = tree(kind, int(rng.integers(1, 5)))
+        if isinstance(e, float):
+            e = ex.Const(e) + a[ds.i]
+        core.add_con(e, itr, -1.0, 1.0)
+    for _ in range(int(rng.integers(1, 3))):
+        kind, itr = iters[int(rng.integers(2))]
+        e = tree(kind, int(rng.integers(1, 4)))
+        core.add_obj(ds.w * (e if not isinstance(e, float) else ex.Const(e) + b[ds.i]), itr)
+    x = rng.uniform(-1, 1, core.nvar)
+    y = rng.uniform(-1, 1, core.ncon)
+    return core, x, y
+
+
+def _oracle(core):
+    from oracle.oracle import OracleModel
+    return OracleModel(core)
+
+
+@pytest.mark.parametrize("seed", range(44))
+def test_compiled_programs_match_the_oracle_on_random_models(seed, hostcheck_lib):
+    L = hostcheck_lib
+    big = {40: (20011, 1), 41: (8193, 4), 42: (1, 4), 43: (3, 4)}
+    core, x, y = random_model(seed, *big.get(seed, (None, None)))
+    om = _oracle(core)
+    m = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L)
+    assert (m.meta.nvar, m.meta.ncon, m.meta.nnzj, m.meta.nnzh) == (om.nvar, om.ncon, om.nnzj, om.nnzh)
+
+    def hc(which, n, yy=None, s=1.0):
+        out = np.zeros(max(n, 1))
+        assert L.hostcheck_eval_groups(m.h, which, x.ctypes.data, None if yy is None else yy.ctypes.data, s, out.ctypes.data, None) == 0
+        return out[:n]
+
+    assert_close(hc(0, 1)[0], om.obj(x), "obj")
+    assert_close(hc(1, om.nvar), om.grad(x), "grad")
+    assert_close(hc(2, om.ncon), om.cons(x), "cons")
+    assert_close(hc(3, om.nnzj), om.jac_coord(x), "jac")
+    assert_close(hc(4, om.nnzh, y, 0.6), om.hess_coord(x, y, 0.6), "hess")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_gpu(), reason="needs a CUDA device")
+@pytest.mark.parametrize("seed", range(30))
+def test_cuda_engine_matches_the_oracle_on_random_models(seed):
+    import torch
+    # the last seeds use support counts large enough for the arithmetic block schedule (>= 64 blocks per group), with
+    # ragged ends, and a product iterator over them
+    big = {24: (20011, 1), 25: (9000, 1), 26: (8193, 4), 27: (33333, 1), 28: (12800, 1), 29: (10007, 3)}
+    core, x, y = random_model(1000 + seed, *big.get(seed, (None, None)))
+    om = _oracle(core)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    for flags in (ex.lib.IEXA_F_DEFAULT, ex.lib.IEXA_F_NO_SPECIALISE):
+        m = ex.ExaModel(core, device=0, flags=flags)
+        if flags == ex.lib.IEXA_F_DEFAULT:
+            assert m.cmeta.n_kernels_specialised > 0, m.L.iexa_engine_note(m.h).decode()
+        z = lambda n, dt=torch.float64: torch.zeros(max(int(n), 1), dtype=dt, device="cuda")
+        c, jv, hv, g = z(om.ncon), z(om.nnzj), z(om.nnzh), z(om.nvar)
+        ex.cons_(m, xd, c); ex.jac_coord_(m, xd, jv); ex.hess_coord_(m, xd, yd, hv, 0.6); ex.grad_(m, xd, g)
+        n = lambda t, k: t.cpu().numpy()[:k]
+        assert_close(ex.obj(m, xd), om.obj(x), "obj")
+        assert_close(n(g, om.nvar), om.grad(x), "grad")
+        assert_close(n(c, om.ncon), om.cons(x), "cons")
+        assert_close(n(jv, om.nnzj), om.jac_coord(x), "jac")
+        assert_close(n(hv, om.nnzh), om.hess_coord(x, y, 0.6), "hess")
+        jr, jc = z(om.nnzj, torch.int32), z(om.nnzj, torch.int32)
+        hr, hc = z(om.nnzh, torch.int32), z(om.nnzh, torch.int32)
+        ex.jac_structure_(m, jr, jc); ex.hess_structure_(m, hr, hc)
+        ro, co = om.jac_structure()
+        assert np.array_equal(n(jr, om.nnzj), ro) and np.array_equal(n(jc, om.nnzj), co), "jac structure"
+        ro, co = om.hess_structure()
+        assert np.array_equal(n(hr, om.nnzh), ro) and np.array_equal(n(hc, om.nnzh), co), "hess structure"

@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-bash tools/gpu_profile.sh v8
+( time python -m pytest tests/test_fuzz.py -m gpu -x -q ) > gpurun_out/s25_fuzz.log 2>&1
