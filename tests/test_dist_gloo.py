@@ -36,6 +36,16 @@ class HostEvaluator:
     def hess_coord_(self, x, y, v, w): return self._run(4, x, y, w, v)
 
 
+def _case_core(case):
+    """named model, or ``fuzz<seed>``: a random model of tests/test_fuzz.py (arbitrary integer columns, product iterators)"""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from iexa_b200 import models
+    if case.startswith("fuzz"):
+        import test_fuzz
+        return test_fuzz.random_model(int(case[4:]), K1=130, K2=4)[0]
+    return {"ode_5x5": models.ode_5x5, "quadrotor": lambda: models.quadrotor(13, "oc"), "farmer": lambda: models.farmer(23)}[case]()
+
+
 def _worker(rank, world, port, case, q):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -47,8 +57,7 @@ def _worker(rank, world, port, case, q):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         L = ex.lib.load(os.path.join(ROOT, "tests", "hostcheck", "libiexa_hostcheck.so"))
-        core = {"ode_5x5": models.ode_5x5, "quadrotor": lambda: models.quadrotor(13, "oc"),
-                "farmer": lambda: models.farmer(23)}[case]()
+        core = _case_core(case)
         sm = ShardedExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L)
         sm._ev = HostEvaluator(L, sm.model)
         x, y = eval_point(core, seed=4)
@@ -67,7 +76,7 @@ def _worker(rank, world, port, case, q):
         cover = 0
         for s0, ln in sm.x_ranges():
             xp[s0:s0 + ln] = x[s0:s0 + ln]; cover += ln
-        assert world == 1 or case == "ode_5x5" or cover < core.nvar, "x ranges are not a proper subset"
+        assert world == 1 or case == "ode_5x5" or case.startswith("fuzz") or cover < core.nvar, "x ranges are not a proper subset"
         c2 = sm.cons_(xp, np.zeros(max(sm.model.loc_ncon, 1)))
         jv2 = sm.jac_coord_(xp, np.zeros(max(sm.model.loc_nnzj, 1)))
         hv2 = sm.hess_coord_(xp, yl, np.zeros(max(sm.model.loc_nnzh, 1)), 0.7)
@@ -94,7 +103,7 @@ def _worker(rank, world, port, case, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,world", [("ode_5x5", 2), ("quadrotor", 2), ("quadrotor", 3), ("farmer", 2)])
+@pytest.mark.parametrize("case,world", [("ode_5x5", 2), ("quadrotor", 2), ("quadrotor", 3), ("farmer", 2), ("fuzz7", 3), ("fuzz11", 2)])
 def test_sharded_evaluation_matches_oracle(case, world, hostcheck_lib):
     import torch.multiprocessing as mp
     sys.path.insert(0, ROOT)
@@ -120,8 +129,7 @@ def test_sharded_evaluation_matches_oracle(case, world, hostcheck_lib):
         p.join(timeout=60)
         assert p.exitcode == 0, "a rank failed"
     assert res is not None
-    core = {"ode_5x5": models.ode_5x5, "quadrotor": lambda: models.quadrotor(13, "oc"),
-            "farmer": lambda: models.farmer(23)}[case]()
+    core = _case_core(case)
     om = OracleModel(core)
     x, y = eval_point(core, seed=4)
     assert abs(res["f"] - om.obj(x)) <= 1e-12 * max(1.0, abs(om.obj(x)))
