@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-( time python -m pytest tests/test_fuzz.py -m gpu -x -q ) > gpurun_out/s25_fuzz.log 2>&1
+./tools/stream_probe > gpurun_out/s28_probe.log 2>&1
