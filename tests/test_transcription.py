@@ -157,3 +157,34 @@ def test_constrained_measure_is_expanded_inline_with_a_warning():
     r, c = om.jac_structure()
     J = np.zeros(6); np.add.at(J, c - 1, om.jac_coord(x))
     assert np.allclose(J, np.r_[1.0, 2 * w * x[1:]], atol=1e-14)
+
+
+@pytest.mark.parametrize("method,degree", [(io.FiniteDifference("backward"), 1), (io.FiniteDifference("forward"), 1),
+                                           (io.FiniteDifference("central"), 1), (io.OrthogonalCollocation(3), 2),
+                                           (io.OrthogonalCollocation(4), 3), (io.OrthogonalCollocation(5), 4)])
+def test_derivative_approximation_rows_are_exact_for_polynomials(method, degree):
+    """The derivative-approximation generators (transform.jl:511-562 with InfiniteOpt's derivative_expr_data: finite
+    differences, orthogonal collocation with num_nodes Lobatto nodes per interval) vanish when y is a polynomial of the
+    degree the scheme integrates exactly (on NON-uniform public supports: 1 for the finite differences, num_nodes - 1 for
+    collocation) and the derivative variable holds y' — evaluated
+    through the oracle at x = (y(t_i), y'(t_i))."""
+    from oracle.oracle import OracleModel
+    m = io.InfiniteModel()
+    pub = np.array([0.0, 0.3, 0.35, 1.1, 2.0, 2.05, 3.0])
+    t = m.infinite_parameter(supports=pub, derivative_method=method)
+    y = m.variable(t)
+    m.constraint(m.deriv(y, t), "==", 1.0)           # any constraint that brings the derivative variable in
+    m.objective("Min", m.integral(y ** 2, t))
+    core, data = exa_core(m)
+    ts = data.supports[0]
+    T = len(ts)
+    coef = np.array([0.7, -1.3, 0.5, 0.25, -0.125])[:degree + 1]
+    p = np.polynomial.Polynomial(coef)
+    x = np.concatenate([p(ts), p.deriv()(ts)])       # layout: y block, then the derivative variable (transform.jl:141-144)
+    assert core.nvar == 2 * T
+    om = OracleModel(core)
+    c = om.cons(x)
+    rows = c[T:]                                      # the approximation rows follow the T rows of the constraint
+    assert len(rows) >= T - 2 and np.max(np.abs(rows)) <= 1e-12, np.max(np.abs(rows))
+    if isinstance(method, io.OrthogonalCollocation):
+        assert T == len(pub) + (method.num_nodes - 2) * (len(pub) - 1)      # internal nodes (transform.jl:22)
