@@ -52,6 +52,7 @@ struct GeneratedSource {
 };
 
 int spec_block(); // threads per block of the specialised kernels (env IEXA_BLOCK, default 128)
+int class_chunk(); // instances of a shape class per block (env IEXA_CLASS_CHUNK, default 8)
 GeneratedSource generate_source(const Plan &plan);
 bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string &err);
 

@@ -1,7 +1,7 @@
 """scratch timing of the callbacks on any config model (not a test).
 
 usage: python tests/quick_bench.py <model> <size> [flags]
-  model: quad | quadfd | pandemic | pandemic128 | opf | opf30 | farmer
+  model: quad | quadfd | pandemic | pandemic128 | opf | opf30 | opf118 | farmer
 """
 import os
 import sys
@@ -26,6 +26,7 @@ core = {"quad": lambda: models.quadrotor(N, "oc"), "quadfd": lambda: models.quad
         "pandemic": lambda: models.pandemic(N, 4), "pandemic128": lambda: models.pandemic(N, 128),
         "opf": lambda: exa_core(opf.opf(None, num_supports=N))[0],
         "opf30": lambda: exa_core(opf.opf(opf.synthetic_grid(30), num_supports=N))[0],
+        "opf118": lambda: exa_core(opf.opf(opf.synthetic_grid(118), num_supports=N))[0],
         "farmer": lambda: models.farmer(N)}[name]()
 t1 = time.time()
 m = ex.ExaModel(core, device=0, flags=flags)
