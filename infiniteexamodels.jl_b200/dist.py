@@ -186,6 +186,21 @@ class ShardedExaModel:
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)  # slices are disjoint
         return out
 
+    def gather_rows(self, local_vec, offset: int, size: int):
+        """rows ``offset .. offset+size`` (0-based, global numbering) of a row-sharded vector — the multipliers or the
+        constraint values of ONE constraint (``map_dual``, infiniteopt_backend.jl:490-508, on sharded buffers): every
+        rank contributes the rows it owns, an all-reduce of ``size`` doubles assembles them on all ranks."""
+        torch = self.torch
+        t = torch.as_tensor(local_vec)
+        out = torch.zeros(size, dtype=t.dtype, device=t.device)
+        for gs, ls, ln in self.segments(0):
+            lo, hi = max(gs, offset), min(gs + ln, offset + size)
+            if lo < hi:
+                out[lo - offset:hi - offset] = t[ls + (lo - gs):ls + (hi - gs)]
+        if self.world > 1:
+            self.dist.all_reduce(out, op=self.dist.ReduceOp.SUM, group=self.group)
+        return out
+
     # ---- callbacks ------------------------------------------------------------------------------
     def _reduce_scalar(self, v: float, like=None) -> float:
         if self.world == 1:

@@ -94,6 +94,10 @@ def _worker(rank, world, port, case, q):
         c3 = sm.cons_(xo, np.zeros(max(sm.model.loc_ncon, 1)))
         jv3 = sm.jac_coord_(xo, np.zeros(max(sm.model.loc_nnzj, 1)))
         assert np.array_equal(c3, c) and np.array_equal(jv3, jv), "halo exchange left a read range stale"
+        # map_dual on sharded buffers: the multipliers of ONE constraint (rows of one generator) from the local slices
+        gcon = core.cons[min(1, len(core.cons) - 1)]
+        d = sm.gather_rows(yl, gcon.row_offset, gcon.itr.K).numpy()
+        assert np.array_equal(d, y[gcon.row_offset:gcon.row_offset + gcon.itr.K]), "gather_rows"
         # owned gradient entries: sum over ranks of the per-rank g must double-count ONLY the shared slice
         gsum = torch.from_numpy(g.copy()); dist.all_reduce(gsum)
         if rank == 0:
