@@ -157,6 +157,33 @@ def test_callbacks_capture_into_a_cuda_graph(mode, oracle_cache):
         xd += 0.01 * torch.cos(torch.arange(xd.numel(), device="cuda", dtype=torch.float64))  # next iterate, same buffers
 
 
+def test_device_objective_and_explicit_page_locking(oracle_cache):
+    """iexa_obj_device (no host synchronisation: the objective lands in a device double, what a GPU-resident solver or
+    the multi-GPU all-reduce consumes) and iexa_host_register / iexa_host_unregister (explicit page-locking of the
+    caller's host vectors for the Ipopt-style path)."""
+    import ctypes as C
+    import torch
+    core, om = _oracle(oracle_cache, "pandemic_50x4")
+    m = ex.ExaModel(core, device=0)
+    L = m.L
+    x, y = eval_point(core, seed=5)
+    xd = torch.from_numpy(x).cuda()
+    fd = torch.zeros(1, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.iexa_obj_device(m.h, C.c_void_p(xd.data_ptr()), C.c_void_p(fd.data_ptr()), C.c_void_p(st)) == 0, L.iexa_last_error()
+    assert_close(fd.item(), om.obj(x), "obj_device")
+    # page-lock the caller's vectors, evaluate through the host path, unlock
+    xh = x.copy(); jv = np.zeros(om.nnzj)
+    for buf in (xh, jv):
+        assert L.iexa_host_register(m.h, C.c_void_p(buf.ctypes.data), buf.nbytes) == 0, L.iexa_last_error()
+    assert_close(ex.jac_coord_(m, xh, jv), om.jac_coord(x), "jac_coord through registered host buffers")
+    assert L.iexa_host_register(m.h, C.c_void_p(xh.ctypes.data), xh.nbytes) == 0       # registering twice is a no-op
+    for buf in (xh, jv):
+        assert L.iexa_host_unregister(m.h, C.c_void_p(buf.ctypes.data)) == 0, L.iexa_last_error()
+    assert L.iexa_host_unregister(m.h, C.c_void_p(jv.ctypes.data)) == 0                # so is unregistering twice
+    assert_close(ex.jac_coord_(m, xh, jv), om.jac_coord(x), "jac_coord after unregistering")
+
+
 def test_parameter_update_in_place(oracle_cache):
     """set_parameter! semantics (infiniteopt_backend.jl:511-548): θ changes, no plan rebuild."""
     import torch
