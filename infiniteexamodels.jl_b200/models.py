@@ -152,13 +152,15 @@ def ode_5x5(nt: int = 5, nx: int = 5) -> ExaCore:
 
 
 # ------------------------------------------------------------------------------------------------
-def pandemic(num_supports: int = 100, num_scenarios: int = 4, seed: int = 0) -> ExaCore:
-    """ESCAPE34/pandemic.jl:4-34 — SEIR optimal control, backward FD in t, scenarios ξ~U(0.1,0.6)."""
+def pandemic(num_supports: int = 100, num_scenarios: int = 4, seed: int = 0, xi=None) -> ExaCore:
+    """ESCAPE34/pandemic.jl:4-34 — SEIR optimal control, backward FD in t, scenarios ξ~U(0.1,0.6) (``xi``: explicit
+    scenario supports, e.g. the ones a Julia run drew — julia/dump_golden.jl writes them next to its dump)."""
     gamma, beta, Npop = 0.303, 0.727, 1e5
     extra = np.array([0.001, 0.002, 0.004, 0.008, 0.02, 0.04, 0.08, 0.2, 0.4, 0.8])
     ts = np.unique(np.concatenate([np.linspace(0, 200, int(num_supports)), extra]))
     T, S = len(ts), int(num_scenarios)
-    xi = np.random.default_rng(seed).uniform(0.1, 0.6, S)
+    xi = np.random.default_rng(seed).uniform(0.1, 0.6, S) if xi is None else np.asarray(xi, dtype=np.float64)
+    assert len(xi) == S
     core = ExaCore(minimize=True)
     ds = DataSource()
     it_t = Itr(T, {"group_idx1": np.arange(1, T + 1)}, {"ip1": ts})

@@ -49,4 +49,9 @@ dump("ode_5x5", ode_5x5(), dir)
 include(joinpath(@__DIR__, "..", "..", "reference", "ESCAPE34", "quadrotor.jl"))   # adjust to the checkout
 dump("quadrotor_oc_40", quad(num_supports = 40), dir)
 include(joinpath(@__DIR__, "..", "..", "reference", "ESCAPE34", "pandemic.jl"))
-dump("pandemic_50x4", pandemic(num_supports = 50, num_scenarios = 4), dir)
+pm = pandemic(num_supports = 50, num_scenarios = 4)
+dump("pandemic_50x4", pm, dir)
+# Julia's RNG stream cannot be reproduced in Python: hand the drawn scenario supports to the test next to the dump
+open(joinpath(dir, "pandemic_50x4.xi"), "w") do io
+    write(io, Float64.(vec(supports(pm[:ξ]))))
+end

@@ -11,8 +11,14 @@ import iexa_b200 as ex
 from iexa_b200 import models
 from conftest import ROOT, assert_close
 
+def _pandemic():
+    xi_file = os.path.join(ROOT, "tests", "golden", "pandemic_50x4.xi")   # scenario supports the Julia run drew
+    xi = np.fromfile(xi_file, dtype="<f8") if os.path.exists(xi_file) else None
+    return models.pandemic(50, 4, xi=xi)
+
+
 BUILDERS = {"ode_5x5": lambda: models.ode_5x5(), "quadrotor_oc_40": lambda: models.quadrotor(40, "oc"),
-            "pandemic_50x4": lambda: models.pandemic(50, 4)}
+            "pandemic_50x4": _pandemic}
 DUMPS = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.golden")))
 
 
@@ -34,6 +40,29 @@ def load(path):
 @pytest.mark.skipif(not DUMPS, reason="no ExaModels dump present (needs Julia; see julia/dump_golden.jl)")
 @pytest.mark.parametrize("path", DUMPS)
 def test_against_exa_models_dump(path, hostcheck_lib):
+    compare_with_dump(path, hostcheck_lib)
+
+
+def test_dump_harness_on_a_dump_written_by_the_oracle(tmp_path, hostcheck_lib):
+    """The comparison above has never seen a real dump (no Julia here).  This runs the SAME loader and comparison on a
+    file in julia/dump_golden.jl's binary format whose contents come from the oracle, so that the day a real dump is
+    dropped into tests/golden/ the harness itself is known to work — it pins nothing about ExaModels."""
+    from oracle.oracle import OracleModel
+    from conftest import eval_point
+    core = BUILDERS["quadrotor_oc_40"]()
+    om = OracleModel(core)
+    x, y = eval_point(core, seed=0)
+    jr, jc = om.jac_structure(); hr, hc = om.hess_structure()
+    path = tmp_path / "quadrotor_oc_40.golden"
+    with open(path, "wb") as f:
+        for a in (np.array([om.nvar, om.ncon, om.nnzj, om.nnzh], dtype="<i8"), x, y, np.array([0.7]), np.array([om.obj(x)]),
+                  om.grad(x), om.cons(x), jr.astype("<i8"), jc.astype("<i8"), om.jac_coord(x), hr.astype("<i8"),
+                  hc.astype("<i8"), om.hess_coord(x, y, 0.7)):
+            f.write(np.ascontiguousarray(a).tobytes())
+    compare_with_dump(str(path), hostcheck_lib)
+
+
+def compare_with_dump(path, hostcheck_lib):
     name = os.path.splitext(os.path.basename(path))[0]
     d = load(path)
     L = hostcheck_lib
