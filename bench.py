@@ -8,7 +8,8 @@ roofline target is quoted on; it fits one B200).  With --gpus N the SAME model i
 contiguous support blocks over N ranks (strong scaling, no data-path collective: every rank owns
 its rows / Jacobian slots / Hessian slots).
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference's
+`--workload pandemic` runs the same contract on BASELINE.json configs[1] (ESCAPE34/pandemic.jl, 10^5 time supports x 4
+scenarios; small: a few waves of blocks per kernel).  Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference's
 evaluator (oracle/, all host threads) on a bounded sample of the same workload — ExaModels.jl
 itself cannot be installed here (no Julia, no network).
 """
@@ -27,7 +28,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "ESCAPE34/quadrotor.jl OC(3), 10^6 time supports: cons!+jac_coord!+hess_coord!"
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the north-star evals/s / roofline / 8-GPU targets are quoted on (default)
+    "quadrotor": dict(name="ESCAPE34/quadrotor.jl OC(3), 10^6 time supports: cons!+jac_coord!+hess_coord!", supports=1_000_000,
+                      cpu_sample=20_000, build=lambda n: __import__("iexa_b200").models.quadrotor(n, "oc")),
+    # BASELINE.json configs[1]: SEIR optimal control, 10^5 time supports x 4 scenarios (small: a few waves per kernel)
+    "pandemic": dict(name="ESCAPE34/pandemic.jl, 10^5 time supports x 4 scenarios: cons!+jac_coord!+hess_coord!", supports=100_000,
+                     cpu_sample=20_000, build=lambda n: __import__("iexa_b200").models.pandemic(n, 4)),
+}
+WORKLOAD = WORKLOADS["quadrotor"]["name"]
 METRIC = "cons+jac+hess evals/s"
 UNIT = "evals/s"
 
@@ -38,12 +47,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--supports", type=int, default=1_000_000, help="public time supports (default: the named size)")
-    ap.add_argument("--cpu-sample", type=int, default=20_000, help="supports of the bounded CPU sample")
+    ap.add_argument("--workload", default="quadrotor", choices=sorted(WORKLOADS), help="BASELINE.json configuration (default: configs[2])")
+    ap.add_argument("--supports", type=int, default=None, help="public time supports (default: the named size of the workload)")
+    ap.add_argument("--cpu-sample", type=int, default=None, help="supports of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--interp", action="store_true", help="AOT tape-interpreter kernels only (no NVRTC)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    args.supports = w["supports"] if args.supports is None else args.supports
+    args.cpu_sample = w["cpu_sample"] if args.cpu_sample is None else args.cpu_sample
+    args.build, args.workload_name = w["build"], w["name"]
+    return args
 
 
 class ClockSampler:
@@ -96,7 +111,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_eval_rate(sample_supports: int, full_supports: int, threads: int, reps: int = 2):
+def cpu_eval_rate(build, full_rows: int, sample_supports: int, threads: int, reps: int = 2):
     """evals/s of the oracle (CPU restatement of the reference evaluator) on a bounded sample,
     scaled linearly to the full support count."""
     import iexa_b200 as ex  # noqa: F401  (models only; the oracle does the arithmetic)
@@ -104,10 +119,10 @@ def cpu_eval_rate(sample_supports: int, full_supports: int, threads: int, reps: 
     from oracle import oracle as orc
     from oracle.oracle import OracleModel
     orc.set_threads(threads)
-    core = models.quadrotor(sample_supports, "oc")
+    core = build(sample_supports)
     om = OracleModel(core)
     rng = np.random.default_rng(0)
-    x = core.x0_vec + 0.1 * rng.uniform(-1, 1, core.nvar)
+    x = np.where(np.isfinite(core.x0_vec), core.x0_vec, 0.0) + 0.1 * rng.uniform(-1, 1, core.nvar)
     y = rng.uniform(-1, 1, core.ncon)
     om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)  # warm-up
     ts = []
@@ -116,7 +131,7 @@ def cpu_eval_rate(sample_supports: int, full_supports: int, threads: int, reps: 
         om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)
         ts.append(time.perf_counter() - t0)
     t = min(ts)
-    scale = (2 * full_supports - 1) / (2 * sample_supports - 1)
+    scale = full_rows / core.ncon          # rows (and slots) are proportional to the number of supports
     return 1.0 / (t * scale), t
 
 
@@ -131,10 +146,10 @@ def run_reference(args):
     from oracle.oracle import OracleModel
     orc.set_threads(threads)
     ns = args.cpu_sample
-    core = models.quadrotor(ns, "oc")
+    core = args.build(ns)
     om = OracleModel(core)
     rng = np.random.default_rng(0)
-    x = core.x0_vec + 0.1 * rng.uniform(-1, 1, core.nvar)
+    x = np.where(np.isfinite(core.x0_vec), core.x0_vec, 0.0) + 0.1 * rng.uniform(-1, 1, core.nvar)
     y = rng.uniform(-1, 1, core.ncon)
     for _ in range(args.warmup):
         om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)
@@ -142,7 +157,8 @@ def run_reference(args):
     for _ in range(args.steps):
         om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    scale = (2 * args.supports - 1) / (2 * ns - 1)
+    full = args.build(args.supports) if args.supports <= 200_000 else None
+    scale = (full.ncon / core.ncon) if full is not None else (2 * args.supports - 1) / (2 * ns - 1)   # quadrotor: T = 2N - 1 supports
     v = 1.0 / (dt * scale)
     sample = (f"oracle (C restatement of ExaModels' per-support recursive AD, OpenMP over supports) on "
               f"{ns} of {args.supports} public supports, time scaled linearly by {scale:.1f}")
@@ -150,7 +166,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "supports": args.supports},
+        "config": {"workload": args.workload_name, "supports": args.supports},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "ExaModels.jl (the reference's evaluator) is not installable offline: no Julia, no network",
@@ -177,11 +193,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    core = models.quadrotor(args.supports, "oc")
+    core = args.build(args.supports)
     flags = ex.lib.IEXA_F_NO_SPECIALISE if args.interp else ex.lib.IEXA_F_DEFAULT
     m = ex.ExaModel(core, device=local_rank, rank=rank, world=world, flags=flags)
     rng = np.random.default_rng(0)
-    x_h = core.x0_vec + 0.1 * rng.uniform(-1, 1, core.nvar)
+    x_h = np.where(np.isfinite(core.x0_vec), core.x0_vec, 0.0) + 0.1 * rng.uniform(-1, 1, core.nvar)
     y_full = rng.uniform(-1, 1, core.ncon)
     # this rank's multipliers, in its local row layout
     segs = (ex.lib.Segment * 4096)()
@@ -373,7 +389,7 @@ def main():
 
     cpu = None
     if not args.no_cpu and world == 1:
-        v1, t1 = cpu_eval_rate(args.cpu_sample, args.supports, 1)
+        v1, t1 = cpu_eval_rate(args.build, int(m.meta.ncon), args.cpu_sample, 1)
         cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"oracle (C restatement of ExaModels' sequential per-support AD) on {args.cpu_sample} of "
                          f"{args.supports} public supports ({t1:.2f} s/eval measured), scaled linearly; ExaModels' "
@@ -383,7 +399,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "supports": args.supports, "nvar": int(m.meta.nvar), "ncon": int(m.meta.ncon),
+        "config": {"workload": args.workload_name, "supports": args.supports, "nvar": int(m.meta.nvar), "ncon": int(m.meta.ncon),
                    "nnzj": int(m.meta.nnzj), "nnzh": int(m.meta.nnzh), "sharding": f"contiguous support blocks x{world}",
                    "l2": "inputs larger than L2 (x = %.0f MB, outputs %.1f GB per eval)" % (m.meta.nvar * 8 / 1e6, (m.loc_nnzj + m.loc_nnzh + m.loc_ncon) * 8 / 1e9),
                    "kernels": "interpreter" if args.interp else f"nvrtc-specialised ({m.cmeta.n_kernels_specialised})"},
