@@ -212,6 +212,18 @@ class ShardedExaModel:
         return float(t.item())
 
     def obj(self, x) -> float:
+        torch = self.torch
+        if self._ev is None and isinstance(x, torch.Tensor) and x.is_cuda:
+            # device path: the rank's partial stays on the GPU (iexa_obj_device, no host synchronisation), NCCL
+            # all-reduces the one double, and the only synchronisation is the final read
+            m = self.model
+            if getattr(self, "_fdev", None) is None or self._fdev.device != x.device:
+                self._fdev = torch.zeros(1, dtype=torch.float64, device=x.device)
+            st = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(m.L, m.L.iexa_obj_device(m.h, C.c_void_p(x.data_ptr()), C.c_void_p(self._fdev.data_ptr()), C.c_void_p(st)))
+            if self.world > 1:
+                self.dist.all_reduce(self._fdev, op=self.dist.ReduceOp.SUM, group=self.group)
+            return float(self._fdev.item())
         part = self._ev.obj(x) if self._ev else _m.obj(self.model, x)
         return self._reduce_scalar(part, x)
 
