@@ -182,6 +182,26 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__r
   if (threadIdx.x == 0) out[0] = red[0];
 }
 
+// zero-fill of the gradient entries no single-writer slot covers: ALL ranges in one launch (one cudaMemsetAsync per
+// range is one stream operation each — four for the quadrotor, dozens for models with many variable blocks).
+// ranges: [start, length] pairs (doubles); 16-byte stores where the alignment allows
+__global__ void __launch_bounds__(256) zero_ranges_kernel(const long long *__restrict__ ranges, int nranges,
+                                                          double *__restrict__ g) {
+  for (int r = blockIdx.y; r < nranges; r += gridDim.y) {
+    const long long s = ranges[2 * r], n = ranges[2 * r + 1];
+    double *p = g + s;
+    const long long head = (n > 0 && (((unsigned long long)p >> 3) & 1ull)) ? 1 : 0;
+    const long long npair = (n - head) >> 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      if (head) p[0] = 0.0;
+      if ((n - head) & 1) p[n - 1] = 0.0;
+    }
+    double2 *q = reinterpret_cast<double2 *>(p + head);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += (long long)gridDim.x * blockDim.x)
+      q[i] = make_double2(0.0, 0.0);
+  }
+}
+
 // rows/cols of the Jacobian (which=0) or lower-triangular Hessian (which=1); 1-based
 template <typename IT>
 __global__ void __launch_bounds__(BLOCK)
@@ -370,7 +390,20 @@ class CudaEngine : public Engine {
     double *gd = g;
     if (memspace == IEXA_MEM_HOST) { CK(stage_out_.ensure((size_t)plan_.nvar * 8)); gd = stage_out_.as<double>(); }
     // only the entries that are not written by a single-writer slot need zero-filling
-    for (auto &zr : plan_.grad_zero_ranges) CK(cudaMemsetAsync(gd + zr.first, 0, (size_t)zr.second * 8, st));
+    if (!plan_.grad_zero_ranges.empty()) {
+      const int nr = (int)plan_.grad_zero_ranges.size();
+      if (!zero_ranges_.p) {
+        std::vector<long long> rr;
+        for (auto &zr : plan_.grad_zero_ranges) { rr.push_back(zr.first); rr.push_back(zr.second); }
+        CK(zero_ranges_.ensure(rr.size() * 8));
+        CK(cudaMemcpy(zero_ranges_.p, rr.data(), rr.size() * 8, cudaMemcpyHostToDevice));
+      }
+      int64_t longest = 0;
+      for (auto &zr : plan_.grad_zero_ranges) longest = std::max<int64_t>(longest, zr.second);
+      const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((longest / 2 + 255) / 256, 148 * 8));
+      zero_ranges_kernel<<<dim3(gx, std::min(nr, 65535)), 256, 0, st>>>(zero_ranges_.as<long long>(), nr, gd);
+      CK(cudaGetLastError());
+    }
     rc = launch(CB_GRAD, PROG_D1, SINK_SCATTER, xd, nullptr, 1.0, gd, st, err);
     if (rc) return rc;
     return out(g, gd, plan_.nvar, memspace, st, err);
@@ -408,6 +441,7 @@ class CudaEngine : public Engine {
     if (cb < 0 || cb >= CB__N) return 0;
     int n = table_[cb].nblocks > 0 ? 1 : 0;
     if (cb == CB_OBJ && n) n += 1;
+    if (cb == CB_GRAD && n && !plan_.grad_zero_ranges.empty()) n += 1;
     return n;
   }
   int n_specialised() const override { return spec_ ? spec_->n_kernels() : 0; }
@@ -424,6 +458,7 @@ class CudaEngine : public Engine {
   int device_;
   uint32_t flags_;
   DevBuf leaf_, desc_, gens_, theta_, work_;
+  DevBuf zero_ranges_;
   DevBuf partials_, fdev_, stage_x_, stage_y_, stage_v_, stage_out_, stage_a_, stage_b_, scratch_;
   DevBuf coo_rows_j_, coo_cols_j_, coo_rows_h_, coo_cols_h_, coo_vals_;
   bool coo_j_ready_ = false, coo_h_ready_ = false;
