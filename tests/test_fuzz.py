@@ -9,6 +9,8 @@ parameters, ragged support counts around the block size.
 
 This is the net under the code generator's special cases (affine columns, 32-bit index arithmetic, loads issued first,
 sincos pairing, arithmetic block schedule, staged tile write-out)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -90,7 +92,7 @@ def _oracle(core):
     return OracleModel(core)
 
 
-@pytest.mark.parametrize("seed", range(44))
+@pytest.mark.parametrize("seed", list(range(44)) + list(range(100, 100 + int(os.environ.get("IEXA_FUZZ_SEEDS", "0")))))
 def test_compiled_programs_match_the_oracle_on_random_models(seed, hostcheck_lib):
     L = hostcheck_lib
     big = {40: (20011, 1), 41: (8193, 4), 42: (1, 4), 43: (3, 4)}
@@ -113,7 +115,8 @@ def test_compiled_programs_match_the_oracle_on_random_models(seed, hostcheck_lib
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not has_gpu(), reason="needs a CUDA device")
-@pytest.mark.parametrize("seed", range(30))
+# IEXA_FUZZ_SEEDS=<n> widens the seeded sweep (a one-off hunt: 150 extra seeds on the GPU and 400 on the host executor were run green at the end of round 1)
+@pytest.mark.parametrize("seed", list(range(30)) + list(range(100, 100 + int(os.environ.get("IEXA_FUZZ_SEEDS", "0")))))
 def test_cuda_engine_matches_the_oracle_on_random_models(seed):
     import torch
     # the last seeds use support counts large enough for the arithmetic block schedule (>= 64 blocks per group), with
