@@ -242,4 +242,90 @@ function Base.getproperty(m::B200ExaModel, s::Symbol)
     return getfield(m, s)
 end
 
+"page-lock a host vector the solver reuses every iteration (Ipopt path): copies then run at PCIe speed"
+function page_lock!(m::B200ExaModel, v::Array{Float64})
+    GC.@preserve v check(ccall((:iexa_host_register, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), m.plan.h, _ptr(v), sizeof(v)))
+    return v
+end
+function page_unlock!(m::B200ExaModel, v::Array{Float64})
+    GC.@preserve v check(ccall((:iexa_host_unregister, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), m.plan.h, _ptr(v)))
+    return v
+end
+
+"objective into a device scalar, no host synchronisation (GPU-resident solvers; the partial of a sharded model)"
+function obj_device!(m::B200ExaModel, x::CuArray{Float64}, f::CuArray{Float64})
+    GC.@preserve x f check(ccall((:iexa_obj_device, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                                 m.plan.h, _ptr(x), _ptr(f), _st(x)))
+    return f
+end
+
+# ---- multi-GPU queries (one Julia process per GPU; iexa_finalize(rank, world) shards the supports) ---------------------
+struct IexaSegment
+    global_start::Int64
+    local_start::Int64
+    length::Int64
+end
+
+"local ranges of rows (0) / Jacobian slots (1) / Hessian slots (2) and their global positions (0-based)"
+function segments(m::B200ExaModel, which::Integer)
+    n = ccall((:iexa_segments, LIB), Int64, (Ptr{Cvoid}, Int32, Ptr{IexaSegment}, Int64), m.plan.h, which, C_NULL, 0)
+    out = Vector{IexaSegment}(undef, max(n, 0))
+    n > 0 && ccall((:iexa_segments, LIB), Int64, (Ptr{Cvoid}, Int32, Ptr{IexaSegment}, Int64), m.plan.h, which, out, n)
+    return out
+end
+
+"1-based variable indices whose gradient entries must be all-reduced after grad! (NCCL.jl on the same buffer)"
+function shared_vars(m::B200ExaModel)
+    n = ccall((:iexa_shared_vars, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Int64), m.plan.h, C_NULL, 0)
+    out = Vector{Int64}(undef, max(n, 0))
+    n > 0 && ccall((:iexa_shared_vars, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Int64), m.plan.h, out, n)
+    return out
+end
+
+"the ranges of x this rank reads (own supports + shared variables + halos): what a distributed solver keeps current here"
+function x_ranges(m::B200ExaModel)
+    n = ccall((:iexa_x_ranges, LIB), Int64, (Ptr{Cvoid}, Ptr{IexaSegment}, Int64), m.plan.h, C_NULL, 0)
+    out = Vector{IexaSegment}(undef, max(n, 0))
+    n > 0 && ccall((:iexa_x_ranges, LIB), Int64, (Ptr{Cvoid}, Ptr{IexaSegment}, Int64), m.plan.h, out, n)
+    return out
+end
+
+# ---- KKT assembly: COO -> CSR value map for cuDSS (replaces MadNLPGPU's transfer! kernel) ------------------------------
+mutable struct CsrMap
+    h::Ptr{Cvoid}
+    nnz::Int64
+end
+
+"locality keys of the Jacobian (0) / Hessian (1) COO slots, for `CsrMap(...; keys)` of patterns with duplicates"
+function coo_locality!(m::B200ExaModel, which::Integer, keys::AbstractVector{Int32})
+    GC.@preserve keys check(ccall((:iexa_coo_locality, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32, Ptr{Cvoid}),
+                                  m.plan.h, which, _ptr(keys), _ms(keys), _st(keys)))
+    return keys
+end
+
+function CsrMap(nrows::Integer, ncols::Integer, rows::AbstractVector{T}, cols::AbstractVector{T};
+                keys::Union{Nothing,AbstractVector{Int32}} = nothing, device::Integer = 0) where {T<:Integer}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve rows cols keys check(ccall((:iexa_csr_create_keyed, LIB), Int32,
+        (Ref{Ptr{Cvoid}}, Int64, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32, Int32),
+        h, nrows, ncols, length(rows), _ptr(rows), _ptr(cols), sizeof(T), _ptr(keys), _ms(rows), device))
+    c = CsrMap(h[], ccall((:iexa_csr_nnz, LIB), Int64, (Ptr{Cvoid},), h[]))
+    finalizer(c -> ccall((:iexa_csr_destroy, LIB), Int32, (Ptr{Cvoid},), c.h), c)
+    return c
+end
+
+"0-based CSR pattern (cuDSS convention)"
+function pattern!(c::CsrMap, rowptr::AbstractVector{Int32}, colind::AbstractVector{Int32})
+    GC.@preserve rowptr colind check(ccall((:iexa_csr_pattern, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32),
+                                           c.h, _ptr(rowptr), _ptr(colind), _ms(rowptr)))
+    return rowptr, colind
+end
+
+"COO values -> CSR values, duplicates summed, no atomics; once per iteration"
+function apply!(c::CsrMap, coo_vals::AbstractVector{Float64}, csr_vals::AbstractVector{Float64})
+    GC.@preserve coo_vals csr_vals check(ccall((:iexa_csr_apply, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}),
+                                               c.h, _ptr(coo_vals), _ptr(csr_vals), _ms(coo_vals), _st(coo_vals)))
+    return csr_vals
+end
+
 end # module
