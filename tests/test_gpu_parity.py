@@ -19,6 +19,7 @@ CASES = {
     "quadrotor_fd_100": lambda: models.quadrotor(100, "fd"),     # BASELINE configs[0]
     "quadrotor_oc_ragged": lambda: models.quadrotor(333, "oc"),  # support count not a multiple of the block
     "pandemic_50x4": lambda: models.pandemic(50, 4),
+    "pandemic_100x128": lambda: models.pandemic(100, 128),       # largest pandemic case of the reference's study grid (ESCAPE34/run_cases_gpu.jl:100)
     "farmer_1000": lambda: models.farmer(1000),
 }
 MODES = {"interp": ex.lib.IEXA_F_NO_SPECIALISE, "nvrtc": ex.lib.IEXA_F_DEFAULT}

@@ -15,6 +15,7 @@ CASES = {
     "quadrotor_oc": lambda: models.quadrotor(9, "oc"),
     "quadrotor_fd": lambda: models.quadrotor(12, "fd"),
     "pandemic": lambda: models.pandemic(7, 3),
+    "pandemic_100x128": lambda: models.pandemic(100, 128),   # the largest pandemic case of the reference's study grid (ESCAPE34/run_cases_gpu.jl:100)
     "farmer": lambda: models.farmer(11),
 }
 
