@@ -159,9 +159,14 @@ int32_t iexa_get_vector(const iexa_plan *p, int32_t which, double *out) {
   GUARD_BEGIN
   NEED_PLAN(p);
   const iexa::Plan &P = p->plan;
-  const std::vector<double> *v = which == 0 ? &P.x0 : which == 1 ? &P.lvar : which == 2 ? &P.uvar
-                                 : which == 3 ? &P.lcon : which == 4 ? &P.ucon : which == 5 ? &P.y0 : nullptr;
-  if (!v || !out) return fail(IEXA_ERR_INVALID, "bad vector selector");
+  if (!out || which < 0 || which > 5) return fail(IEXA_ERR_INVALID, "bad vector selector");
+  if (which == 3 || which == 4) { P.fill_con_bounds(which == 4, out); return IEXA_OK; }
+  if (which == 5) {
+    if (P.y0.empty()) std::fill(out, out + P.ncon, 0.0);
+    else std::memcpy(out, P.y0.data(), P.y0.size() * 8);
+    return IEXA_OK;
+  }
+  const std::vector<double> *v = which == 0 ? &P.x0 : which == 1 ? &P.lvar : &P.uvar;
   if (!v->empty()) std::memcpy(out, v->data(), v->size() * 8);
   return IEXA_OK;
   GUARD_END
@@ -170,9 +175,9 @@ int32_t iexa_set_vector(iexa_plan *p, int32_t which, const double *in) {
   GUARD_BEGIN
   NEED_PLAN(p);
   iexa::Plan &P = p->plan;
-  std::vector<double> *v = which == 0 ? &P.x0 : which == 5 ? &P.y0 : nullptr;
-  if (!v || !in) return fail(IEXA_ERR_INVALID, "only x0 (0) and y0 (5) can be set");
-  if (!v->empty()) std::memcpy(v->data(), in, v->size() * 8);
+  if (!in || (which != 0 && which != 5)) return fail(IEXA_ERR_INVALID, "only x0 (0) and y0 (5) can be set");
+  if (which == 5) { P.y0.assign(in, in + P.ncon); return IEXA_OK; }
+  if (!P.x0.empty()) std::memcpy(P.x0.data(), in, P.x0.size() * 8);
   return IEXA_OK;
   GUARD_END
 }

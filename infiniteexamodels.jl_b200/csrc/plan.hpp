@@ -8,6 +8,7 @@
 // generator g are o0_g + k, Jacobian slots o1_g + o1step_g*k + c, Hessian slots
 // o2_g + o2step_g*k + c with all OBJECTIVE generators first.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -110,7 +111,8 @@ struct Plan {
   int64_t nvar = 0, npar = 0, ncon = 0, nnzj = 0, nnzh = 0, nnzg = 0;
   int64_t loc_ncon = 0, loc_nnzj = 0, loc_nnzh = 0;
   int32_t rank = 0, world = 1, device = -1;
-  std::vector<double> lcon, ucon, y0;
+  std::vector<double> y0; // multipliers start: allocated on the first iexa_set_vector(5); all zeros until then
+  // lcon / ucon are constants per generator (transform.jl:396-411): filled on demand by fill_con_bounds()
 
   Plan() {
     itrs.emplace_back(); // iterator 0 is the empty iterator [(;)] (transform.jl:440, :614)
@@ -130,6 +132,11 @@ struct Plan {
     theta.insert(theta.end(), v, v + n);
     npar += n;
     return off;
+  }
+
+  // dense lcon (upper == false) / ucon of the global row numbering, straight into the caller's buffer
+  void fill_con_bounds(bool upper, double *out) const {
+    for (const Generator &g : cons) std::fill(out + g.o0, out + g.o0 + g.K, upper ? g.ucon : g.lcon);
   }
 
   int32_t itr_base(int64_t K, int32_t n_int, const int64_t *const *ic, int32_t n_fp,
@@ -200,7 +207,7 @@ struct Plan {
     g.is_obj = false; g.lcon = lc; g.ucon = uc;
     g.o0 = ncon;
     ncon += g.K;
-    lcon.resize(lcon.size() + g.K, lc); ucon.resize(ucon.size() + g.K, uc); y0.resize(y0.size() + g.K, 0.0);
+
     cons.push_back(std::move(g));
     return cons.back().o0;
   }

@@ -23,19 +23,24 @@ from . import lib as _lib
 from .core import ExaCore, Itr
 
 
-@dataclass
 class NLPModelMeta:
-    nvar: int
-    ncon: int
-    nnzj: int
-    nnzh: int
-    x0: np.ndarray
-    lvar: np.ndarray
-    uvar: np.ndarray
-    y0: np.ndarray
-    lcon: np.ndarray
-    ucon: np.ndarray
-    minimize: bool
+    """``NLPModels.NLPModelMeta``: nvar, ncon, nnzj, nnzh, minimize and the vectors x0, lvar, uvar, y0, lcon, ucon.
+    The vectors are fetched from the plan on first access (and then kept: they are ordinary mutable arrays, like
+    ``NLPModels.get_x0(model)`` — infiniteopt_backend.jl:600-601); a 10^6-support model never pays for the six
+    44-million-entry copies unless somebody asks for them."""
+    _VECTORS = {"x0": 0, "lvar": 1, "uvar": 2, "lcon": 3, "ucon": 4, "y0": 5}
+
+    def __init__(self, nvar, ncon, nnzj, nnzh, minimize, fetch):
+        self.nvar, self.ncon, self.nnzj, self.nnzh, self.minimize = nvar, ncon, nnzj, nnzh, minimize
+        self._fetch, self._cache = fetch, {}
+
+    def __getattr__(self, name):
+        if name in NLPModelMeta._VECTORS:
+            if name not in self._cache:
+                which = NLPModelMeta._VECTORS[name]
+                self._cache[name] = self._fetch(which, self.nvar if which <= 2 else self.ncon)
+            return self._cache[name]
+        raise AttributeError(name)
 
 
 def _is_torch(a):
@@ -103,8 +108,7 @@ class ExaModel:
                 _lib.check(L, L.iexa_get_vector(h, which, a.ctypes.data))
             return a
 
-        self.meta = NLPModelMeta(m.nvar, m.ncon, m.nnzj, m.nnzh, vec(0, m.nvar), vec(1, m.nvar), vec(2, m.nvar),
-                                 vec(5, m.ncon), vec(3, m.ncon), vec(4, m.ncon), bool(m.minimize))
+        self.meta = NLPModelMeta(m.nvar, m.ncon, m.nnzj, m.nnzh, bool(m.minimize), vec)
         # local (this rank's) sizes; equal to the global ones when world == 1
         self.loc_ncon, self.loc_nnzj, self.loc_nnzh = m.loc_ncon, m.loc_nnzj, m.loc_nnzh
 
