@@ -362,7 +362,93 @@ def param_function_problem():
     P.dump(x=rng.uniform(0.5, 5.0, len(P.vars)))
 
 
+def opf_case3(K=2, seed=0):
+    """ESCAPE34/opf.jl:36-286 — two-stage stochastic AC-OPF (BASELINE configs[3]) on the 3-bus / 3-branch / 3-generator
+    case this repo embeds instead of the pglib download of opf.jl:15-18 (the grid NUMBERS below are that embedded case;
+    the per-unit conversion, branch admittances and every constraint are restated from opf.jl and PowerModels' conventions,
+    not from infiniteexamodels.jl_b200/opf.py).  K scenarios of the 2*nbus load perturbation theta ~ N(0, diag((0.1*[Pd; Qd])^2))
+    (opf.jl:48-50,112).  Layout: the 24 first-stage variables in declaration order (va0, vm0, pg0, qg0, p0, q0 over
+    buses / generators / arcs), then the 24 second-stage variables as blocks of K.  Rows are matched by value."""
+    base = 100.0
+    bus = {1: (110.0, 40.0), 2: (110.0, 40.0), 3: (95.0, 50.0)}                       # pd, qd [MW, MVAr]
+    gen = {1: (1, (0.11, 5.0, 0.0)), 2: (2, (0.085, 1.2, 0.0)), 3: (3, (0.0, 0.0, 0.0))}   # bus, cost (quadratic, linear, constant)
+    pmax = {1: 2000.0, 2: 2000.0, 3: 0.0}; qlim = 1000.0
+    branch = {1: (1, 3, 0.065, 0.62, 0.45, 9000.0), 2: (3, 2, 0.025, 0.75, 0.7, 50.0), 3: (1, 2, 0.042, 0.9, 0.3, 9000.0)}
+    buses = [1, 2, 3]
+    nbus = 3
+    arcs = [(l, f, t) for l, (f, t, *_) in branch.items()] + [(l, t, f) for l, (f, t, *_) in branch.items()]
+    rng = np.random.default_rng(seed)
+    sd = 0.1 * np.array([bus[i][0] / base for i in buses] + [bus[i][1] / base for i in buses])
+    theta = rng.normal(0.0, 1.0, size=(2 * nbus, K)) * sd[:, None]
+
+    P = NLP("opf_case3")
+    va0 = {i: P.var(f"va0_{i}", 1)[0] for i in buses}
+    vm0 = {i: P.var(f"vm0_{i}", 1, 1.0)[0] for i in buses}
+    pg0 = {i: P.var(f"pg0_{i}", 1)[0] for i in gen}
+    qg0 = {i: P.var(f"qg0_{i}", 1)[0] for i in gen}
+    p0 = {a: P.var("p0_%d_%d_%d" % a, 1)[0] for a in arcs}
+    q0 = {a: P.var("q0_%d_%d_%d" % a, 1)[0] for a in arcs}
+    va = {i: P.var(f"va_{i}", K) for i in buses}
+    vm = {i: P.var(f"vm_{i}", K, 1.0) for i in buses}
+    pg = {i: P.var(f"pg_{i}", K) for i in gen}
+    qg = {i: P.var(f"qg_{i}", K) for i in gen}
+    p = {a: P.var("p_%d_%d_%d" % a, K) for a in arcs}
+    q = {a: P.var("q_%d_%d_%d" % a, K) for a in arcs}
+    P.obj = sum(R(c[0] * base ** 2) * pg0[i] ** 2 + R(c[1] * base) * pg0[i] + R(c[2]) for i, (_, c) in gen.items())
+
+    def stage(va, vm, pg, qg, p, q, th):
+        """th: None (first stage) or (k -> vector of 2*nbus perturbations); variables are scalars or functions of k"""
+        rows = []
+        rows.append(va[1])                                                    # reference bus: va == 0
+        for l, (f, t, r, x, bch, rate) in branch.items():
+            z2 = r * r + x * x
+            g, b = r / z2, -x / z2                                            # series admittance y = 1/(r + jx)
+            tr, ti, ttm = 1.0, 0.0, 1.0                                        # no transformer: tap 1, shift 0
+            g_fr = g_to = 0.0; b_fr = b_to = bch / 2                          # line charging split over both ends
+            cfr, sfr = sp.cos(va[f] - va[t]), sp.sin(va[f] - va[t])
+            cto, sto = sp.cos(va[t] - va[f]), sp.sin(va[t] - va[f])
+            rows.append(("pf", p[(l, f, t)] - (R((g + g_fr) / ttm) * vm[f] ** 2 + R((-g * tr + b * ti) / ttm) * (vm[f] * vm[t] * cfr)
+                                                + R((-b * tr - g * ti) / ttm) * (vm[f] * vm[t] * sfr))))
+            rows.append(("qf", q[(l, f, t)] - (-R((b + b_fr) / ttm) * vm[f] ** 2 - R((-b * tr - g * ti) / ttm) * (vm[f] * vm[t] * cfr)
+                                                + R((-g * tr + b * ti) / ttm) * (vm[f] * vm[t] * sfr))))
+            rows.append(("pt", p[(l, t, f)] - (R(g + g_to) * vm[t] ** 2 + R((-g * tr - b * ti) / ttm) * (vm[t] * vm[f] * cto)
+                                                + R((-b * tr + g * ti) / ttm) * (vm[t] * vm[f] * sto))))
+            rows.append(("qt", q[(l, t, f)] - (-R(b + b_to) * vm[t] ** 2 - R((-b * tr + g * ti) / ttm) * (vm[t] * vm[f] * cto)
+                                                + R((-g * tr - b * ti) / ttm) * (vm[t] * vm[f] * sto))))
+            rows.append(("ang", va[f] - va[t]))
+            rows.append(("sf", p[(l, f, t)] ** 2 + q[(l, f, t)] ** 2))
+            rows.append(("st", p[(l, t, f)] ** 2 + q[(l, t, f)] ** 2))
+        for n_, i in enumerate(buses):
+            pd, qd = bus[i][0] / base, bus[i][1] / base
+            gens_here = [g_ for g_, (b_, _) in gen.items() if b_ == i]
+            arcs_here = [a for a in arcs if a[1] == i]
+            # everything moves left; affine rows keep their constant in the set (JuMP normalisation), so the function
+            # part is  sum(p) - sum(pg) [- theta_i: theta is a PARAMETER of the expression, not a constant]
+            fp = sum(p[a] for a in arcs_here) - sum(pg[g_] for g_ in gens_here)
+            fq = sum(q[a] for a in arcs_here) - sum(qg[g_] for g_ in gens_here)
+            if th is not None:
+                fp, fq = fp - R(th[n_]), fq - R(th[nbus + n_])
+            rows.append(("bp", fp)); rows.append(("bq", fq))
+        return [r_[1] if isinstance(r_, tuple) else r_ for r_ in rows]
+
+    P.cons += stage(va0, vm0, pg0, qg0, p0, q0, None)
+    for k in range(K):
+        at = lambda d: {key: v[k] for key, v in d.items()}
+        P.cons += stage(at(va), at(vm), at(pg), at(qg), at(p), at(q), theta[:, k])
+    for i in gen:                                                             # ramping: pg0 - pg(k), qg0 - qg(k)
+        P.cons += [pg0[i] - pg[i][k] for k in range(K)]
+    for i in gen:
+        P.cons += [qg0[i] - qg[i][k] for k in range(K)]
+    rng2 = np.random.default_rng(17)
+    x = rng2.uniform(-0.3, 0.3, len(P.vars))
+    for i, s_ in enumerate(P.vars):                                          # voltage magnitudes around 1
+        if str(s_).startswith("vm"):
+            x[i] = rng2.uniform(0.92, 1.08)
+    P.dump(x=x)
+
+
 if __name__ == "__main__":
+    opf_case3()
     param_function_problem()
     solve_tests()
     ode_5x5()

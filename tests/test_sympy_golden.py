@@ -76,11 +76,18 @@ def _param_function_problem():
         return exa_core(infmodels.param_function_problem())[0]
 
 
+def _opf_case3():
+    from iexa_b200 import opf
+    from iexa_b200.transform import exa_core
+    return exa_core(opf.opf(None, num_supports=2, seed=0))[0]
+
+
+BUILDERS["opf_case3"] = _opf_case3
 BUILDERS["param_function_problem"] = _param_function_problem
 BUILDERS["solve_tp1"] = lambda: _solve_problem(-1)
 for _v in range(5):
     BUILDERS[f"solve_tp2_v{_v}"] = (lambda v: (lambda: _solve_problem(v)))(_v)
-ROW_MATCHED = {n for n in BUILDERS if n.startswith("solve_")} | {"param_function_problem"}   # fixture rows are in the generator script's order
+ROW_MATCHED = {n for n in BUILDERS if n.startswith("solve_")} | {"param_function_problem", "opf_case3"}   # fixture rows are in the generator script's order
 
 
 def load(name):
