@@ -296,44 +296,56 @@ def operators():
         f.write("\n".join(names) + "\n")
 
 
-def solve_tests():
-    """test/solve.jl:2-27 ("Test Problem 1", finite differences) and :48-95 ("Test Problem 2" and its four alternative
-    objectives) — the models the reference checks DIFFERENTIALLY against JuMP's TranscriptionBackend, i.e. against the
-    fully expanded scalar NLP, which is what is written out here.  They exercise the point variable y(0, 1), a
-    DomainRestriction, the derivative of a semi-infinite variable, and the objective heuristics of
+def solve_problem(variant=-1):
+    """test/solve.jl:2-27 ("Test Problem 1", ``variant=-1``, finite differences) and :48-95 ("Test Problem 2", ``variant=0``,
+    and its four alternative objectives 1..4) — the models the reference checks DIFFERENTIALLY against JuMP's
+    TranscriptionBackend, i.e. against the fully expanded scalar NLP, which is what is written out here.  They exercise the
+    point variable y(0, 1), a DomainRestriction, the derivative of a semi-infinite variable, and the objective heuristics of
     src/transform.jl:642-767 (terms moved inside the inner measure / full expansion).  Layout: z, y (t fastest),
-    d(y)/dt, d(y(0, x))/dx.  Rows are stored in the order written here; the test matches rows by value."""
+    d(y)/dt, d(y(0, x))/dx.  Rows are stored in the order written here; the tests match rows by value.  The returned NLP
+    also carries the bounds (lvar/uvar/lcon/ucon) so that tests/test_differential_solves.py can SOLVE it."""
     nt = nx = 5
     ts, xs = np.linspace(0, 1, nt), np.linspace(-1, 1, nx)
     wt, wx = trapezoid(ts), trapezoid(xs)
     dt, dx = np.diff(ts), np.diff(xs)
+    restricted = variant == -1
+    P = NLP("solve_tp1" if restricted else f"solve_tp2_v{variant}")
+    z = P.var("z", 1, 10.0)[0]
+    y = np.array(P.var("y", nt * nx)).reshape(nx, nt).T
+    dy = np.array(P.var("dy", nt * nx)).reshape(nx, nt).T
+    d2 = P.var("d2", nx)                                        # d/dx of y(0, x)
+    inf = float("inf")
+    P.lvar = [-inf] + [0.0] * (nt * nx) + [-inf] * (nt * nx + nx); P.uvar = [inf] * len(P.vars)
+    P.lcon, P.ucon = [], []
 
-    def base(name, restricted):
-        P = NLP(name)
-        z = P.var("z", 1, 10.0)[0]
-        y = np.array(P.var("y", nt * nx)).reshape(nx, nt).T
-        dy = np.array(P.var("dy", nt * nx)).reshape(nx, nt).T
-        d2 = P.var("d2", nx)                                        # d/dx of y(0, x)
-        P.cons += [dy[i, j] - (sp.sin(y[i, j]) + z + R(1.2)) for j in range(nx) for i in range(nt)]
-        P.cons += [y[i, j] + z - R(ts[i]) for j in range(nx) for i in range(nt) if (not restricted or ts[i] <= 0.5)]
-        P.cons += [d2[j] for j in range(nx)]                          # == 5 (the constant lives in the set)
-        P.cons += [R(dt[i - 1]) * dy[i, j] - y[i, j] + y[i - 1, j] for j in range(nx) for i in range(1, nt)]
-        P.cons += [R(dx[j - 1]) * d2[j] - y[0, j] + y[0, j - 1] for j in range(1, nx)]
-        inner = [sum(R(wt[i]) * y[i, j] ** 2 for i in range(nt)) for j in range(nx)]   # ∫(y², t) at x_j
-        return P, z, y, inner
+    def rows(exprs, lo, hi):
+        P.cons += exprs; P.lcon += [lo] * len(exprs); P.ucon += [hi] * len(exprs)
 
+    rows([dy[i, j] - (sp.sin(y[i, j]) + z + R(1.2)) for j in range(nx) for i in range(nt)], 0.0, 0.0)
+    rows([y[i, j] + z - R(ts[i]) for j in range(nx) for i in range(nt) if (not restricted or ts[i] <= 0.5)], -inf, 42.0)
+    rows([d2[j] for j in range(nx)], 5.0, 5.0)                    # == 5 (the constant lives in the set)
+    rows([R(dt[i - 1]) * dy[i, j] - y[i, j] + y[i - 1, j] for j in range(nx) for i in range(1, nt)], 0.0, 0.0)
+    rows([R(dx[j - 1]) * d2[j] - y[0, j] + y[0, j - 1] for j in range(1, nx)], 0.0, 0.0)
+    I = [sum(R(wt[i]) * y[i, j] ** 2 for i in range(nt)) for j in range(nx)]   # ∫(y², t) at x_j
+    if variant == -1:
+        P.obj = sum(R(wx[j]) * I[j] for j in range(nx)) + 2 * y[0, nx - 1]          # ∫(∫(y², t), x) + 2y(0, 1)
+    elif variant == 0:
+        P.obj = sum(R(wx[j]) * (I[j] + 2 * z) for j in range(nx)) + 2 * y[0, nx - 1]
+    elif variant == 1:
+        P.obj = sum(R(wx[j]) * (I[j] + 2 * z ** 2) for j in range(nx)) + 2 * y[0, nx - 1]
+    elif variant == 2:
+        P.obj = sum(R(wx[j]) * (I[j] + sp.sin(z ** 2)) for j in range(nx))
+    elif variant == 3:
+        P.obj = sum(R(wx[j]) * (I[j] * sp.cos(z)) for j in range(nx))
+    else:
+        P.obj = sum(R(wx[j]) * (z * (I[j] + z ** 3)) for j in range(nx))
+    return P
+
+
+def solve_tests():
     rng = np.random.default_rng(21)
-    P, z, y, inner = base("solve_tp1", True)
-    P.obj = sum(R(wx[j]) * inner[j] for j in range(nx)) + 2 * y[0, nx - 1]          # ∫(∫(y², t), x) + 2y(0, 1)
-    P.dump(x=rng.uniform(0.2, 1.5, len(P.vars)))
-    variants = [lambda I, z, y: sum(R(wx[j]) * (I[j] + 2 * z) for j in range(nx)) + 2 * y[0, nx - 1],
-                lambda I, z, y: sum(R(wx[j]) * (I[j] + 2 * z ** 2) for j in range(nx)) + 2 * y[0, nx - 1],
-                lambda I, z, y: sum(R(wx[j]) * (I[j] + sp.sin(z ** 2)) for j in range(nx)),
-                lambda I, z, y: sum(R(wx[j]) * (I[j] * sp.cos(z)) for j in range(nx)),
-                lambda I, z, y: sum(R(wx[j]) * (z * (I[j] + z ** 3)) for j in range(nx))]
-    for v, f in enumerate(variants):
-        P, z, y, inner = base(f"solve_tp2_v{v}", False)
-        P.obj = f(inner, z, y)
+    for variant in (-1, 0, 1, 2, 3, 4):
+        P = solve_problem(variant)
         P.dump(x=rng.uniform(0.2, 1.5, len(P.vars)))
 
 
