@@ -94,6 +94,9 @@ class ExaTranscriptionBackend:
             x0[self.data.finvar_mappings[vref] - 1] = float(value)
         elif vref in self.data.infvar_mappings:
             blk = self.data.infvar_mappings[vref]
+            if callable(value):      # a function of the supports, e.g. set_start_value(x, t -> 42) (test/solve.jl:225)
+                value = _evaluate_parameter_function(lambda *s: float(value(*s)) if np.ndim(s[0]) == 0 else np.vectorize(value)(*s),
+                                                     self.data, vref.groups, blk.size)
             x0[blk.offset:blk.offset + blk.length] = np.broadcast_to(np.asarray(value, dtype=np.float64), blk.size).reshape(-1, order="F")
         else:
             return False
