@@ -98,6 +98,8 @@ class VarInfo:
     ub: object = None
     fix: object = None
     start: object = None
+    binary: bool = False
+    integer: bool = False
 
 
 class FiniteVariable(Ref):
@@ -439,8 +441,8 @@ class InfiniteModel:
         p = ParameterFunction(self, func, prefs); self.param_funcs.append(p); return p
 
     # -- variables ---------------------------------------------------------------------------------
-    def variable(self, *prefs, lb=None, ub=None, start=None, fix=None):
-        info = VarInfo(lb, ub, fix, start)
+    def variable(self, *prefs, lb=None, ub=None, start=None, fix=None, binary=False, integer=False):
+        info = VarInfo(lb, ub, fix, start, bool(binary), bool(integer))
         if prefs:
             v = InfiniteVariable(self, prefs, info); self.infinite_vars.append(v)
         else:
@@ -487,6 +489,9 @@ class InfiniteModel:
             f = expr
         else:
             f = expr if (_is_num(rhs) and rhs == 0) else _sub(expr, rhs)
+            if sense not in ("==", "<=", ">="):     # _get_constr_bounds(set) fallback, transform.jl:408-411
+                raise ValueError(f"Constraint set `{sense}` is not supported by InfiniteExaModels, "
+                                 "if you need support for this constraint type, please open an issue.")
             lo, hi = {"==": (0.0, 0.0), "<=": (-np.inf, 0.0), ">=": (0.0, np.inf)}[sense]
         if isinstance(f, Ref): f = _aff(f)
         if isinstance(f, AffExpr):

@@ -105,7 +105,14 @@ def _process_value(val, supp):
     return val(*supp) if callable(val) else val
 
 
+def _ensure_continuous(info: io.VarInfo):
+    """transform.jl:41-45"""
+    if info.binary or info.integer:
+        raise ValueError("Integer variables are not supported by ExaModels.")
+
+
 def _get_variable_bounds_and_start(info: io.VarInfo, itrs: Optional[List[Itr]] = None, data=None, groups=()):
+    _ensure_continuous(info)
     vals = (info.lb, info.ub, info.fix, info.start)
     if itrs is None or not any(callable(v) for v in vals):
         lb, ub, start = -np.inf, np.inf, 0.0

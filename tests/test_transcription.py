@@ -188,3 +188,20 @@ def test_derivative_approximation_rows_are_exact_for_polynomials(method, degree)
     assert len(rows) >= T - 2 and np.max(np.abs(rows)) <= 1e-12, np.max(np.abs(rows))
     if isinstance(method, io.OrthogonalCollocation):
         assert T == len(pub) + (method.num_nodes - 2) * (len(pub) - 1)      # internal nodes (transform.jl:22)
+
+
+def test_error_paths_read_like_the_reference():
+    """integer variables (transform.jl:41-45) and unsupported constraint sets (transform.jl:408-411)"""
+    m = io.InfiniteModel()
+    t = m.infinite_parameter(0, 1, num_supports=3)
+    m.variable(t, integer=True)
+    with pytest.raises(ValueError, match="Integer variables are not supported by ExaModels."):
+        exa_core(m)
+    m2 = io.InfiniteModel()
+    z = m2.variable(binary=True)
+    with pytest.raises(ValueError, match="Integer variables are not supported by ExaModels."):
+        exa_core(m2)
+    m3 = io.InfiniteModel()
+    w = m3.variable()
+    with pytest.raises(ValueError, match="is not supported by InfiniteExaModels"):
+        m3.constraint(w, "in SecondOrderCone", 1.0)
