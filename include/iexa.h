@@ -173,7 +173,12 @@ int32_t iexa_get_vector(const iexa_plan *p, int32_t which, double *out);
 int32_t iexa_set_vector(iexa_plan *p, int32_t which, const double *in); /* x0 / y0 warm start */
 
 /* ExaModels.set_parameter! — infiniteopt_backend.jl:522,:546 ; model.θ — :479          */
+/* iexa_set_par has no stream argument: it synchronises the DEVICE before it overwrites theta, so it is ordered against
+ * callbacks in flight on any stream (CUDA.jl task streams, torch side streams are non-blocking with respect to the
+ * legacy default stream).  iexa_set_par_stream is the asynchronous form: the update is enqueued on `stream` like a
+ * callback (values are staged in a pinned buffer of the engine; vals_host may be reused as soon as the call returns). */
 int32_t iexa_set_par(iexa_plan *p, int64_t offset0, int64_t n, const double *vals_host);
+int32_t iexa_set_par_stream(iexa_plan *p, int64_t offset0, int64_t n, const double *vals_host, void *stream);
 int32_t iexa_get_par(const iexa_plan *p, int64_t offset0, int64_t n, double *vals_host);
 
 /* ---- NLPModels callbacks (ExaModels 0.11.2 methods reached from
@@ -191,6 +196,15 @@ int32_t iexa_jac_coord(iexa_plan *p, const double *x, double *vals, int32_t mems
 /* y may be NULL (objective-only Hessian)                                               */
 int32_t iexa_hess_coord(iexa_plan *p, const double *x, const double *y, double obj_weight,
                         double *vals, int32_t memspace, void *stream);
+/* Matrix-free products (NLPModels jprod! / jtprod! / hprod!: the model handed to the solver at
+ * ext/InfiniteExaModelsMadNLP.jl:49-50 / ext/InfiniteExaModelsIpopt.jl:48-49 carries the full API).  Fused kernels:
+ * the first / second order programs with a product epilogue — no COO values are written or read.
+ *   jprod:  Jv[row] = sum_c d1_c * v[col_c] in registers, one coalesced store per row, no atomics: bit-reproducible.
+ *   jtprod / hprod: one sum per touched variable and support in registers; single-writer blocks are plain stores,
+ *   the rest atomics (warp-shuffle reduced for shared variables) in a second, ordered launch.
+ * v of jprod / hprod and the results of jtprod / hprod have nvar entries; v of jtprod and Jv have the LOCAL row count.
+ * world > 1: jtprod / hprod return this rank's partial sums (all-reduce the vector).  The kernels of these three entry
+ * points are compiled on the first call of any of them.                                                          */
 int32_t iexa_jprod(iexa_plan *p, const double *x, const double *v, double *Jv, int32_t memspace,
                    void *stream);
 int32_t iexa_jtprod(iexa_plan *p, const double *x, const double *v, double *Jtv,
@@ -226,7 +240,9 @@ int64_t iexa_x_ranges(const iexa_plan *p, iexa_segment *out, int64_t cap);
 
 /* ---- byte accounting used by bench.py's roofline: ALGORITHMIC bytes of
  *      one call of each callback, computed from the finalised plan.
- * which: 0 obj, 1 grad, 2 cons, 3 jac_coord, 4 hess_coord                              */
+ * which: 0 obj, 1 grad, 2 cons, 3 jac_coord, 4 hess_coord, 5 jprod, 6 jtprod, 7 hprod
+ * (products: the inputs their first / second order programs load, the touched part of v — or y and v — and every
+ * entry of the dense result once; no COO values are materialised)                          */
 int64_t iexa_algorithmic_bytes(const iexa_plan *p, int32_t which);
 /* number of kernel launches one call of callback `which` performs                      */
 int32_t iexa_launches_per_call(const iexa_plan *p, int32_t which);
@@ -238,6 +254,8 @@ const char *iexa_engine_note(const iexa_plan *p);
 /* ---- diagnostics: the CUDA translation unit that iexa_finalize specialises with NVRTC.
  *      _source returns its length (copies up to cap-1 bytes); _compile runs NVRTC for sm_100a
  *      without loading the image (works on a machine without a GPU).                       */
+/* cap < 0 (capacity -cap) and *cubin_bytes == -1 on entry select the second translation unit: the jprod! / jtprod! /
+ * hprod! kernels, which the engine compiles on the first product call                                   */
 int64_t iexa_debug_codegen_source(const iexa_plan *p, char *buf, int64_t cap);
 /* regroup a host-only plan with (1) / without (0) shape canonicalisation before inspecting its source */
 int32_t iexa_debug_set_class_mode(iexa_plan *p, int32_t on);

@@ -182,18 +182,22 @@ int32_t iexa_set_vector(iexa_plan *p, int32_t which, const double *in) {
   GUARD_END
 }
 
-int32_t iexa_set_par(iexa_plan *p, int64_t off, int64_t n, const double *vals) {
+static int32_t set_par_impl(iexa_plan *p, int64_t off, int64_t n, const double *vals, void *stream, bool device_sync) {
   GUARD_BEGIN
   NEED_PLAN(p);
   if (off < 0 || n < 0 || off + n > p->plan.npar || (n > 0 && !vals)) return fail(IEXA_ERR_INVALID, "parameter range out of bounds");
   std::memcpy(p->plan.theta.data() + off, vals, (size_t)n * 8);
   if (p->engine) {
     std::string err;
-    int rc = p->engine->set_par(off, n, vals, err);
+    int rc = p->engine->set_par(off, n, vals, stream, device_sync, err);
     if (rc) return fail(rc, err);
   }
   return IEXA_OK;
   GUARD_END
+}
+int32_t iexa_set_par(iexa_plan *p, int64_t off, int64_t n, const double *vals) { return set_par_impl(p, off, n, vals, nullptr, true); }
+int32_t iexa_set_par_stream(iexa_plan *p, int64_t off, int64_t n, const double *vals, void *stream) {
+  return set_par_impl(p, off, n, vals, stream, false);
 }
 int32_t iexa_get_par(const iexa_plan *p, int64_t off, int64_t n, double *vals) {
   GUARD_BEGIN
@@ -350,37 +354,43 @@ int64_t iexa_x_ranges(const iexa_plan *p, iexa_segment *out, int64_t cap) {
 
 // ---- algorithmic bytes --------------------------------------------------------
 int64_t iexa_algorithmic_bytes(const iexa_plan *pc, int32_t which) {
-  if (!pc || !pc->plan.finalized || which < 0 || which > 4) return -1;
+  if (!pc || !pc->plan.finalized || which < 0 || which > 7) return -1;
   iexa_plan *p = const_cast<iexa_plan *>(pc);
   if (p->bytes_cache[which] >= 0) return p->bytes_cache[which];
   const iexa::Plan &P = p->plan;
   std::vector<const iexa::Generator *> gens;
-  const bool use_obj = which == 0 || which == 1 || which == 4;
+  const bool use_obj = which == 0 || which == 1 || which == 4 || which == 7;
   const bool use_con = which >= 2;
   if (use_obj) for (auto &g : P.objs) gens.push_back(&g);
   if (use_con) for (auto &g : P.cons) gens.push_back(&g);
-  std::vector<bool> xs((size_t)P.nvar, false), ts((size_t)P.npar, false);
+  std::vector<bool> xs((size_t)P.nvar, false), ts((size_t)P.npar, false), vs(which >= 5 ? (size_t)P.nvar : 0, false);
   std::vector<std::vector<bool>> colseen(P.columns.size());
   int64_t bytes = 0;
   for (const iexa::Generator *gp : gens) {
     const iexa::Generator &g = *gp;
-    const iexa::Program &pr = (which == 0 || which == 2) ? g.c.val : (which == 1 || which == 3) ? g.c.d1 : g.c.d2;
+    const iexa::Program &pr = (which == 0 || which == 2) ? g.c.val : (which == 1 || which == 3) ? g.c.d1 : which == 4 ? g.c.d2
+                              : which == 5 ? g.c.jv : which == 6 ? g.c.jtv : g.c.hv;
     if (pr.nout == 0) continue;
     const iexa::Iterator &it = P.itrs[g.itr];
-    std::vector<int32_t> lx, lp;
+    std::vector<int32_t> lx, lp, lv;
     std::vector<int32_t> fcols, icols_used;
     std::vector<bool> iused(g.c.int_cols.size(), false);
     auto mark_idx = [&](int32_t islot) { for (auto &t : g.c.uidx[islot].terms) iused[t.first] = true; };
     for (const iexa::Instr &I : pr.code) {
       if (I.op == iexa::D_LOADX) { lx.push_back(I.a); mark_idx(I.a); }
       else if (I.op == iexa::D_LOADP) { lp.push_back(I.a); mark_idx(I.a); }
+      else if (I.op == iexa::D_LOADV) { lv.push_back(I.a); mark_idx(I.a); }
+      else if (I.op == iexa::D_SELNE) { mark_idx(I.a); mark_idx(I.b); }
       else if (I.op == iexa::D_FIELD) fcols.push_back(I.a);
       else if (I.op == iexa::D_SEL2) { mark_idx(I.a); mark_idx(I.b); }
     }
     if (which == 1) for (int32_t s : g.c.jac_slot) mark_idx(s);
+    if (which == 6) for (int32_t s : g.c.jtv_slot) mark_idx(s);
+    if (which == 7) for (int32_t s : g.c.hv_slot) mark_idx(s);
     for (int64_t k = g.k0; k < g.k1; ++k) {
       for (int32_t s : lx) { int64_t i = P.index_value(g, s, k) - 1; if (i >= 0 && i < P.nvar && !xs[i]) { xs[i] = true; bytes += 8; } }
       for (int32_t s : lp) { int64_t i = P.index_value(g, s, k) - 1; if (i >= 0 && i < P.npar && !ts[i]) { ts[i] = true; bytes += 8; } }
+      for (int32_t s : lv) { int64_t i = P.index_value(g, s, k) - 1; if (i >= 0 && i < P.nvar && !vs[i]) { vs[i] = true; bytes += 8; } }
     }
     auto touch_col = [&](const iexa::ColRef &r, int esz) {
       const iexa::HostColumn &c = P.columns[r.col];
@@ -396,7 +406,8 @@ int64_t iexa_algorithmic_bytes(const iexa_plan *pc, int32_t which) {
     };
     for (int32_t s : fcols) touch_col(it.fp_cols[g.c.fp_cols[s]], 8);
     for (size_t s = 0; s < iused.size(); ++s) if (iused[s]) touch_col(it.int_cols[g.c.int_cols[s]], 4);
-    if (which == 4 && !g.is_obj && pr.uses_w) bytes += 8 * (g.k1 - g.k0); // multipliers y
+    if ((which == 4 || which == 7) && !g.is_obj && pr.uses_w) bytes += 8 * (g.k1 - g.k0); // multipliers y
+    if (which == 6 && pr.uses_w) bytes += 8 * (g.k1 - g.k0);                                // v[row]
   }
   switch (which) {
     case 0: bytes += 8; break;
@@ -404,6 +415,8 @@ int64_t iexa_algorithmic_bytes(const iexa_plan *pc, int32_t which) {
     case 2: bytes += 8 * P.loc_ncon; break;
     case 3: bytes += 8 * P.loc_nnzj; break;
     case 4: bytes += 8 * P.loc_nnzh; break;
+    case 5: bytes += 8 * P.loc_ncon; break;
+    case 6: case 7: bytes += 8 * P.nvar; break; // every entry of the dense result is written once
   }
   p->bytes_cache[which] = bytes;
   return bytes;
@@ -411,7 +424,9 @@ int64_t iexa_algorithmic_bytes(const iexa_plan *pc, int32_t which) {
 
 int64_t iexa_debug_codegen_source(const iexa_plan *p, char *buf, int64_t cap) {
   if (!p || !p->plan.finalized) return -1;
-  std::string src = iexa::Specialiser::generate_source(p->plan);
+  const int set = cap < 0 ? 1 : 0; // cap < 0: the product module (jprod! / jtprod! / hprod!), capacity -cap
+  if (cap < 0) cap = -cap;
+  std::string src = iexa::Specialiser::generate_source(p->plan, set);
   if (buf && cap > 0) {
     size_t n = std::min<size_t>((size_t)cap - 1, src.size());
     std::memcpy(buf, src.data(), n);
@@ -432,7 +447,8 @@ int32_t iexa_debug_codegen_compile(const iexa_plan *p, int64_t *cubin_bytes) {
   GUARD_BEGIN
   NEED_PLAN(p);
   if (!p->plan.finalized) return fail(IEXA_ERR_STATE, "plan not finalized");
-  std::string src = iexa::Specialiser::generate_source(p->plan), err;
+  const int set = (cubin_bytes && *cubin_bytes == -1) ? 1 : 0; // in: -1 selects the product module
+  std::string src = iexa::Specialiser::generate_source(p->plan, set), err;
   std::vector<char> cubin;
   if (!iexa::compile_cubin(src, cubin, err)) return fail(IEXA_ERR_NVRTC, err);
   if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "engine.hpp"
 #include "exec.hpp"
 #include "plan.hpp"
 
@@ -43,17 +44,20 @@ struct CbSchedule {
 };
 CbSchedule make_schedule(const Plan &plan, const std::vector<int> &groups);
 
+// The kernels live in two NVRTC modules: the five NLPModels callbacks every solver uses (set 0, compiled at
+// iexa_finalize) and the matrix-free products jprod! / jtprod! / hprod! (set 1, compiled on their first call: MadNLP and
+// Ipopt never call them, so they cost those solvers no build time).  Arrays below are indexed by kernel slot (engine.hpp).
 struct GeneratedSource {
-  CbSchedule sched[5];
+  CbSchedule sched[KS__N];
   std::string text;
   std::vector<CiEntry> ci;
-  std::vector<int> groups_of[5]; // groups with work, per callback
-  size_t smem_bytes[5] = {0, 0, 0, 0, 0};
+  std::vector<int> groups_of[KS__N]; // groups with work, per kernel slot
+  size_t smem_bytes[KS__N] = {0};
 };
 
 int spec_block(); // threads per block of the specialised kernels (env IEXA_BLOCK, default 128)
 int class_chunk(); // instances of a shape class per block (env IEXA_CLASS_CHUNK, default 8)
-GeneratedSource generate_source(const Plan &plan);
+GeneratedSource generate_source(const Plan &plan, int set = 0);
 bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string &err);
 
 class Specialiser {
@@ -63,22 +67,26 @@ class Specialiser {
   // col_dev_ptr[c]: device address of Plan::columns[c] (nullptr for iota columns)
   // may switch the plan to class mode (shape canonicalisation) when the source would exceed the budget
   bool build(Plan &plan, const std::vector<const void *> &col_dev_ptr, std::string &err);
-  bool has(int cb) const { return cb >= 0 && cb < 5 && fn_[cb] != nullptr; }
-  const std::vector<int> &groups_of(int cb) const { return groups_of_[cb]; }
-  const CbSchedule &schedule(int cb) const { return sched_[cb]; }
-  bool launch(int cb, const WorkItem *work, const double *x, const double *theta,
-              const double *y, double sigma, double *out, double *partials, cudaStream_t st,
+  // second module: jprod! / jtprod! / hprod! kernels of the SAME groups (never regroups the plan)
+  bool build_products(Plan &plan, const std::vector<const void *> &col_dev_ptr, std::string &err);
+  bool products_built() const { return module_[1] != nullptr; }
+  bool has(int ks) const { return ks >= 0 && ks < KS__N && fn_[ks] != nullptr; }
+  const std::vector<int> &groups_of(int ks) const { return groups_of_[ks]; }
+  const CbSchedule &schedule(int ks) const { return sched_[ks]; }
+  bool launch(int ks, const WorkItem *work, const double *x, const double *theta,
+              const double *y, const double *v, double sigma, double *out, double *partials, cudaStream_t st,
               std::string &err);
   int n_kernels() const { return n_kernels_; }
-  static std::string generate_source(const Plan &plan);
+  static std::string generate_source(const Plan &plan, int set = 0);
 
  private:
-  void *module_ = nullptr; // CUmodule
+  bool load_set(Plan &plan, const std::vector<const void *> &col_dev_ptr, int set, bool allow_regroup, std::string &err);
+  void *module_[2] = {nullptr, nullptr}; // CUmodule
   std::vector<unsigned long long> dev_allocs_; // instance tables of class groups
-  void *fn_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t smem_[5] = {0, 0, 0, 0, 0};
-  std::vector<int> groups_of_[5];
-  CbSchedule sched_[5];
+  void *fn_[KS__N] = {nullptr};
+  size_t smem_[KS__N] = {0};
+  std::vector<int> groups_of_[KS__N];
+  CbSchedule sched_[KS__N];
   int n_kernels_ = 0;
 };
 

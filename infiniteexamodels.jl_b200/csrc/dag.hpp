@@ -25,6 +25,8 @@ enum DOp : int32_t {
   D_W,         // root weight of group member a: y[row] for constraints, obj_weight for objectives
   D_SEL2,      // (index slot a == index slot b) ? 2.0 : 1.0   (lower-triangle diagonal rule)
   D_CPAR,      // per-instance constant a of a shape class (plan.hpp: Group::is_class); opaque to folding
+  D_LOADV,     // v[index slot a]: the vector of a matrix-free product (jprod! / hprod!), addressed like x
+  D_SELNE,     // (index slot a != index slot b) ? 1.0 : 0.0   (mirror contribution of a lower-triangle entry)
   D_ADD, D_SUB, D_MUL, D_DIV, D_NEG, D_POW,
   D_SQRT, D_CBRT, D_ABS, D_SIGNP, D_EXP, D_EXP2, D_LOG, D_LOG2, D_LOG10, D_LOG1P,
   D_SIN, D_COS, D_TAN, D_ASIN, D_ACOS, D_ATAN, D_SINH, D_COSH, D_TANH, D_ATANH,
@@ -78,6 +80,12 @@ class Dag {
   int loadp(int islot) { return intern(D_LOADP, islot, 0, 0.0); }
   int w(int member = 0) { return intern(D_W, member, 0, 0.0); }
   int cpar(int j) { return intern(D_CPAR, j, 0, 0.0); }
+  int loadv(int islot) { return intern(D_LOADV, islot, 0, 0.0); }
+  int selne(int ia, int ib) {
+    if (ia == ib) return cnst(0.0);
+    if (ia > ib) std::swap(ia, ib);
+    return intern(D_SELNE, ia, ib, 0.0);
+  }
   int sel2(int ia, int ib) {
     if (ia == ib) return cnst(2.0);
     if (ia > ib) std::swap(ia, ib);

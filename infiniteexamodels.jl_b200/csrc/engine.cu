@@ -31,7 +31,7 @@ namespace iexa {
   } while (0)
 
 constexpr int BLOCK = 128;
-enum { SINK_DENSE = 0, SINK_SUM = 1, SINK_SCATTER = 2 };
+enum { SINK_DENSE = 0, SINK_SUM = 1, SINK_SCATTER = 2, SINK_SCATTER_PROD = 3 };
 
 // ------------------------------------------------------------------------------------------
 // Tape interpreter.  Registers live in a per-thread local array (interleaved per thread by
@@ -42,7 +42,7 @@ template <int NREG>
 __global__ void __launch_bounds__(BLOCK)
 interp_kernel(const GenD *__restrict__ gens, const WorkItem *__restrict__ work, int prog, int sink,
               const double *__restrict__ x, const double *__restrict__ theta,
-              const double *__restrict__ y, double sigma, double *__restrict__ out,
+              const double *__restrict__ y, const double *__restrict__ vec, double sigma, double *__restrict__ out,
               double *__restrict__ partials) {
   const WorkItem w = work[blockIdx.x];
   const GenD &g = gens[w.gen];
@@ -65,14 +65,26 @@ interp_kernel(const GenD *__restrict__ gens, const WorkItem *__restrict__ work, 
       case D_FIELD: r[dst] = col_fp(g.fcol[ia], k); break;
       case D_LOADX: r[dst] = __ldg(x + (idx_eval(g, ia, k) - 1)); break;
       case D_LOADP: r[dst] = __ldg(theta + (idx_eval(g, ia, k) - 1)); break;
+      case D_LOADV: r[dst] = __ldg(vec + (idx_eval(g, ia, k) - 1)); break;
       case D_W: r[dst] = W; break;
       case D_SEL2: r[dst] = idx_eval(g, ia, k) == idx_eval(g, ib, k) ? 2.0 : 1.0; break;
+      case D_SELNE: r[dst] = idx_eval(g, ia, k) != idx_eval(g, ib, k) ? 1.0 : 0.0; break;
       case D_OUT: {
         const double v = ia >= 0 ? r[ia] : cp[~ia];
         if (sink == SINK_DENSE) {
           if (active) out[obase + dst] = v;
         } else if (sink == SINK_SUM) {
           if (active) acc += v;
+        } else if (sink == SINK_SCATTER_PROD) { // jtprod! / hprod!: out is zero-filled, every output adds
+          const int islot = g.scat_slot[prog - PROG_JTV][dst];
+          if (g.idx[islot].nterms == 0) {
+            double s = active ? v : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(out + (g.idx[islot].base - 1), s);
+          } else if (active) {
+            atomicAdd(out + (idx_eval(g, islot, k) - 1), v);
+          }
         } else {
           int islot = g.jac_slot[dst];
           if (islot < 0) { // single writer (Plan::analyse_grad): plain store, the range is not zero-filled
@@ -115,7 +127,7 @@ interp_kernel(const GenD *__restrict__ gens, const WorkItem *__restrict__ work, 
 __global__ void __launch_bounds__(BLOCK)
 interp_kernel_big(const GenD *__restrict__ gens, const WorkItem *__restrict__ work, int prog, int sink,
                   const double *__restrict__ x, const double *__restrict__ theta,
-                  const double *__restrict__ y, double sigma, double *__restrict__ out,
+                  const double *__restrict__ y, const double *__restrict__ vec, double sigma, double *__restrict__ out,
                   double *__restrict__ partials, double *__restrict__ scratch) {
   const WorkItem w = work[blockIdx.x];
   const GenD &g = gens[w.gen];
@@ -135,12 +147,15 @@ interp_kernel_big(const GenD *__restrict__ gens, const WorkItem *__restrict__ wo
       case D_FIELD: r[I.dst * nthr] = col_fp(g.fcol[I.a], k); break;
       case D_LOADX: r[I.dst * nthr] = x[idx_eval(g, I.a, k) - 1]; break;
       case D_LOADP: r[I.dst * nthr] = theta[idx_eval(g, I.a, k) - 1]; break;
+      case D_LOADV: r[I.dst * nthr] = vec[idx_eval(g, I.a, k) - 1]; break;
       case D_W: r[I.dst * nthr] = W; break;
       case D_SEL2: r[I.dst * nthr] = idx_eval(g, I.a, k) == idx_eval(g, I.b, k) ? 2.0 : 1.0; break;
+      case D_SELNE: r[I.dst * nthr] = idx_eval(g, I.a, k) != idx_eval(g, I.b, k) ? 1.0 : 0.0; break;
       case D_OUT: {
         const double v = I.a >= 0 ? r[I.a * nthr] : P.cpool[~I.a];
         if (sink == SINK_DENSE) { if (active) out[obase + I.dst] = v; }
         else if (sink == SINK_SUM) { if (active) acc += v; }
+        else if (sink == SINK_SCATTER_PROD) { if (active) atomicAdd(out + (idx_eval(g, g.scat_slot[prog - PROG_JTV][I.dst], k) - 1), v); }
         else if (active) {
           const int is_ = g.jac_slot[I.dst];
           if (is_ < 0) out[idx_eval(g, ~is_, k) - 1] = v;
@@ -241,23 +256,6 @@ structure_kernel(const GenD *__restrict__ gens, const WorkItem *__restrict__ wor
   }
 }
 
-// COO products used by jprod!/jtprod!/hprod! (matrix-free solvers only; not on the MadNLP/Ipopt path)
-__global__ void coo_prod_kernel(long long nnz, const int *__restrict__ rows, const int *__restrict__ cols,
-                                const double *__restrict__ vals, const double *__restrict__ v,
-                                double *__restrict__ out, int mode) {
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nnz;
-       p += (long long)gridDim.x * blockDim.x) {
-    const int i = rows[p] - 1, j = cols[p] - 1;
-    const double a = vals[p];
-    if (mode == 0) atomicAdd(out + i, a * v[j]);          // Jv
-    else if (mode == 1) atomicAdd(out + j, a * v[i]);     // J'v
-    else {                                                 // Hv, lower-triangular storage
-      atomicAdd(out + i, a * v[j]);
-      if (i != j) atomicAdd(out + j, a * v[i]);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 struct DevBuf {
   void *p = nullptr;
@@ -291,6 +289,9 @@ class CudaEngine : public Engine {
     cudaSetDevice(device_);
     for (auto &kv : registered_) cudaHostUnregister(kv.first);
     if (pinned_f_) cudaFreeHost(pinned_f_);
+    if (par_stage_) cudaFreeHost(par_stage_);
+    if (par_stage_event_) cudaEventDestroy(par_stage_event_);
+    if (stage_x_event_) cudaEventDestroy(stage_x_event_);
     spec_.reset();
   }
 
@@ -390,20 +391,7 @@ class CudaEngine : public Engine {
     double *gd = g;
     if (memspace == IEXA_MEM_HOST) { CK(stage_out_.ensure((size_t)plan_.nvar * 8)); gd = stage_out_.as<double>(); }
     // only the entries that are not written by a single-writer slot need zero-filling
-    if (!plan_.grad_zero_ranges.empty()) {
-      const int nr = (int)plan_.grad_zero_ranges.size();
-      if (!zero_ranges_.p) {
-        std::vector<long long> rr;
-        for (auto &zr : plan_.grad_zero_ranges) { rr.push_back(zr.first); rr.push_back(zr.second); }
-        CK(zero_ranges_.ensure(rr.size() * 8));
-        CK(cudaMemcpy(zero_ranges_.p, rr.data(), rr.size() * 8, cudaMemcpyHostToDevice));
-      }
-      int64_t longest = 0;
-      for (auto &zr : plan_.grad_zero_ranges) longest = std::max<int64_t>(longest, zr.second);
-      const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((longest / 2 + 255) / 256, 148 * 8));
-      zero_ranges_kernel<<<dim3(gx, std::min(nr, 65535)), 256, 0, st>>>(zero_ranges_.as<long long>(), nr, gd);
-      CK(cudaGetLastError());
-    }
+    if ((rc = zero_ranges(plan_.grad_zero_ranges, zero_ranges_, gd, st, err))) return rc;
     rc = launch(CB_GRAD, PROG_D1, SINK_SCATTER, xd, nullptr, 1.0, gd, st, err);
     if (rc) return rc;
     return out(g, gd, plan_.nvar, memspace, st, err);
@@ -421,24 +409,52 @@ class CudaEngine : public Engine {
   }
 
   int jprod(const double *x, const double *v, double *Jv, int memspace, void *stream, std::string &err) override {
-    return prod(0, x, nullptr, v, 1.0, Jv, memspace, stream, err);
+    return prod(CB_JPROD, x, nullptr, v, 1.0, Jv, memspace, stream, err);
   }
   int jtprod(const double *x, const double *v, double *Jtv, int memspace, void *stream, std::string &err) override {
-    return prod(1, x, nullptr, v, 1.0, Jtv, memspace, stream, err);
+    return prod(CB_JTPROD, x, nullptr, v, 1.0, Jtv, memspace, stream, err);
   }
   int hprod(const double *x, const double *y, const double *v, double sigma, double *Hv, int memspace,
             void *stream, std::string &err) override {
-    return prod(2, x, y, v, sigma, Hv, memspace, stream, err);
+    return prod(CB_HPROD, x, y, v, sigma, Hv, memspace, stream, err);
   }
 
-  int set_par(int64_t off, int64_t n, const double *vals, std::string &err) override {
+  // set_parameter! (infiniteopt_backend.jl:522,546): ordered on the CALLER's stream like every callback, so an update
+  // can neither overtake a callback enqueued before it nor be overtaken by one enqueued after it.  The values are staged
+  // in a pinned buffer of the engine (the caller's array may be pageable and may change right after the call).
+  int set_par(int64_t off, int64_t n, const double *vals, void *stream, bool device_sync, std::string &err) override {
     CK(cudaSetDevice(device_));
-    if (n > 0) CK(cudaMemcpy(theta_.as<double>() + off, vals, (size_t)n * 8, cudaMemcpyHostToDevice));
+    if (n <= 0) return IEXA_OK;
+    if (device_sync) { // iexa_set_par: no stream given — safe against callbacks in flight on ANY stream
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(theta_.as<double>() + off, vals, (size_t)n * 8, cudaMemcpyHostToDevice));
+      return IEXA_OK;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (par_stage_event_) CK(cudaEventSynchronize(par_stage_event_)); // the previous update has left the staging buffer
+    else CK(cudaEventCreateWithFlags(&par_stage_event_, cudaEventDisableTiming));
+    if (par_stage_bytes_ < (size_t)n * 8) {
+      if (par_stage_) cudaFreeHost(par_stage_);
+      par_stage_ = nullptr; par_stage_bytes_ = 0;
+      CK(cudaMallocHost((void **)&par_stage_, (size_t)n * 8));
+      par_stage_bytes_ = (size_t)n * 8;
+    }
+    std::memcpy(par_stage_, vals, (size_t)n * 8);
+    CK(cudaMemcpyAsync(theta_.as<double>() + off, par_stage_, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(par_stage_event_, st));
     return IEXA_OK;
   }
 
   int launches(int cb) const override {
     if (cb < 0 || cb >= CB__N) return 0;
+    if (cb >= CB_JPROD) {
+      const Table &T = table_[cb == CB_JPROD ? CB_CONS : cb == CB_JTPROD ? CB_JAC : CB_HESS];
+      if (cb == CB_JPROD) return T.nblocks > 0 ? 1 : 0;
+      if (!(spec_ && spec_->products_built())) return 1 + (T.nblocks > 0 ? 1 : 0); // memset + interpreter
+      const int w = cb == CB_JTPROD ? 0 : 1;
+      return (plan_.scat_zero_ranges[w].empty() ? 0 : 1) + (spec_->has(w == 0 ? KS_JTPROD0 : KS_HPROD0) ? 1 : 0) +
+             (spec_->has(w == 0 ? KS_JTPROD1 : KS_HPROD1) ? 1 : 0);
+    }
     int n = table_[cb].nblocks > 0 ? 1 : 0;
     if (cb == CB_OBJ && n) n += 1;
     if (cb == CB_GRAD && n && !plan_.grad_zero_ranges.empty()) n += 1;
@@ -460,13 +476,15 @@ class CudaEngine : public Engine {
   DevBuf leaf_, desc_, gens_, theta_, work_;
   DevBuf zero_ranges_;
   DevBuf partials_, fdev_, stage_x_, stage_y_, stage_v_, stage_out_, stage_a_, stage_b_, scratch_;
-  DevBuf coo_rows_j_, coo_cols_j_, coo_rows_h_, coo_cols_h_, coo_vals_;
-  bool coo_j_ready_ = false, coo_h_ready_ = false;
+  DevBuf scat_zero_[2];        // zero ranges of jtprod! / hprod! (Plan::scat_zero_ranges)
+  int prod_max_nreg_[3] = {0, 0, 0}; // interpreter register file of the jv / jtv / hv programs
+  bool prod_spec_tried_ = false;
+  double *par_stage_ = nullptr; size_t par_stage_bytes_ = 0; cudaEvent_t par_stage_event_ = nullptr;
   GenD *gens_dev_ = nullptr;
   std::vector<GenD> gens_host_; // device pointers inside; objs first then cons
   Table table_[CB__N];
-  Table gtable_[CB__N]; // specialised path: block -> (group, block of supports)
-  DevBuf gwork_;
+  Table gtable_[KS__N]; // specialised path, per kernel slot: block -> (group, block of supports)
+  DevBuf gwork_[2];
   std::vector<const void *> col_dev_ptr_;
   double *pinned_f_ = nullptr;
   std::map<void *, size_t> registered_;
@@ -487,18 +505,22 @@ class CudaEngine : public Engine {
     std::vector<Generator *> all;
     for (auto &g : P.objs) all.push_back(&g);
     for (auto &g : P.cons) all.push_back(&g);
-    struct Offs { size_t code[3], cpool[3], jac_slot, hess_slot; };
+    struct Offs { size_t code[PROG__N], cpool[PROG__N], jac_slot, hess_slot, scat[2]; };
     std::vector<Offs> offs(all.size());
     for (size_t gi = 0; gi < all.size(); ++gi) {
       Generator &g = *all[gi];
       const Iterator &it = P.itrs[g.itr];
       for (int32_t s : g.c.int_cols) need_col(it.int_cols[s].col);
       for (int32_t s : g.c.fp_cols) need_col(it.fp_cols[s].col);
-      Program *pr[3] = {&g.c.val, &g.c.d1, &g.c.d2};
-      for (int p = 0; p < 3; ++p) {
+      Program *pr[PROG__N] = {&g.c.val, &g.c.d1, &g.c.d2, &g.c.jv, &g.c.jtv, &g.c.hv};
+      for (int p = 0; p < PROG__N; ++p) {
         offs[gi].code[p] = A.add(pr[p]->code.data(), pr[p]->code.size() * sizeof(Instr));
         offs[gi].cpool[p] = A.add(pr[p]->cpool.data(), pr[p]->cpool.size() * 8);
       }
+      offs[gi].scat[0] = A.add(g.c.jtv_slot.data(), g.c.jtv_slot.size() * 4);
+      offs[gi].scat[1] = A.add(g.c.hv_slot.data(), g.c.hv_slot.size() * 4);
+      if (!g.is_obj) { prod_max_nreg_[0] = std::max(prod_max_nreg_[0], g.c.jv.nreg); prod_max_nreg_[1] = std::max(prod_max_nreg_[1], g.c.jtv.nreg); }
+      prod_max_nreg_[2] = std::max(prod_max_nreg_[2], g.c.hv.nreg);
       std::vector<int32_t> js(g.c.jac_slot);
       if (g.is_obj) for (size_t c = 0; c < js.size(); ++c) if (c < g.grad_direct.size() && g.grad_direct[c]) js[c] = ~js[c];
       offs[gi].jac_slot = A.add(js.data(), js.size() * 4);
@@ -560,8 +582,11 @@ class CudaEngine : public Engine {
       d.n_fcol = (int32_t)g.c.fp_cols.size();
       d.n_idx = (int32_t)g.c.uidx.size();
       d.is_obj = g.is_obj ? 1 : 0;
-      Program *pr[3] = {&g.c.val, &g.c.d1, &g.c.d2};
-      for (int p = 0; p < 3; ++p) {
+      Program *pr[PROG__N] = {&g.c.val, &g.c.d1, &g.c.d2, &g.c.jv, &g.c.jtv, &g.c.hv};
+      d.scat_slot[0] = (const int32_t *)(lb + offs[gi].scat[0]);
+      d.scat_slot[1] = (const int32_t *)(lb + offs[gi].scat[1]);
+      for (int p = PROG_JV; p < PROG__N; ++p) { d.out_local[p] = g.l0; d.out_global[p] = g.o0; d.ostep[p] = 1; }
+      for (int p = 0; p < PROG__N; ++p) {
         d.prog[p].code = (const Instr *)(lb + offs[gi].code[p]);
         d.prog[p].cpool = (const double *)(lb + offs[gi].cpool[p]);
         d.prog[p].ncode = (int32_t)pr[p]->code.size();
@@ -589,7 +614,7 @@ class CudaEngine : public Engine {
     // work tables
     const int nobj = (int)P.objs.size(), ncon = (int)P.cons.size();
     std::vector<WorkItem> items;
-    size_t starts[CB__N + 1];
+    size_t starts[6];
     auto add_range = [&](int g0, int g1, int prog, bool skip_empty_out, int &max_nreg) {
       for (int gi = g0; gi < g1; ++gi) {
         const Generator &g = *all[gi];
@@ -600,16 +625,16 @@ class CudaEngine : public Engine {
         for (int64_t b = 0; b * BLOCK < n; ++b) items.push_back(WorkItem{gi, (int32_t)b});
       }
     };
-    int mr[CB__N] = {0, 0, 0, 0, 0};
+    int mr[5] = {0, 0, 0, 0, 0};
     starts[CB_OBJ] = items.size();  add_range(0, nobj, PROG_VAL, false, mr[CB_OBJ]);
     starts[CB_GRAD] = items.size(); add_range(0, nobj, PROG_D1, true, mr[CB_GRAD]);
     starts[CB_CONS] = items.size(); add_range(nobj, nobj + ncon, PROG_VAL, false, mr[CB_CONS]);
     starts[CB_JAC] = items.size();  add_range(nobj, nobj + ncon, PROG_D1, true, mr[CB_JAC]);
     starts[CB_HESS] = items.size(); add_range(0, nobj + ncon, PROG_D2, true, mr[CB_HESS]);
-    starts[CB__N] = items.size();
+    starts[5] = items.size();
     CK(work_.ensure(items.size() * sizeof(WorkItem) + 16));
     if (!items.empty()) CK(cudaMemcpy(work_.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
-    for (int cb = 0; cb < CB__N; ++cb) {
+    for (int cb = 0; cb < 5; ++cb) {
       table_[cb].work = work_.as<WorkItem>() + starts[cb];
       table_[cb].nblocks = (int)(starts[cb + 1] - starts[cb]);
       table_[cb].max_nreg = mr[cb];
@@ -617,10 +642,12 @@ class CudaEngine : public Engine {
     return IEXA_OK;
   }
 
-  int build_group_tables(std::string &err) {
+  // work tables of the specialised kernels of one module (set 0: the five callbacks; set 1: the products)
+  int build_group_tables(std::string &err, int set = 0) {
+    const int ks0 = set == 0 ? 0 : KS_JPROD, ks1 = set == 0 ? KS_JPROD : KS__N;
     std::vector<WorkItem> items;
-    size_t starts[CB__N + 1];
-    for (int cb = 0; cb < CB__N; ++cb) {
+    size_t starts[KS__N + 1];
+    for (int cb = ks0; cb < ks1; ++cb) {
       starts[cb] = items.size();
       if (!spec_->has(cb)) continue;
       // Big groups are scheduled arithmetically (CbSchedule, codegen.hpp); the table holds the rest.
@@ -642,7 +669,8 @@ class CudaEngine : public Engine {
       const char *oe = getenv("IEXA_ORDER");
       bool lpt = oe ? oe[0] == 'l' : false;
       if (lpt) { // heaviest groups first (longest processing time first): the kernel drains on short blocks
-        const int prog = (cb == CB_OBJ || cb == CB_CONS) ? PROG_VAL : (cb == CB_GRAD || cb == CB_JAC) ? PROG_D1 : PROG_D2;
+        const int prog = (cb == CB_OBJ || cb == CB_CONS) ? PROG_VAL : (cb == CB_GRAD || cb == CB_JAC) ? PROG_D1 : cb == CB_HESS ? PROG_D2
+                         : cb == KS_JPROD ? PROG_JV : (cb == KS_JTPROD0 || cb == KS_JTPROD1) ? PROG_JTV : PROG_HV;
         std::stable_sort(ord.begin(), ord.end(), [&](const Ord &a, const Ord &b) {
           return plan_.groups[a.gi].prog[prog].code.size() > plan_.groups[b.gi].prog[prog].code.size();
         });
@@ -650,11 +678,12 @@ class CudaEngine : public Engine {
       std::stable_sort(ord.begin(), ord.end(), [](const Ord &a, const Ord &b) { return a.frac < b.frac; });
       for (const Ord &o : ord) items.push_back(WorkItem{o.gi, o.b});
     }
-    starts[CB__N] = items.size();
-    CK(gwork_.ensure(items.size() * sizeof(WorkItem) + 16));
-    if (!items.empty()) CK(cudaMemcpy(gwork_.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
-    for (int cb = 0; cb < CB__N; ++cb) {
-      gtable_[cb].work = gwork_.as<WorkItem>() + starts[cb];
+    starts[ks1] = items.size();
+    DevBuf &gw = gwork_[set];
+    CK(gw.ensure(items.size() * sizeof(WorkItem) + 16));
+    if (!items.empty()) CK(cudaMemcpy(gw.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    for (int cb = ks0; cb < ks1; ++cb) {
+      gtable_[cb].work = gw.as<WorkItem>() + starts[cb];
       if (!spec_->has(cb)) { gtable_[cb].nblocks = 0; continue; }
       const CbSchedule &S = spec_->schedule(cb);
       if ((int64_t)(starts[cb + 1] - starts[cb]) != S.ntable) { err = "work table does not match the block schedule"; return IEXA_ERR_INVALID; }
@@ -694,10 +723,20 @@ class CudaEngine : public Engine {
     if (!src) { dev = nullptr; return IEXA_OK; }
     if (memspace == IEXA_MEM_DEVICE) { dev = src; return IEXA_OK; }
     const bool is_x = &stage == &stage_x_;
-    if (is_x && same_x_ && stage_x_valid_ && stage.bytes >= (size_t)n * 8) { dev = stage.as<double>(); return IEXA_OK; } // new_x == false
+    if (is_x && same_x_ && stage_x_valid_ && stage.bytes >= (size_t)n * 8) { // new_x == false
+      // the device copy may have been uploaded on ANOTHER stream: order this call after that upload
+      if (st != stage_x_stream_ && stage_x_event_) CK(cudaStreamWaitEvent(st, stage_x_event_, 0));
+      dev = stage.as<double>();
+      return IEXA_OK;
+    }
     CK(stage.ensure((size_t)n * 8));
     CK(cudaMemcpyAsync(stage.p, src, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    if (is_x) stage_x_valid_ = true;
+    if (is_x) {
+      stage_x_valid_ = true;
+      if (!stage_x_event_) CK(cudaEventCreateWithFlags(&stage_x_event_, cudaEventDisableTiming));
+      CK(cudaEventRecord(stage_x_event_, st));
+      stage_x_stream_ = st;
+    }
     dev = stage.as<double>();
     return IEXA_OK;
   }
@@ -707,6 +746,7 @@ class CudaEngine : public Engine {
     return same_x_ ? (int)IEXA_MEM_HOST : memspace;
   }
   bool same_x_ = false, stage_x_valid_ = false;
+  cudaEvent_t stage_x_event_ = nullptr; cudaStream_t stage_x_stream_ = nullptr;
   int out(double *dst, const double *dev, int64_t n, int memspace, cudaStream_t st, std::string &err) {
     if (memspace == IEXA_MEM_DEVICE) return IEXA_OK;
     CK(cudaMemcpyAsync(dst, dev, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
@@ -723,18 +763,26 @@ class CudaEngine : public Engine {
     if (spec_ && spec_->has(cb)) {
       const Table &GT = gtable_[cb];
       if (GT.nblocks == 0) return IEXA_OK;
-      if (!spec_->launch(cb, GT.work, xd, th, yd, sigma, outd, part, st, err)) return IEXA_ERR_CUDA;
+      if (!spec_->launch(cb, GT.work, xd, th, yd, nullptr, sigma, outd, part, st, err)) return IEXA_ERR_CUDA;
       return IEXA_OK;
     }
-    if (T.max_nreg <= 32)
-      interp_kernel<32><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, sigma, outd, part);
-    else if (T.max_nreg <= 96)
-      interp_kernel<96><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, sigma, outd, part);
-    else if (T.max_nreg <= 256)
-      interp_kernel<256><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, sigma, outd, part);
+    return launch_interp(T, T.max_nreg, prog, sink, xd, yd, nullptr, sigma, outd, st, err);
+  }
+
+  int launch_interp(const Table &T, int max_nreg, int prog, int sink, const double *xd, const double *yd, const double *vd,
+                    double sigma, double *outd, cudaStream_t st, std::string &err) {
+    if (T.nblocks == 0) return IEXA_OK;
+    double *part = partials_.as<double>();
+    const double *th = theta_.as<double>();
+    if (max_nreg <= 32)
+      interp_kernel<32><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, vd, sigma, outd, part);
+    else if (max_nreg <= 96)
+      interp_kernel<96><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, vd, sigma, outd, part);
+    else if (max_nreg <= 256)
+      interp_kernel<256><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, vd, sigma, outd, part);
     else {
-      CK(scratch_.ensure((size_t)T.max_nreg * T.nblocks * BLOCK * 8));
-      interp_kernel_big<<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, sigma, outd, part,
+      CK(scratch_.ensure((size_t)max_nreg * T.nblocks * BLOCK * 8));
+      interp_kernel_big<<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, vd, sigma, outd, part,
                                                      scratch_.as<double>());
     }
     CK(cudaGetLastError());
@@ -758,51 +806,76 @@ class CudaEngine : public Engine {
     return out(o, od, n, memspace, st, err);
   }
 
-  int ensure_coo(int which, cudaStream_t st, std::string &err) {
-    bool &ready = which == 0 ? coo_j_ready_ : coo_h_ready_;
-    if (ready) return IEXA_OK;
-    const int64_t n = which == 0 ? plan_.loc_nnzj : plan_.loc_nnzh;
-    DevBuf &r = which == 0 ? coo_rows_j_ : coo_rows_h_, &c = which == 0 ? coo_cols_j_ : coo_cols_h_;
-    CK(r.ensure((size_t)n * 4)); CK(c.ensure((size_t)n * 4));
-    const Table &T = table_[which == 0 ? CB_JAC : CB_HESS];
-    if (T.nblocks > 0) {
-      structure_kernel<int32_t><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, which, 1, r.as<int32_t>(), c.as<int32_t>());
-      CK(cudaGetLastError());
+  int zero_ranges(const std::vector<std::pair<int64_t, int64_t>> &ranges, DevBuf &tab, double *dst, cudaStream_t st, std::string &err) {
+    if (ranges.empty()) return IEXA_OK;
+    const int nr = (int)ranges.size();
+    if (!tab.p) {
+      std::vector<long long> rr;
+      for (auto &zr : ranges) { rr.push_back(zr.first); rr.push_back(zr.second); }
+      CK(tab.ensure(rr.size() * 8));
+      CK(cudaMemcpy(tab.p, rr.data(), rr.size() * 8, cudaMemcpyHostToDevice));
     }
-    ready = true;
+    int64_t longest = 0;
+    for (auto &zr : ranges) longest = std::max<int64_t>(longest, zr.second);
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((longest / 2 + 255) / 256, 148 * 8));
+    zero_ranges_kernel<<<dim3(gx, std::min(nr, 65535)), 256, 0, st>>>(tab.as<long long>(), nr, dst);
+    CK(cudaGetLastError());
     return IEXA_OK;
   }
 
-  int prod(int mode, const double *x, const double *y, const double *v, double sigma, double *o, int memspace,
+  // jprod! / jtprod! / hprod! — fused product kernels: the first / second order programs with a product epilogue
+  // (gen.hpp: build_products), no COO values are materialised.
+  //   jprod!:  Jv[row] = sum_c d1_c * v[col_c] in registers, one coalesced store per row; no atomics (bit-reproducible);
+  //   jtprod! / hprod!: per group ONE sum per touched variable (contributions of all fused rows combined in registers);
+  //   phase-0 groups store their single-writer blocks directly (no zero-fill), phase 1 adds the rest with atomics
+  //   (warp-shuffle reduced for shared variables) — Plan::analyse_scatter.
+  int prod(int cb, const double *x, const double *y, const double *v, double sigma, double *o, int memspace,
            void *stream, std::string &err) {
     CK(cudaSetDevice(device_));
     memspace = host_mode(memspace);
     cudaStream_t st = (cudaStream_t)stream;
-    const int which = mode == 2 ? 1 : 0;
-    const int64_t nnz = which == 0 ? plan_.loc_nnzj : plan_.loc_nnzh;
-    const int64_t nv = mode == 1 ? plan_.loc_ncon : plan_.nvar;
-    const int64_t no = mode == 0 ? plan_.loc_ncon : plan_.nvar;
-    int rc = ensure_coo(which, st, err);
-    if (rc) return rc;
+    const int64_t nv = cb == CB_JTPROD ? plan_.loc_ncon : plan_.nvar;
+    const int64_t no = cb == CB_JPROD ? plan_.loc_ncon : plan_.nvar;
+    if (spec_ && !prod_spec_tried_) { // the product kernels are compiled on their first use (second NVRTC module)
+      prod_spec_tried_ = true;
+      std::string serr;
+      if (!spec_->build_products(plan_, col_dev_ptr_, serr) || build_group_tables(serr, 1) != IEXA_OK) { prod_note_ = serr; spec_error_ = "product kernels: " + serr; }
+    }
     const double *xd = nullptr, *yd = nullptr, *vd = nullptr;
+    int rc;
     if ((rc = in(x, plan_.nvar, memspace, stage_x_, st, xd, err))) return rc;
     if ((rc = in(y, plan_.loc_ncon, memspace, stage_y_, st, yd, err))) return rc;
     if ((rc = in(v, nv, memspace, stage_v_, st, vd, err))) return rc;
-    CK(coo_vals_.ensure((size_t)nnz * 8));
-    rc = which == 0 ? launch(CB_JAC, PROG_D1, SINK_DENSE, xd, nullptr, 1.0, coo_vals_.as<double>(), st, err)
-                    : launch(CB_HESS, PROG_D2, SINK_DENSE, xd, yd, sigma, coo_vals_.as<double>(), st, err);
-    if (rc) return rc;
     double *od = o;
     if (memspace == IEXA_MEM_HOST) { CK(stage_out_.ensure((size_t)no * 8)); od = stage_out_.as<double>(); }
-    CK(cudaMemsetAsync(od, 0, (size_t)no * 8, st));
-    if (nnz > 0) {
-      const DevBuf &r = which == 0 ? coo_rows_j_ : coo_rows_h_, &c = which == 0 ? coo_cols_j_ : coo_cols_h_;
-      int nb = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 16);
-      coo_prod_kernel<<<nb, 256, 0, st>>>(nnz, (const int *)r.p, (const int *)c.p, coo_vals_.as<double>(), vd, od, mode);
-      CK(cudaGetLastError());
+    const bool spec = spec_ && spec_->products_built() && prod_note_.empty();
+    double *part = partials_.as<double>();
+    const double *th = theta_.as<double>();
+    if (cb == CB_JPROD) {
+      if (spec) {
+        if (spec_->has(KS_JPROD) && gtable_[KS_JPROD].nblocks > 0 &&
+            !spec_->launch(KS_JPROD, gtable_[KS_JPROD].work, xd, th, nullptr, vd, 1.0, od, part, st, err)) return IEXA_ERR_CUDA;
+      } else if ((rc = launch_interp(table_[CB_CONS], prod_max_nreg_[0], PROG_JV, SINK_DENSE, xd, nullptr, vd, 1.0, od, st, err))) return rc;
+      return out(o, od, no, memspace, st, err);
+    }
+    const int w = cb == CB_JTPROD ? 0 : 1;
+    // J'v: the root weight leaf of every row is v[row] — the kernels read it through their y argument
+    const double *wy = w == 0 ? vd : yd, *wv = w == 0 ? nullptr : vd;
+    if (spec) {
+      if ((rc = zero_ranges(plan_.scat_zero_ranges[w], scat_zero_[w], od, st, err))) return rc;
+      for (int ph = 0; ph < 2; ++ph) {
+        const int ks = (w == 0 ? KS_JTPROD0 : KS_HPROD0) + ph;
+        if (spec_->has(ks) && gtable_[ks].nblocks > 0 &&
+            !spec_->launch(ks, gtable_[ks].work, xd, th, wy, wv, sigma, od, part, st, err)) return IEXA_ERR_CUDA;
+      }
+    } else {
+      CK(cudaMemsetAsync(od, 0, (size_t)no * 8, st));
+      if ((rc = launch_interp(table_[w == 0 ? CB_JAC : CB_HESS], prod_max_nreg_[1 + w], w == 0 ? PROG_JTV : PROG_HV, SINK_SCATTER_PROD,
+                              xd, wy, wv, sigma, od, st, err))) return rc;
     }
     return out(o, od, no, memspace, st, err);
   }
+  std::string prod_note_;
 };
 
 Engine *make_cuda_engine(Plan &plan, int device, uint32_t flags, std::string &err) {

@@ -6,7 +6,10 @@
 
 namespace iexa {
 
-enum Callback { CB_OBJ = 0, CB_GRAD = 1, CB_CONS = 2, CB_JAC = 3, CB_HESS = 4, CB__N = 5 };
+enum Callback { CB_OBJ = 0, CB_GRAD = 1, CB_CONS = 2, CB_JAC = 3, CB_HESS = 4, CB_JPROD = 5, CB_JTPROD = 6, CB_HPROD = 7, CB__N = 8 };
+// kernel slots of the specialised path: the five callbacks, jprod!, and the two phases of each scatter product
+// (phase 0: groups whose single-writer outputs are plain stores; phase 1: everything else, atomics — plan.hpp)
+enum KernelSlot { KS_JPROD = 5, KS_JTPROD0 = 6, KS_JTPROD1 = 7, KS_HPROD0 = 8, KS_HPROD1 = 9, KS__N = 10 };
 
 struct Engine {
   virtual ~Engine() {}
@@ -26,7 +29,7 @@ struct Engine {
                      std::string &err) = 0;
   virtual int hprod(const double *x, const double *y, const double *v, double sigma, double *Hv,
                     int memspace, void *stream, std::string &err) = 0;
-  virtual int set_par(int64_t off, int64_t n, const double *vals, std::string &err) = 0;
+  virtual int set_par(int64_t off, int64_t n, const double *vals, void *stream, bool device_sync, std::string &err) = 0;
   virtual int host_register(void *p, size_t bytes, std::string &err) = 0;
   virtual int host_unregister(void *p, std::string &err) = 0;
   virtual int launches(int cb) const = 0;

@@ -65,7 +65,7 @@ struct ProgD {
   const double *cpool;
   int32_t ncode, nreg, nout, uses_w;
 };
-enum { PROG_VAL = 0, PROG_D1 = 1, PROG_D2 = 2 };
+enum { PROG_VAL = 0, PROG_D1 = 1, PROG_D2 = 2, PROG_JV = 3, PROG_JTV = 4, PROG_HV = 5, PROG__N = 6 };
 struct GenD {
   long long K, k0, k1;
   long long row_local;  // local row of support k0 (constraints): W = y[row_local + k - k0]
@@ -76,11 +76,11 @@ struct GenD {
   const int32_t *jac_slot;  // [o1step] index slot per first-order slot
   const int32_t *hess_slot; // [2*o2step] index-slot pairs
   int32_t n_icol, n_fcol, n_idx, is_obj;
-  ProgD prog[3];
-  long long out_local[3];  // local output offset of support k0 for val / d1 / d2
-  long long out_global[3]; // global offsets o0 / o1 (og for objectives) / o2
-  int32_t ostep[3];
-  int32_t pad;
+  ProgD prog[PROG__N];
+  long long out_local[PROG__N];  // local output offset of support k0 for val / d1 / d2 / jv (jtv, hv: unused)
+  long long out_global[PROG__N]; // global offsets o0 / o1 (og for objectives) / o2
+  int32_t ostep[PROG__N];
+  const int32_t *scat_slot[2];   // jtv / hv: index slot of every program output
 };
 
 IEXA_HD long long col_int(const ColD &c, long long k) {

@@ -56,7 +56,56 @@ struct GenCompiled {
   // programs
   Program val, d1, d2;
   std::vector<uint8_t> x_slots_val, x_slots_d1, x_slots_d2; // which index slots each program LOADX-es
+  // matrix-free products (jprod! / jtprod! / hprod!) as programs of their own: jv has ONE output (the row's
+  // sum_c d1[c]*v[col_c]); jtv / hv have one output per touched index slot (jtv_slot / hv_slot name it)
+  Program jv, jtv, hv;
+  std::vector<int32_t> jtv_slot, hv_slot;
+  std::vector<uint8_t> x_slots_prod; // scratch of schedule()
 };
+
+// ---- matrix-free products as DAG outputs --------------------------------------------------------------
+// ExaModels reuses its reverse passes with an (out, v) pair in place of the value vector (SURVEY App. A.5:
+// Jv[row] += adj*v[col], Jtv[col] += adj*v[row], Hv[i] += h*v[j] (+ mirror)).  Here the products are built ONCE from
+// the symbolic first / second order slot values of the members of a Dag (a generator, or a fused group): no COO
+// values are materialised, and everything the slots share with each other (trig of the same state, common adjoints)
+// is shared by the product too.
+struct MemberSlots {
+  std::vector<int> s1, s2;                              // DAG ids of the first / second order slot values
+  std::vector<int32_t> jac_slot;                        // index slot per first-order slot
+  std::vector<std::pair<int32_t, int32_t>> hess_slot;   // index-slot pair per second-order slot
+  int wid = 0;                                          // member id of the root weight W (D_W)
+};
+struct ProductOuts {
+  std::vector<int> jv;                    // one node per member
+  std::vector<int> jtv, hv;               // one node per touched index slot, in order of first appearance
+  std::vector<int32_t> jtv_slot, hv_slot;
+};
+inline ProductOuts build_products(Dag &d, const std::vector<MemberSlots> &M, bool is_obj) {
+  ProductOuts P;
+  std::map<int32_t, int> jpos, hpos;
+  auto acc = [&](std::map<int32_t, int> &pos, std::vector<int> &outs, std::vector<int32_t> &slots, int32_t u, int term) {
+    auto it = pos.find(u);
+    if (it == pos.end()) { it = pos.emplace(u, (int)outs.size()).first; outs.push_back(d.cnst(0.0)); slots.push_back(u); }
+    outs[it->second] = d.add(outs[it->second], term);
+  };
+  for (const MemberSlots &m : M) {
+    if (!is_obj) {
+      int row = d.cnst(0.0);
+      for (size_t c = 0; c < m.s1.size(); ++c) row = d.add(row, d.mul(m.s1[c], d.loadv(m.jac_slot[c])));
+      P.jv.push_back(row);
+      // J'v: the weight leaf W of member wid is v[row] here (the kernel is handed v in place of y)
+      for (size_t c = 0; c < m.s1.size(); ++c) acc(jpos, P.jtv, P.jtv_slot, m.jac_slot[c], d.mul(m.s1[c], d.w(m.wid)));
+    }
+    // Hv: slot (u1, u2) with value h (root weight already inside) is the lower-triangle entry (max, min) of the
+    // symmetric matrix: Hv[u1] += h*v[u2], and the mirror Hv[u2] += h*v[u1] unless both land on the same variable
+    for (size_t c = 0; c < m.s2.size(); ++c) {
+      const int32_t u1 = m.hess_slot[c].first, u2 = m.hess_slot[c].second;
+      acc(hpos, P.hv, P.hv_slot, u1, d.mul(m.s2[c], d.loadv(u2)));
+      if (u1 != u2) acc(hpos, P.hv, P.hv_slot, u2, d.mul(d.mul(m.s2[c], d.selne(u1, u2)), d.loadv(u1)));
+    }
+  }
+  return P;
+}
 
 Program schedule(const Dag &dag, const std::vector<int> &outs, size_t n_islots, std::vector<uint8_t> &x_slots);
 
@@ -95,7 +144,18 @@ class GenCompiler {
     g.val = schedule(dag_, {val_[n_ - 1]}, ctx_.uidx.size(), g.x_slots_val);
     g.d1 = schedule(dag_, slot1_, ctx_.uidx.size(), g.x_slots_d1);
     g.d2 = schedule(dag_, slot2_, ctx_.uidx.size(), g.x_slots_d2);
+    MemberSlots ms;
+    ms.s1 = slot1_; ms.s2 = slot2_; ms.jac_slot = g.jac_slot; ms.hess_slot = g.hess_slot; ms.wid = wid_;
+    ProductOuts po = build_products(dag_, {ms}, is_obj_);
+    if (!is_obj_) {
+      g.jv = schedule(dag_, po.jv, ctx_.uidx.size(), g.x_slots_prod);
+      g.jtv = schedule(dag_, po.jtv, ctx_.uidx.size(), g.x_slots_prod);
+      g.jtv_slot = po.jtv_slot;
+    }
+    g.hv = schedule(dag_, po.hv, ctx_.uidx.size(), g.x_slots_prod);
+    g.hv_slot = po.hv_slot;
   }
+  bool is_obj_ = false; // objective generators have no rows: no jv / jtv programs
 
  private:
   void init(const iexa_node *nodes, const iexa_index *idx, int32_t n_idx) {

@@ -32,6 +32,7 @@ struct HostColumn {
   bool affine = false;
   int64_t aa = 0, ab = 0, ac = 1, ad = 0;
   std::vector<int32_t> ivals;   // int column (narrowed; x/theta indices fit in int32)
+  int32_t vmin = 0, vmax = 0;   // min / max of a stored int column (index-range queries over the whole column)
   std::vector<double> fvals;
   int64_t ival(int64_t j) const { return affine ? aa + ab * (j / ac) + ad * (j % ac) : (int64_t)ivals[j]; }
   // v(j) = a + b*(j/c) + d*(j%c) for some period c <= 8?
@@ -85,10 +86,16 @@ struct Group {
   int64_t k0 = 0, k1 = 0;
   std::vector<int32_t> members; // indices into Plan::objs or Plan::cons
   SlotCtx ctx;
-  Program prog[3];                                    // val, d1, d2 over all members
-  std::vector<std::pair<int32_t, int32_t>> outmap[3]; // program output j -> (member position, slot)
+  // val, d1, d2 over all members, then the matrix-free products jv (one output per member), jtv and hv (one output per
+  // touched index slot of the group: contributions of all members are summed in the program)
+  Program prog[6];
+  std::vector<std::pair<int32_t, int32_t>> outmap[6]; // program output j -> (member position, slot); jtv / hv: (0, index slot)
   std::vector<std::vector<int32_t>> jac_slot;         // per member: group index slot of each first-order slot
-  std::vector<uint8_t> x_slots[3];
+  std::vector<uint8_t> x_slots[6];
+  // scatter products (jtprod! / hprod!): phase of the group (0: launched first, may store single-writer outputs directly;
+  // 1: launched after phase 0, atomics only) and, per output, 1 = plain store — Plan::analyse_scatter
+  int scat_phase[2] = {1, 1};
+  std::vector<uint8_t> scat_direct[2];
   size_t dag_nodes = 0;
   // Shape class (build_groups(class_mode = true)): ONE member program shared by many generators of
   // identical shape — same tape structure, columns and index-term structure; they differ only in
@@ -158,6 +165,7 @@ struct Plan {
           if (v < INT32_MIN || v > INT32_MAX) throw std::invalid_argument("iterator: integer field exceeds int32");
           c.ivals[k] = (int32_t)v;
         }
+        if (K > 0) { c.vmin = *std::min_element(c.ivals.begin(), c.ivals.end()); c.vmax = *std::max_element(c.ivals.begin(), c.ivals.end()); }
       }
       it.int_cols.push_back(ColRef{(int32_t)columns.size(), 1, K > 0 ? K : 1});
       columns.push_back(std::move(c));
@@ -188,11 +196,12 @@ struct Plan {
   }
 
   Generator make_gen(const iexa_node *nodes, int32_t n, const iexa_index *idx, int32_t n_idx,
-                     int32_t itr) {
+                     int32_t itr, bool is_obj) {
     if (finalized) throw std::logic_error("plan already finalized");
     if (itr < 0 || itr >= (int32_t)itrs.size()) throw std::invalid_argument("bad iterator id");
     const Iterator &it = itrs[itr];
     GenCompiler gc(nodes, n, idx, n_idx, (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size());
+    gc.is_obj_ = is_obj;
     gc.compile();
     Generator g;
     g.itr = itr;
@@ -203,7 +212,7 @@ struct Plan {
 
   int64_t add_con(const iexa_node *nodes, int32_t n, const iexa_index *idx, int32_t n_idx,
                   int32_t itr, double lc, double uc) {
-    Generator g = make_gen(nodes, n, idx, n_idx, itr);
+    Generator g = make_gen(nodes, n, idx, n_idx, itr, false);
     g.is_obj = false; g.lcon = lc; g.ucon = uc;
     g.o0 = ncon;
     ncon += g.K;
@@ -212,7 +221,7 @@ struct Plan {
     return cons.back().o0;
   }
   void add_obj(const iexa_node *nodes, int32_t n, const iexa_index *idx, int32_t n_idx, int32_t itr) {
-    Generator g = make_gen(nodes, n, idx, n_idx, itr);
+    Generator g = make_gen(nodes, n, idx, n_idx, itr, true);
     g.is_obj = true;
     objs.push_back(std::move(g));
   }
@@ -237,11 +246,14 @@ struct Plan {
 
   void layout(int32_t rank_, int32_t world_) {
     if (world_ < 1 || rank_ < 0 || rank_ >= world_) throw std::invalid_argument("bad rank/world");
+    check_index_bounds();
     rank = rank_; world = world_;
     nnzj = nnzh = nnzg = 0;
     loc_ncon = loc_nnzj = loc_nnzh = 0;
     auto range = [&](Generator &g) {
-      // contiguous support blocks; length-1 generators live on rank 0
+      // contiguous support blocks; generators shorter than the world (length-1 generators: point constraints,
+      // non-measure objective terms) go one support per rank starting at rank 0
+      if (g.K < world) { g.k0 = std::min<int64_t>(rank, g.K); g.k1 = std::min<int64_t>(rank + 1, g.K); return; }
       g.k0 = (g.K * rank) / world;
       g.k1 = (g.K * (rank + 1)) / world;
     };
@@ -330,6 +342,11 @@ struct Plan {
           G.prog[0] = schedule(dag, o0, G.ctx.uidx.size(), G.x_slots[0]);
           G.prog[1] = schedule(dag, gc.slot1(), G.ctx.uidx.size(), G.x_slots[1]);
           G.prog[2] = schedule(dag, gc.slot2(), G.ctx.uidx.size(), G.x_slots[2]);
+          {
+            MemberSlots ms;
+            ms.s1 = gc.slot1(); ms.s2 = gc.slot2(); ms.jac_slot = gc.g.jac_slot; ms.hess_slot = gc.g.hess_slot; ms.wid = 0;
+            finish_products(G, dag, {ms});
+          }
           G.dag_nodes = dag.nodes.size();
           for (int32_t gi : inst) taken[gi] = 1;
         }
@@ -338,6 +355,7 @@ struct Plan {
       std::vector<std::unique_ptr<Dag>> dags;
       std::vector<std::vector<int>> outs[3];
       std::vector<int> slots1, slots2;
+      std::vector<std::vector<MemberSlots>> mslots; // per local dag: the members' slot nodes (for the product programs)
       std::vector<int> gid_of_local; // local dag index -> group index
       for (size_t gi = 0; gi < gens.size(); ++gi) {
         if (taken[gi]) continue;
@@ -359,6 +377,7 @@ struct Plan {
           dags.emplace_back(new Dag());
           for (auto &o : outs) o.emplace_back();
           slots1.push_back(0); slots2.push_back(0);
+          mslots.emplace_back();
           gid_of_local.push_back((int)groups.size() - 1);
           open[g.itr] = li;
         }
@@ -375,14 +394,33 @@ struct Plan {
         for (size_t c = 0; c < gc.slot2().size(); ++c) { outs[2][li].push_back(gc.slot2()[c]); G.outmap[2].push_back({mpos, (int32_t)c}); }
         slots1[li] += g.c.o1step > 1 ? (g.c.o1step | 1) : 0;
         slots2[li] += g.c.o2step > 1 ? (g.c.o2step | 1) : 0;
+        MemberSlots ms;
+        ms.s1 = gc.slot1(); ms.s2 = gc.slot2(); ms.jac_slot = gc.g.jac_slot; ms.hess_slot = gc.g.hess_slot; ms.wid = mpos;
+        mslots[li].push_back(std::move(ms));
       }
       for (size_t li = 0; li < dags.size(); ++li) {
         Group &G = groups[gid_of_local[li]];
         for (int p = 0; p < 3; ++p) G.prog[p] = schedule(*dags[li], outs[p][li], G.ctx.uidx.size(), G.x_slots[p]);
+        finish_products(G, *dags[li], mslots[li]);
         G.dag_nodes = dags[li]->nodes.size();
       }
     }
     class_mode_ = class_mode;
+    analyse_scatter();
+  }
+  // jv / jtv / hv programs of a group from its members' slot nodes (gen.hpp: build_products)
+  static void finish_products(Group &G, Dag &dag, const std::vector<MemberSlots> &M) {
+    ProductOuts po = build_products(dag, M, G.is_obj);
+    const size_t nis = G.ctx.uidx.size();
+    for (int p = 3; p < 6; ++p) { G.outmap[p].clear(); G.prog[p] = Program(); }
+    if (!G.is_obj) {
+      G.prog[3] = schedule(dag, po.jv, nis, G.x_slots[3]);
+      for (size_t m = 0; m < po.jv.size(); ++m) G.outmap[3].push_back({(int32_t)m, 0});
+      G.prog[4] = schedule(dag, po.jtv, nis, G.x_slots[4]);
+      for (int32_t u : po.jtv_slot) G.outmap[4].push_back({0, u});
+    }
+    G.prog[5] = schedule(dag, po.hv, nis, G.x_slots[5]);
+    for (int32_t u : po.hv_slot) G.outmap[5].push_back({0, u});
   }
   bool class_mode_ = false;
 
@@ -444,6 +482,162 @@ struct Plan {
       pos = std::max(pos, d.second);
     }
     if (pos < nvar) grad_zero_ranges.push_back({pos, nvar - pos});
+  }
+
+
+  // ---- index-expression queries (sharding, single-writer analysis, bounds checks) ------------------------
+  // conservative cover [lo, hi] (1-based, inclusive) of  base + sum coef*col(k)  over supports k in [k0, k1)
+  void index_range(const Iterator &it, const std::vector<int32_t> &int_cols, const IndexExpr &e, int64_t k0, int64_t k1,
+                   int64_t &lo, int64_t &hi) const {
+    lo = hi = e.base;
+    for (auto &t : e.terms) {
+      const ColRef &r = it.int_cols[int_cols[t.first]];
+      const HostColumn &c = columns[r.col];
+      // positions j = (k / div) % mod visited by k in [k0, k1)
+      int64_t q0 = k0 / r.div, q1 = (k1 - 1) / r.div, j0 = 0, j1 = r.mod - 1;
+      if (q1 - q0 + 1 < r.mod && q0 % r.mod <= q1 % r.mod) { j0 = q0 % r.mod; j1 = q1 % r.mod; }
+      int64_t vmin, vmax;
+      if (c.affine) {
+        const int64_t a0 = c.ab * (j0 / c.ac), a1 = c.ab * (j1 / c.ac), dm = c.ad * (c.ac - 1);
+        vmin = c.aa + std::min(a0, a1) + std::min<int64_t>(0, dm);
+        vmax = c.aa + std::max(a0, a1) + std::max<int64_t>(0, dm);
+      } else if (j0 == 0 && j1 == (int64_t)c.ivals.size() - 1) {
+        vmin = c.vmin; vmax = c.vmax;
+      } else {
+        vmin = vmax = c.ivals[j0];
+        for (int64_t j = j0; j <= j1; ++j) { vmin = std::min<int64_t>(vmin, c.ivals[j]); vmax = std::max<int64_t>(vmax, c.ivals[j]); }
+      }
+      lo += t.second >= 0 ? t.second * vmin : t.second * vmax;
+      hi += t.second >= 0 ? t.second * vmax : t.second * vmin;
+    }
+  }
+  // index(k) == c0 + s*k for EVERY k in [0, K) with s = +1 or -1?  True for an unrestricted support index
+  // (base + k + 1), for shifted ranges (2..T), and for the column-major index of a variable over a product iterator
+  // whose factors are all unrestricted (i_t + T*(i_xi - 1): the mixed-radix digits of k recombine to k itself).
+  bool linear_in_k(const Iterator &it, const std::vector<int32_t> &int_cols, int64_t K, const IndexExpr &e,
+                   int64_t &c0, int64_t &s) const {
+    if (e.terms.empty() || K <= 0) return false;
+    std::map<std::pair<int64_t, int64_t>, int64_t> w; // digit (div, mod) of k -> weight
+    c0 = e.base;
+    for (auto &t : e.terms) {
+      const ColRef &r = it.int_cols[int_cols[t.first]];
+      const HostColumn &c = columns[r.col];
+      if (!c.affine || c.ac != 1) return false;
+      c0 += t.second * c.aa;
+      if (r.mod > 1) w[{r.div, r.mod}] += t.second * c.ab;
+    }
+    int64_t expect_div = 1, last = 0;
+    s = 0;
+    for (auto &kv : w) { // ascending div
+      if (kv.first.first != expect_div) return false;
+      if (s == 0) { s = kv.second; if (s != 1 && s != -1) return false; }
+      if (kv.second != s * kv.first.first) return false;
+      expect_div = kv.first.first * kv.first.second;
+      last = expect_div;
+    }
+    return s != 0 && last >= K;
+  }
+
+  // every x / theta index a tape can produce must stay inside [1, nvar] / [1, npar]: the kernels address
+  // x[idx-1] / theta[idx-1] / out[idx-1] unchecked (a bad tape must be IEXA_ERR_INVALID, not an Xid)
+  void check_index_bounds() const {
+    auto check = [&](const Generator &g) {
+      if (g.K <= 0) return;
+      const Iterator &it = itrs[g.itr];
+      std::vector<int8_t> kind(g.c.uidx.size(), 0); // bit 0: VAR leaf, bit 1: PAR leaf
+      for (const iexa_node &n : g.c.tape) {
+        if (n.op == IEXA_OP_VAR) kind[g.c.idx_map[n.a]] |= 1;
+        else if (n.op == IEXA_OP_PAR) kind[g.c.idx_map[n.a]] |= 2;
+      }
+      for (size_t u = 0; u < kind.size(); ++u) {
+        for (int bit = 1; bit <= 2; bit <<= 1) {
+          if (!(kind[u] & bit)) continue;
+          const int64_t n = bit == 1 ? nvar : npar;
+          int64_t lo, hi;
+          index_range(it, g.c.int_cols, g.c.uidx[u], 0, g.K, lo, hi);
+          if (lo >= 1 && hi <= n) continue;
+          // the cover is conservative for correlated columns: decide exactly before rejecting
+          for (int64_t k = 0; k < g.K; ++k) {
+            const int64_t v = index_value(g, (int32_t)u, k);
+            if (v < 1 || v > n)
+              throw std::invalid_argument(std::string(bit == 1 ? "variable" : "parameter") + " index " + std::to_string(v) +
+                                          " out of range [1, " + std::to_string(n) + "] at support " + std::to_string(k + 1) +
+                                          " of " + (g.is_obj ? "an objective" : "a constraint") + " generator");
+          }
+        }
+      }
+    };
+    for (auto &g : objs) check(g);
+    for (auto &g : cons) check(g);
+  }
+
+  // ---- jtprod! / hprod!: two-phase scatter ----------------------------------------------------------------
+  // The scatter products add into a dense nvar-vector.  An output of a group whose index is  c0 ± k  walks a contiguous
+  // block exactly once (single writer INSIDE the group).  Groups are visited longest first; a group joins PHASE 0 when
+  // its single-writer blocks touch nothing an already accepted phase-0 group writes (directly or atomically) and its
+  // other outputs stay clear of every accepted block: its blocks are then plain stores that need no zero-fill.
+  // Everything else runs in PHASE 1 — a second launch, ordered after the first — with atomics (warp-reduced for shared
+  // variables).  Quadrotor jtprod!: the fused ODE rows (K = T) store all 22 variable blocks directly, the collocation /
+  // restriction / initial-condition rows add on top in phase 1, nothing is zero-filled.
+  std::vector<std::pair<int64_t, int64_t>> scat_zero_ranges[2]; // [jtprod, hprod]: 0-based (start, length) zeroed first
+  void analyse_scatter() {
+    const bool no_direct = getenv("IEXA_NO_SCATTER_DIRECT") != nullptr;
+    typedef std::pair<int64_t, int64_t> Iv; // [lo, hi] 1-based inclusive
+    auto overlaps = [](const std::vector<Iv> &v, const Iv &a) {
+      for (const Iv &b : v) if (a.first <= b.second && b.first <= a.second) return true;
+      return false;
+    };
+    for (int w = 0; w < 2; ++w) {
+      const int prog = 4 + w;
+      std::vector<int> order;
+      for (size_t gi = 0; gi < groups.size(); ++gi) {
+        Group &G = groups[gi];
+        G.scat_phase[w] = 1;
+        G.scat_direct[w].assign(G.outmap[prog].size(), 0);
+        if (G.prog[prog].nout > 0 && G.k1 > G.k0 && !G.is_class && !no_direct) order.push_back((int)gi);
+      }
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return groups[a].k1 - groups[a].k0 > groups[b].k1 - groups[b].k0; });
+      std::vector<Iv> direct, atomic;
+      for (int gi : order) {
+        Group &G = groups[gi];
+        const Iterator &it = itrs[G.itr];
+        std::vector<Iv> D, A;
+        std::vector<uint8_t> isd(G.outmap[prog].size(), 0);
+        for (size_t j = 0; j < G.outmap[prog].size(); ++j) {
+          const IndexExpr &e = G.ctx.uidx[G.outmap[prog][j].second];
+          int64_t c0, sgn, lo, hi;
+          if (linear_in_k(it, G.ctx.int_cols, G.K, e, c0, sgn)) {
+            const int64_t a = c0 + sgn * G.k0, b = c0 + sgn * (G.k1 - 1);
+            D.push_back({std::min(a, b), std::max(a, b)});
+            isd[j] = 1;
+          } else {
+            index_range(it, G.ctx.int_cols, e, G.k0, G.k1, lo, hi);
+            A.push_back({lo, hi});
+          }
+        }
+        if (D.empty()) continue;
+        bool ok = true;
+        for (size_t i = 0; i < D.size() && ok; ++i) {
+          if (D[i].first < 1 || D[i].second > nvar) ok = false;
+          for (size_t j = i + 1; j < D.size() && ok; ++j) if (D[i].first <= D[j].second && D[j].first <= D[i].second) ok = false;
+          if (ok && (overlaps(direct, D[i]) || overlaps(atomic, D[i]) || overlaps(A, D[i]))) ok = false;
+        }
+        for (size_t i = 0; i < A.size() && ok; ++i) if (overlaps(direct, A[i])) ok = false;
+        if (!ok) continue;
+        G.scat_phase[w] = 0;
+        G.scat_direct[w] = isd;
+        direct.insert(direct.end(), D.begin(), D.end());
+        atomic.insert(atomic.end(), A.begin(), A.end());
+      }
+      std::sort(direct.begin(), direct.end());
+      scat_zero_ranges[w].clear();
+      int64_t pos = 0; // 0-based
+      for (const Iv &d : direct) {
+        if (d.first - 1 > pos) scat_zero_ranges[w].push_back({pos, d.first - 1 - pos});
+        pos = std::max(pos, d.second);
+      }
+      if (pos < nvar) scat_zero_ranges[w].push_back({pos, nvar - pos});
+    }
   }
 
   const Generator &member(const Group &G, int mpos) const { return (G.is_obj ? objs : cons)[G.members[mpos]]; }

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 IEXA_MEM_HOST, IEXA_MEM_DEVICE, IEXA_MEM_HOST_SAME_X = 0, 1, 2
 IEXA_F_DEFAULT, IEXA_F_NO_SPECIALISE, IEXA_F_NO_DEVICE = 0, 1, 2
-CB_OBJ, CB_GRAD, CB_CONS, CB_JAC, CB_HESS = range(5)
+CB_OBJ, CB_GRAD, CB_CONS, CB_JAC, CB_HESS, CB_JPROD, CB_JTPROD, CB_HPROD = range(8)
 
 
 class IexaError(RuntimeError):
@@ -33,7 +33,7 @@ SYMBOLS = [
     "iexa_last_error", "iexa_version", "iexa_plan_create", "iexa_plan_destroy", "iexa_add_var",
     "iexa_add_par", "iexa_patch_var", "iexa_itr_base", "iexa_itr_product", "iexa_add_con",
     "iexa_add_obj", "iexa_finalize", "iexa_get_meta", "iexa_get_vector", "iexa_set_vector",
-    "iexa_set_par", "iexa_get_par", "iexa_jac_structure", "iexa_hess_structure", "iexa_obj",
+    "iexa_set_par", "iexa_set_par_stream", "iexa_get_par", "iexa_jac_structure", "iexa_hess_structure", "iexa_obj",
     "iexa_grad", "iexa_cons", "iexa_jac_coord", "iexa_hess_coord", "iexa_jprod", "iexa_jtprod",
     "iexa_hprod", "iexa_obj_device", "iexa_host_register", "iexa_host_unregister", "iexa_segments", "iexa_shared_vars", "iexa_x_ranges", "iexa_algorithmic_bytes",
     "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_set_class_mode", "iexa_debug_codegen_compile",
@@ -65,6 +65,7 @@ def _declare(L):
     sig("iexa_get_vector", _i32, _vp, _i32, _vp)
     sig("iexa_set_vector", _i32, _vp, _i32, _vp)
     sig("iexa_set_par", _i32, _vp, _i64, _i64, _vp)
+    sig("iexa_set_par_stream", _i32, _vp, _i64, _i64, _vp, _vp)
     sig("iexa_get_par", _i32, _vp, _i64, _i64, _vp)
     sig("iexa_jac_structure", _i32, _vp, _vp, _vp, _i32, _i32, _vp)
     sig("iexa_hess_structure", _i32, _vp, _vp, _vp, _i32, _i32, _vp)
@@ -101,6 +102,7 @@ def _declare(L):
     sig("hostcheck_eval_groups", _i32, _vp, _i32, _vp, _vp, _dbl, _vp, C.POINTER(_i32))
     sig("hostcheck_set_class_mode", _i32, _vp, _i32)
     sig("hostcheck_structure", _i32, _vp, _i32, _vp, _vp)
+    sig("hostcheck_prod", _i32, _vp, _i32, _i32, _vp, _vp, _vp, _dbl, _vp, _vp)
     sig("hostcheck_gen_stats", _i32, _vp, _i32, _i32, _vp)
     sig("hostcheck_grad_stats", _i32, _vp, _vp)
     return L

@@ -268,12 +268,13 @@ class BoundCall:
             _lib.check(self._m.L, rc)
 
 
-def bind(m: ExaModel, name: str, x, out, y=None, obj_weight: float = 1.0, new_x: bool = True) -> BoundCall:
+def bind(m: ExaModel, name: str, x, out, y=None, obj_weight: float = 1.0, new_x: bool = True, v=None) -> BoundCall:
     """``bind(m, "cons", x, c)``, ``bind(m, "jac_coord", x, vals)``, ``bind(m, "hess_coord", x, vals, y, σ)``,
-    ``bind(m, "grad", x, g)``.  ``new_x=False`` (host buffers only) is Ipopt's ``new_x`` flag: x is the x of the
-    previous host call on this model, so the engine reuses its device copy (IEXA_MEM_HOST_SAME_X)."""
-    bx, bo, by = m._buf(x, m.meta.nvar), m._buf(out), m._buf(y)
-    ms, st = m._pair(bx, bo, by) if y is not None else m._pair(bx, bo)
+    ``bind(m, "grad", x, g)``, ``bind(m, "jprod", x, Jv, v=v)``, ``bind(m, "jtprod", x, Jtv, v=w)``,
+    ``bind(m, "hprod", x, Hv, y, σ, v=v)``.  ``new_x=False`` (host buffers only) is Ipopt's ``new_x`` flag: x is the x
+    of the previous host call on this model, so the engine reuses its device copy (IEXA_MEM_HOST_SAME_X)."""
+    bx, bo, by, bv = m._buf(x, m.meta.nvar), m._buf(out), m._buf(y), m._buf(v)
+    ms, st = m._pair(*[b for b in (bx, bo, by, bv) if b[0] is not None])
     if not new_x and ms == _lib.IEXA_MEM_HOST:
         ms = _lib.IEXA_MEM_HOST_SAME_X
     h = m.h
@@ -287,4 +288,10 @@ def bind(m: ExaModel, name: str, x, out, y=None, obj_weight: float = 1.0, new_x:
         return BoundCall(m, L.iexa_grad, (h, vp(bx[0]), vp(bo[0]), ms, vp(st)), (x, out))
     if name == "hess_coord":
         return BoundCall(m, L.iexa_hess_coord, (h, vp(bx[0]), vp(by[0]), C.c_double(obj_weight), vp(bo[0]), ms, vp(st)), (x, out, y))
+    if name == "jprod":
+        return BoundCall(m, L.iexa_jprod, (h, vp(bx[0]), vp(bv[0]), vp(bo[0]), ms, vp(st)), (x, out, v))
+    if name == "jtprod":
+        return BoundCall(m, L.iexa_jtprod, (h, vp(bx[0]), vp(bv[0]), vp(bo[0]), ms, vp(st)), (x, out, v))
+    if name == "hprod":
+        return BoundCall(m, L.iexa_hprod, (h, vp(bx[0]), vp(by[0]), vp(bv[0]), C.c_double(obj_weight), vp(bo[0]), ms, vp(st)), (x, out, y, v))
     raise ValueError(name)

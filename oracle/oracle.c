@@ -553,14 +553,18 @@ void orc_jprod(const omodel *m, const double *x, const double *v, double *jv) {
   const ogen *g;
   for (int64_t i = 0; i < m->ncon; ++i) jv[i] = 0;
   FOR_GEN(m, g, 0) {
-    anode *t = (anode *)malloc(sizeof(anode) * (size_t)g->n);
-    for (int64_t k = 0; k < g->K; ++k) {
-      forward(m, g, k, x, t, 0);
-      fctx c = {g, t, k, 0, 0, 0, 0, v, 0, 0, 0, 0, 0, 0, 3};
-      jrpass(&c, g->n - 1, 1.0);
-      jv[g->o0 + k] += c.acc;
+#pragma omp parallel
+    {
+      anode *t = (anode *)malloc(sizeof(anode) * (size_t)g->n);
+#pragma omp for
+      for (int64_t k = 0; k < g->K; ++k) { /* rows are independent: the sum of one row stays sequential */
+        forward(m, g, k, x, t, 0);
+        fctx c = {g, t, k, 0, 0, 0, 0, v, 0, 0, 0, 0, 0, 0, 3};
+        jrpass(&c, g->n - 1, 1.0);
+        jv[g->o0 + k] += c.acc;
+      }
+      free(t);
     }
-    free(t);
   }
 }
 

@@ -19,15 +19,17 @@ Engine *make_cuda_engine(Plan &, int, uint32_t, std::string &err) {
 }
 
 static void run_program(const Plan &P, const Generator &g, const Program &pr, int64_t k, const double *x,
-                        double W, std::vector<double> &r, double *out) {
+                        double W, std::vector<double> &r, double *out, const double *v = nullptr) {
   r.resize(pr.nreg > 0 ? pr.nreg : 1);
   for (const Instr &I : pr.code) {
     switch (I.op) {
       case D_FIELD: r[I.dst] = P.fp_col_value(g, I.a, k); break;
       case D_LOADX: r[I.dst] = x[P.index_value(g, I.a, k) - 1]; break;
       case D_LOADP: r[I.dst] = P.theta[P.index_value(g, I.a, k) - 1]; break;
+      case D_LOADV: r[I.dst] = v[P.index_value(g, I.a, k) - 1]; break;
       case D_W: r[I.dst] = W; break;
       case D_SEL2: r[I.dst] = P.index_value(g, I.a, k) == P.index_value(g, I.b, k) ? 2.0 : 1.0; break;
+      case D_SELNE: r[I.dst] = P.index_value(g, I.a, k) != P.index_value(g, I.b, k) ? 1.0 : 0.0; break;
       case D_OUT: out[I.dst] = I.a >= 0 ? r[I.a] : pr.cpool[~I.a]; break;
       default: {
         double a = I.a >= 0 ? r[I.a] : pr.cpool[~I.a];
@@ -52,13 +54,15 @@ static int64_t g_index(const Plan &P, const Group &G, int32_t islot, int64_t k, 
   return v;
 }
 static void run_group(const Plan &P, const Group &G, const Program &pr, int64_t k, const double *x, const double *y,
-                      double sigma, std::vector<double> &r, double *out, const Generator *inst = nullptr) {
+                      double sigma, std::vector<double> &r, double *out, const Generator *inst = nullptr, const double *v = nullptr) {
   r.resize(pr.nreg > 0 ? pr.nreg : 1);
   for (const Instr &I : pr.code) {
     switch (I.op) {
       case D_FIELD: { const ColRef &c = P.itrs[G.itr].fp_cols[G.ctx.fp_cols[I.a]]; r[I.dst] = P.columns[c.col].fvals[(k / c.div) % c.mod]; break; }
       case D_LOADX: r[I.dst] = x[g_index(P, G, I.a, k, inst) - 1]; break;
       case D_LOADP: r[I.dst] = P.theta[g_index(P, G, I.a, k, inst) - 1]; break;
+      case D_LOADV: r[I.dst] = v[g_index(P, G, I.a, k, inst) - 1]; break;
+      case D_SELNE: r[I.dst] = g_index(P, G, I.a, k, inst) != g_index(P, G, I.b, k, inst) ? 1.0 : 0.0; break;
       case D_W: r[I.dst] = G.is_obj ? sigma : (y ? y[(inst ? *inst : P.member(G, I.a)).o0 + k] : 0.0); break;
       case D_SEL2: r[I.dst] = g_index(P, G, I.a, k, inst) == g_index(P, G, I.b, k, inst) ? 2.0 : 1.0; break;
       case D_CPAR: r[I.dst] = inst->c.tape[G.cpar_nodes[I.a]].c; break;
@@ -173,6 +177,69 @@ int32_t hostcheck_eval_groups(iexa_plan *p, int32_t which, const double *x, cons
       }
     }
   }
+  return IEXA_OK;
+}
+
+// matrix-free products through the per-generator programs (use_groups == 0) or the fused group programs.
+// which: 5 jprod (out: ncon), 6 jtprod (v: ncon rows, out: nvar), 7 hprod (out: nvar).  GLOBAL layout.
+// phase_stats (optional, 4 int64): groups in phase 0 / direct outputs / zero-filled entries / groups with work
+int32_t hostcheck_prod(iexa_plan *p, int32_t which, int32_t use_groups, const double *x, const double *y, const double *v,
+                       double sigma, double *out, int64_t *phase_stats) {
+  if (!p || !p->plan.finalized || which < 5 || which > 7) return IEXA_ERR_STATE;
+  const Plan &P = p->plan;
+  std::vector<double> r, tmp;
+  const int64_t no = which == 5 ? P.ncon : P.nvar;
+  const double NaN = std::nan("");
+  // emulate the device protocol: out starts as garbage; zero ranges are zeroed; phase-0 direct outputs STORE
+  for (int64_t i = 0; i < no; ++i) out[i] = use_groups && which != 5 ? NaN : 0.0;
+  if (!use_groups) {
+    auto each = [&](const Generator &g) {
+      const Program &pr = which == 5 ? g.c.jv : which == 6 ? g.c.jtv : g.c.hv;
+      if (g.is_obj && which != 7) return;
+      tmp.assign(pr.nout > 0 ? pr.nout : 1, 0.0);
+      for (int64_t k = 0; k < g.K; ++k) {
+        // J'v: the root weight is v[row]
+        double W = which == 6 ? v[g.o0 + k] : (g.is_obj ? sigma : (y ? y[g.o0 + k] : 0.0));
+        run_program(P, g, pr, k, x, W, r, tmp.data(), v);
+        if (which == 5) out[g.o0 + k] = tmp[0];
+        else {
+          const std::vector<int32_t> &sl = which == 6 ? g.c.jtv_slot : g.c.hv_slot;
+          for (int j = 0; j < pr.nout; ++j) out[P.index_value(g, sl[j], k) - 1] += tmp[j];
+        }
+      }
+    };
+    for (auto &g : P.objs) each(g);
+    for (auto &g : P.cons) each(g);
+    return IEXA_OK;
+  }
+  const int prog = which - 2, w = which - 6;
+  int64_t st[4] = {0, 0, 0, 0};
+  if (which != 5) for (auto &z : P.scat_zero_ranges[w]) { for (int64_t i = 0; i < z.second; ++i) out[z.first + i] = 0.0; st[2] += z.second; }
+  for (int phase = 0; phase < 2; ++phase)
+  for (const Group &G : P.groups) {
+    if (G.is_obj && which != 7) continue;
+    const Program &pr = G.prog[prog];
+    if (which != 5 && (pr.nout == 0 || G.scat_phase[w] != phase)) continue;
+    if (which == 5 && phase == 1) continue;
+    if (which != 5) { st[3]++; if (phase == 0) st[0]++; }
+    tmp.assign(pr.nout > 0 ? pr.nout : 1, 0.0);
+    const std::vector<Generator> &gens = G.is_obj ? P.objs : P.cons;
+    const size_t ninst = G.is_class ? G.inst_gens.size() : 1;
+    // J'v: D_W(member) reads v[row of member] — hand v in as y
+    const double *wy = which == 6 ? v : y;
+    for (size_t ii = 0; ii < ninst; ++ii)
+    for (int64_t k = 0; k < G.K; ++k) {
+      const Generator *inst = G.is_class ? &gens[G.inst_gens[ii]] : nullptr;
+      run_group(P, G, pr, k, x, wy, sigma, r, tmp.data(), inst, v);
+      for (size_t j = 0; j < G.outmap[prog].size(); ++j) {
+        if (which == 5) { const Generator &g = inst ? *inst : P.member(G, G.outmap[prog][j].first); out[g.o0 + k] = tmp[j]; continue; }
+        const int64_t i = g_index(P, G, G.outmap[prog][j].second, k, inst) - 1;
+        const bool direct = phase == 0 && G.scat_direct[w][j];
+        if (direct) { out[i] = tmp[j]; if (ii == 0 && k == 0) st[1]++; } else out[i] += tmp[j];
+      }
+    }
+  }
+  if (phase_stats) for (int i = 0; i < 4; ++i) phase_stats[i] = st[i];
   return IEXA_OK;
 }
 

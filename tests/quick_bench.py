@@ -66,6 +66,17 @@ for nm, fn, w in (("cons", bind(m, "cons", x, c), 2), ("jac", bind(m, "jac_coord
     if w >= 2:
         tot += ms
     print(f"{nm}: {ms:.4f} ms  {B[w]/ms/1e6:.1f} GB/s  frac_of_6552={B[w]/ms/1e6/6552:.3f}")
+if os.environ.get("IEXA_PROD", "1") != "0":  # matrix-free products (fused kernels, second NVRTC module compiled on first use)
+    v = torch.from_numpy(rng.uniform(-1, 1, core.nvar)).cuda()
+    w = torch.from_numpy(rng.uniform(-1, 1, max(core.ncon, 1))).cuda()
+    Jv = torch.zeros(max(m.meta.ncon, 1), dtype=torch.float64, device="cuda")
+    Jtw = torch.zeros(m.meta.nvar, dtype=torch.float64, device="cuda"); Hv = torch.zeros_like(Jtw)
+    tp = time.time(); ex.jprod_(m, x, v, Jv); torch.cuda.synchronize(); print(f"product module build {time.time()-tp:.2f}s note={m.L.iexa_engine_note(m.h).decode()[:80]!r}")
+    Bp = [ex.algorithmic_bytes(m, w_) for w_ in (5, 6, 7)]
+    for nm, fn, b in (("jprod", bind(m, "jprod", x, Jv, v=v), Bp[0]), ("jtprod", bind(m, "jtprod", x, Jtw, v=w), Bp[1]),
+                      ("hprod", bind(m, "hprod", x, Hv, y, 1.0, v=v), Bp[2])):
+        ms = timeit(fn)
+        print(f"{nm}: {ms:.4f} ms  {b/ms/1e6:.1f} GB/s  frac_of_6552={b/ms/1e6/6552:.3f}  bytes={b}  launches={ex.launches_per_call(m, {'jprod': 5, 'jtprod': 6, 'hprod': 7}[nm])}")
 if os.environ.get("IEXA_GRAPH"):  # the three callbacks captured into one CUDA graph and replayed
     st = torch.cuda.Stream()
     with torch.cuda.stream(st):

@@ -98,6 +98,19 @@ def test_config3_quadrotor_1e6_supports_parity_structure_and_properties():
     fdh = (grad_lag(xd + eps * vd) - grad_lag(xd - eps * vd)) / (2 * eps)
     errh = (fdh - Hv).abs().max().item()
     assert errh <= 1e-6 * max(1.0, Hv.abs().max().item()), f"H v vs central differences: {errh:.3e}"
+    # the fused product kernels against the oracle's (out, v) reverse passes at the FULL size, north-star tolerance;
+    # jprod! (no atomics) is bit-reproducible run to run
+    assert_close(Jv.cpu().numpy(), om.jprod(x, v), "jprod")
+    Jv2 = torch.full_like(Jv, 3.0)
+    ex.jprod_(m, xd, vd, Jv2)
+    assert torch.equal(Jv, Jv2), "jprod! is not bit-reproducible"
+    del Jv2, cp, cm, fd, fdh
+    assert_close(Hv.cpu().numpy(), om.hprod(x, y, v, 0.7), "hprod")
+    w = rng.uniform(-1, 1, om.ncon)
+    Jtw = torch.full((om.nvar,), 7.0, dtype=torch.float64, device="cuda")
+    ex.jtprod_(m, xd, _dev(w), Jtw)
+    assert_close(Jtw.cpu().numpy(), om.jtprod(x, w), "jtprod")
+    assert m.L.iexa_engine_note(m.h) == b""
 
 
 def test_config3_world2_sharding_tiles_the_full_model_bit_for_bit():

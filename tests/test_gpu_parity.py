@@ -78,14 +78,20 @@ def test_callbacks_device_buffers(name, mode, oracle_cache):
     rng = np.random.default_rng(5)
     v = rng.uniform(-1, 1, om.nvar); w = rng.uniform(-1, 1, om.ncon)
     vd, wd = torch.from_numpy(v).to(dev), torch.from_numpy(w).to(dev)
-    out = torch.zeros(max(om.ncon, 1), dtype=torch.float64, device=dev)
-    ref = om.jprod(x, v)
+    # (fused product kernels: outputs start as garbage — every entry must be (re)written, the bar is that of the values)
+    out = torch.full((max(om.ncon, 1),), 7.0, dtype=torch.float64, device=dev)
     got = ex.jprod_(m, xd, vd, out).cpu().numpy()[: om.ncon]
-    assert np.allclose(got, ref, rtol=1e-11, atol=1e-12)
-    out = torch.zeros(om.nvar, dtype=torch.float64, device=dev)
-    assert np.allclose(ex.jtprod_(m, xd, wd, out).cpu().numpy(), om.jtprod(x, w), rtol=1e-11, atol=1e-12)
-    out = torch.zeros(om.nvar, dtype=torch.float64, device=dev)
-    assert np.allclose(ex.hprod_(m, xd, yd, vd, out, obj_weight=0.7).cpu().numpy(), om.hprod(x, y, v, 0.7), rtol=1e-11, atol=1e-12)
+    assert_close(got, om.jprod(x, v), "jprod")
+    out2 = torch.full((max(om.ncon, 1),), -3.0, dtype=torch.float64, device=dev)
+    assert (ex.jprod_(m, xd, vd, out2).cpu().numpy()[: om.ncon] == got).all(), "jprod! must be bit-reproducible"
+    out = torch.full((om.nvar,), 7.0, dtype=torch.float64, device=dev)
+    assert_close(ex.jtprod_(m, xd, wd, out).cpu().numpy(), om.jtprod(x, w), "jtprod")
+    out = torch.full((om.nvar,), 7.0, dtype=torch.float64, device=dev)
+    assert_close(ex.hprod_(m, xd, yd, vd, out, obj_weight=0.7).cpu().numpy(), om.hprod(x, y, v, 0.7), "hprod")
+    out = torch.full((om.nvar,), 7.0, dtype=torch.float64, device=dev)
+    assert_close(ex.hprod_(m, xd, None, vd, out, obj_weight=1.3).cpu().numpy(), om.hprod(x, None, v, 1.3), "hprod (objective only)")
+    if mode == "nvrtc":
+        assert m.L.iexa_engine_note(m.h) == b"", m.L.iexa_engine_note(m.h)
 
 
 @pytest.mark.parametrize("name", ["ode_5x5", "quadrotor_fd_100", "pandemic_50x4"])
