@@ -8,14 +8,22 @@ roofline target is quoted on; it fits one B200).  With --gpus N the SAME model i
 contiguous support blocks over N ranks (strong scaling, no data-path collective: every rank owns
 its rows / Jacobian slots / Hessian slots).
 
-`--workload pandemic` runs the same contract on BASELINE.json configs[1] (ESCAPE34/pandemic.jl, 10^5 time supports x 4
-scenarios; small: a few waves of blocks per kernel).  Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference's
-evaluator (oracle/, all host threads) on a bounded sample of the same workload — ExaModels.jl
-itself cannot be installed here (no Julia, no network).
+The ONE JSON line (rank 0) also carries, next to the headline:
+  * ``products``   — per-call ms and roofline of the fused jprod! / jtprod! / hprod! kernels;
+  * ``iteration``  — obj + grad! + cons! + jac_coord! + hess_coord! + 2 x COO->CSR, device-resident; for N > 1 with the
+                     x halo exchange and the NCCL all-reduces (objective, shared gradient slice) INSIDE the timed step
+                     (the analogue of the reference's ``ad_time``, ESCAPE34/utils.jl:7,23);
+  * ``workloads``  — BASELINE configs 2 / 4 / 5 at their named sizes (pandemic 10^5 x 4 and 100 x 128, OPF case3 x 10^5 and
+                     118-bus x 10^4, farmer 10^5): per-callback ms, algorithmic bytes, roofline fraction, and a parity
+                     flag computed in this run against the oracle; with --gpus N the same block for the sharded models.
+
+`--impl reference` times the CPU restatement of the reference's evaluator (oracle/, all host threads) on the FULL named
+configuration — ExaModels.jl itself cannot be installed here (no Julia, no network).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -28,17 +36,40 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # BASELINE.json configs[2]: the configuration the north-star evals/s / roofline / 8-GPU targets are quoted on (default)
-    "quadrotor": dict(name="ESCAPE34/quadrotor.jl OC(3), 10^6 time supports: cons!+jac_coord!+hess_coord!", supports=1_000_000,
-                      cpu_sample=20_000, build=lambda n: __import__("iexa_b200").models.quadrotor(n, "oc")),
-    # BASELINE.json configs[1]: SEIR optimal control, 10^5 time supports x 4 scenarios (small: a few waves per kernel)
-    "pandemic": dict(name="ESCAPE34/pandemic.jl, 10^5 time supports x 4 scenarios: cons!+jac_coord!+hess_coord!", supports=100_000,
-                     cpu_sample=20_000, build=lambda n: __import__("iexa_b200").models.pandemic(n, 4)),
-}
-WORKLOAD = WORKLOADS["quadrotor"]["name"]
 METRIC = "cons+jac+hess evals/s"
 UNIT = "evals/s"
+RTOL, ATOL = 1e-12, 1e-14          # north-star tolerance (BASELINE.json)
+
+
+def _models():
+    from iexa_b200 import models
+    return models
+
+
+def _opf(nbus, K):
+    from iexa_b200 import opf
+    from iexa_b200.transform import exa_core
+    return exa_core(opf.opf(None if nbus == 3 else opf.synthetic_grid(nbus), num_supports=K))[0]
+
+
+HEADLINES = {
+    # BASELINE.json configs[2]: the configuration the north-star evals/s / roofline / 8-GPU targets are quoted on (default)
+    "quadrotor": dict(name="ESCAPE34/quadrotor.jl OC(3), 10^6 time supports: cons!+jac_coord!+hess_coord!", supports=1_000_000,
+                      build=lambda n: _models().quadrotor(n, "oc")),
+    # BASELINE.json configs[1]: SEIR optimal control, 10^5 time supports x 4 scenarios (small: a few waves per kernel)
+    "pandemic": dict(name="ESCAPE34/pandemic.jl, 10^5 time supports x 4 scenarios: cons!+jac_coord!+hess_coord!", supports=100_000,
+                     build=lambda n: _models().pandemic(n, 4)),
+}
+# the other BASELINE configurations at their named sizes: the `workloads` block of the JSON line
+WORKLOADS = {
+    "pandemic_1e5x4": dict(config="configs[1] ESCAPE34/pandemic.jl:4-34, 10^5 time supports x 4 scenarios", build=lambda: _models().pandemic(100_000, 4)),
+    "pandemic_100x128": dict(config="configs[1] ESCAPE34/pandemic.jl at the largest case of the reference's study grid (run_cases_gpu.jl:100): 100 time supports x 128 scenarios",
+                             build=lambda: _models().pandemic(100, 128)),
+    "opf_case3_1e5": dict(config="configs[3] ESCAPE34/opf.jl:36-286, embedded 3-bus case x 10^5 scenarios", build=lambda: _opf(3, 100_000)),
+    "opf_118bus_1e4": dict(config="configs[3] ESCAPE34/opf.jl:36-286, synthetic 118-bus grid (2832 generators -> shape-class kernels) x 10^4 scenarios",
+                           build=lambda: _opf(118, 10_000)),
+    "farmer_1e5": dict(config="configs[4] examples/2stage_example.jl:20-37, 10^5 scenarios (LP: empty Hessian)", build=lambda: _models().farmer(100_000)),
+}
 
 
 def parse():
@@ -47,18 +78,40 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="quadrotor", choices=sorted(WORKLOADS), help="BASELINE.json configuration (default: configs[2])")
+    ap.add_argument("--workload", default="quadrotor", choices=sorted(HEADLINES), help="headline configuration (default: BASELINE configs[2])")
     ap.add_argument("--supports", type=int, default=None, help="public time supports (default: the named size of the workload)")
-    ap.add_argument("--cpu-sample", type=int, default=None, help="supports of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the `workloads` block (configs 2 / 4 / 5)")
+    ap.add_argument("--no-iteration", action="store_true")
+    ap.add_argument("--no-products", action="store_true")
+    ap.add_argument("--only-workloads", default=None, help="comma-separated subset of the workloads block")
     ap.add_argument("--interp", action="store_true", help="AOT tape-interpreter kernels only (no NVRTC)")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = HEADLINES[args.workload]
     args.supports = w["supports"] if args.supports is None else args.supports
-    args.cpu_sample = w["cpu_sample"] if args.cpu_sample is None else args.cpu_sample
     args.build, args.workload_name = w["build"], w["name"]
     return args
+
+
+def host_threads() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def eval_point(core, seed=0):
+    """x = x0 + 0.1 U(-1,1), y ~ U(-1,1)  """
+    rng = np.random.default_rng(seed)
+    x = np.where(np.isfinite(core.x0_vec), core.x0_vec, 0.0) + 0.1 * rng.uniform(-1, 1, core.nvar)
+    y = rng.uniform(-1, 1, core.ncon)
+    return x, y
+
+
+def workload_config(name, supports, nvar, ncon, nnzj, nnzh):
+    """identical in the b200 arm and the reference arm: what is computed, not how"""
+    out_gb = 8 * (ncon + nnzj + nnzh) / 1e9
+    return {"workload": name, "supports": int(supports), "nvar": int(nvar), "ncon": int(ncon), "nnzj": int(nnzj), "nnzh": int(nnzh),
+            "l2": "inputs larger than L2 (x = %.0f MB, outputs %.1f GB per eval): no flush between iterations" % (nvar * 8 / 1e6, out_gb)
+                  if 8 * nvar > 126e6 else "working set near the 126 MB L2: a 512 MB buffer is rewritten between timed iterations (L2 flush)"}
 
 
 class ClockSampler:
@@ -111,66 +164,232 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_eval_rate(build, full_rows: int, sample_supports: int, threads: int, reps: int = 2):
-    """evals/s of the oracle (CPU restatement of the reference evaluator) on a bounded sample,
-    scaled linearly to the full support count."""
-    import iexa_b200 as ex  # noqa: F401  (models only; the oracle does the arithmetic)
-    from iexa_b200 import models
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C restatement of the reference's evaluator) on the FULL configuration
+# ---------------------------------------------------------------------------------------------------------
+def oracle_eval_seconds(om, x, y, threads, reps, warm=1):
     from oracle import oracle as orc
-    from oracle.oracle import OracleModel
     orc.set_threads(threads)
-    core = build(sample_supports)
-    om = OracleModel(core)
-    rng = np.random.default_rng(0)
-    x = np.where(np.isfinite(core.x0_vec), core.x0_vec, 0.0) + 0.1 * rng.uniform(-1, 1, core.nvar)
-    y = rng.uniform(-1, 1, core.ncon)
-    om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)  # warm-up
+    for _ in range(warm):
+        om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
         om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)
         ts.append(time.perf_counter() - t0)
-    t = min(ts)
-    scale = full_rows / core.ncon          # rows (and slots) are proportional to the number of supports
-    return 1.0 / (t * scale), t
+    return ts
 
 
 def run_reference(args):
+    """the reference arm: EVERY step is one full-size eval (cons + jac_coord + hess_coord at the named 10^6 supports) of the
+    oracle with all host threads; nothing is sampled or scaled"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    # each "step" is one eval of the bounded sample; K steps after W warm-ups
-    from iexa_b200 import models
     from oracle import oracle as orc
     from oracle.oracle import OracleModel
+    threads = host_threads()
     orc.set_threads(threads)
-    ns = args.cpu_sample
-    core = args.build(ns)
+    core = args.build(args.supports)
     om = OracleModel(core)
-    rng = np.random.default_rng(0)
-    x = np.where(np.isfinite(core.x0_vec), core.x0_vec, 0.0) + 0.1 * rng.uniform(-1, 1, core.nvar)
-    y = rng.uniform(-1, 1, core.ncon)
+    x, y = eval_point(core)
     for _ in range(args.warmup):
         om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         om.cons(x); om.jac_coord(x); om.hess_coord(x, y, 1.0)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    full = args.build(args.supports) if args.supports <= 200_000 else None
-    scale = (full.ncon / core.ncon) if full is not None else (2 * args.supports - 1) / (2 * ns - 1)   # quadrotor: T = 2N - 1 supports
-    v = 1.0 / (dt * scale)
-    sample = (f"oracle (C restatement of ExaModels' per-support recursive AD, OpenMP over supports) on "
-              f"{ns} of {args.supports} public supports, time scaled linearly by {scale:.1f}")
+    v = 1.0 / dt
+    sample = (f"oracle (C restatement of ExaModels' per-support recursive AD, OpenMP over supports, {threads} threads) on the FULL "
+              f"configuration: every step evaluates all {args.supports} public supports, no sampling, no scaling")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload_name, "supports": args.supports},
+        "config": workload_config(args.workload_name, args.supports, core.nvar, om.ncon, om.nnzj, om.nnzh),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "ExaModels.jl (the reference's evaluator) is not installable offline: no Julia, no network",
+        "note": "ExaModels.jl (the reference's evaluator) is not installable offline: no Julia, no network; the port is a tree-walking "
+                "restatement, not Julia-compiled code",
     }))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# helpers of the GPU arm
+# ---------------------------------------------------------------------------------------------------------
+class Ctx:
+    """torch / distributed plumbing of one rank"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self._flush = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor(np.atleast_1d(np.asarray(v, dtype=np.float64)), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    def sum_over_ranks(self, v):
+        t = self.torch.tensor(np.atleast_1d(np.asarray(v, dtype=np.float64)), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def flush_l2(self):
+        """rewrite a buffer larger than the 126 MB L2"""
+        if self._flush is None:
+            self._flush = self.torch.empty(512 * 1024 * 1024 // 8, dtype=self.torch.float64, device=self.dev)
+        self._flush.fill_(1.0)
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+
+def local_slices(ex, m, which):
+    n = m.L.iexa_segments(m.h, which, None, 0)
+    segs = (ex.lib.Segment * max(n, 1))()
+    m.L.iexa_segments(m.h, which, segs, n)
+    return [(s.global_start, s.local_start, s.length) for s in segs[:n]]
+
+
+def to_local(ex, m, which, glob, n_local):
+    out = np.zeros(max(n_local, 1))
+    for gs, ls, ln in local_slices(ex, m, which):
+        out[ls:ls + ln] = glob[gs:gs + ln]
+    return out
+
+
+def close(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return bool(np.all((np.abs(a - b) <= ATOL + RTOL * np.maximum(np.abs(a), np.abs(b))) | (np.isnan(a) & np.isnan(b))))
+
+
+def parity_vs_oracle(ctx, ex, m, core, x_h, y_full, bufs):
+    """every rank checks ITS slices of c / Jacobian / Hessian values against the oracle's global vectors (computed by rank 0
+    with all host threads and broadcast); returns the flags AND-ed over the ranks"""
+    torch, dist = ctx.torch, ctx.dist
+    from oracle.oracle import OracleModel
+    refs = None
+    if ctx.rank == 0:
+        from oracle import oracle as orc
+        orc.set_threads(host_threads())
+        om = OracleModel(core)
+        refs = [om.cons(x_h), om.jac_coord(x_h), om.hess_coord(x_h, y_full, 1.0)]
+        dims_ok = (om.ncon, om.nnzj, om.nnzh) == (m.meta.ncon, m.meta.nnzj, m.meta.nnzh)
+    if ctx.world > 1:
+        sizes = [m.meta.ncon, m.meta.nnzj, m.meta.nnzh]
+        got = []
+        for i, n in enumerate(sizes):
+            t = torch.from_numpy(refs[i]).to(ctx.dev) if ctx.rank == 0 else torch.empty(max(n, 0), dtype=torch.float64, device=ctx.dev)
+            if n:
+                dist.broadcast(t, src=0)
+            got.append(t.cpu().numpy())
+            del t
+        refs = got
+        dims_ok = True
+    flags = {}
+    for name, which, buf, nloc in (("cons", 0, bufs[0], m.loc_ncon), ("jac_coord", 1, bufs[1], m.loc_nnzj), ("hess_coord", 2, bufs[2], m.loc_nnzh)):
+        loc = buf.cpu().numpy()[:nloc]
+        ref = to_local(ex, m, which, refs[which], nloc)[:nloc]
+        flags[name] = close(loc, ref)
+    flags["dims"] = bool(dims_ok)
+    ok = np.array([float(all(flags.values()))] + [float(flags[k]) for k in ("cons", "jac_coord", "hess_coord", "dims")])
+    if ctx.world > 1:
+        t = torch.tensor(ok, dtype=torch.float64, device=ctx.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = t.cpu().numpy()
+    return {"all": bool(ok[0]), "cons": bool(ok[1]), "jac_coord": bool(ok[2]), "hess_coord": bool(ok[3]), "dims": bool(ok[4]),
+            "tolerance": f"|a-b| <= {ATOL:g} + {RTOL:g}*max(|a|,|b|) vs the oracle on the same x, y (sigma = 1), every local slot of every rank"}
+
+
+def per_callback_ms(ctx, calls, reps, flush):
+    """mean duration of every call in `calls` (CUDA events on the launching stream around each launch), max over ranks"""
+    torch = ctx.torch
+    for _ in range(3):
+        for f in calls:
+            f()
+    ctx.barrier()
+    acc = np.zeros(len(calls))
+    for _ in range(reps):
+        for j, f in enumerate(calls):
+            if flush:
+                ctx.flush_l2()
+            a, b = ctx.ev(), ctx.ev()
+            a.record(); f(); b.record()
+            b.synchronize()
+            acc[j] += a.elapsed_time(b)
+    return ctx.max_over_ranks(acc / reps)
+
+
+def measure_workload(ctx, ex, name, spec, peak, reps=20):
+    """one entry of the `workloads` block"""
+    torch = ctx.torch
+    from iexa_b200.model import bind
+    t0 = time.perf_counter()
+    core = spec["build"]()
+    t_core = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    m = ex.ExaModel(core, device=ctx.local_rank, rank=ctx.rank, world=ctx.world)
+    t_plan = time.perf_counter() - t0
+    x_h, y_full = eval_point(core, seed=11)
+    y_h = to_local(ex, m, 0, y_full, m.loc_ncon)
+    x, y = torch.from_numpy(x_h).to(ctx.dev), torch.from_numpy(y_h).to(ctx.dev)
+    z = lambda n: torch.zeros(max(int(n), 1), dtype=torch.float64, device=ctx.dev)
+    c, jv, hv, g = z(m.loc_ncon), z(m.loc_nnzj), z(m.loc_nnzh), z(m.meta.nvar)
+    names = ["cons", "jac_coord", "hess_coord", "grad"]
+    which = [ex.lib.CB_CONS, ex.lib.CB_JAC, ex.lib.CB_HESS, ex.lib.CB_GRAD]
+    calls = [bind(m, "cons", x, c), bind(m, "jac_coord", x, jv), bind(m, "hess_coord", x, hv, y, 1.0), bind(m, "grad", x, g)]
+    for f in calls:
+        f()
+    ctx.barrier()
+    parity = parity_vs_oracle(ctx, ex, m, core, x_h, y_full, (c, jv, hv))
+    # L2: these working sets are near or below the 126 MB L2 — rewrite a 512 MB buffer before every timed launch
+    ms = per_callback_ms(ctx, calls, reps, flush=True)
+    # back to back, no flush, one event pair around the three callbacks (what a solver iteration sees)
+    ctx.barrier()
+    a, b = ctx.ev(), ctx.ev()
+    a.record()
+    for _ in range(reps):
+        calls[0](); calls[1](); calls[2]()
+    b.record(); ctx.barrier()
+    warm_ms = float(ctx.max_over_ranks(a.elapsed_time(b) / reps)[0])
+    byt = np.array([float(ex.algorithmic_bytes(m, w)) for w in which])
+    byt = ctx.sum_over_ranks(byt)                 # whole job: the ranks' bytes add up
+    per = {}
+    for n, t, bts in zip(names, ms, byt):
+        gbs = bts / (t * 1e-3) / 1e9 if t > 0 else 0.0
+        per[n] = {"ms": float(t), "bytes": int(bts), "GB/s": gbs, "frac": gbs / (peak * ctx.world)}
+    tot_ms, tot_b = float(ms[:3].sum()), float(byt[:3].sum())
+    out = {"config": spec["config"], "nvar": int(m.meta.nvar), "ncon": int(m.meta.ncon), "nnzj": int(m.meta.nnzj), "nnzh": int(m.meta.nnzh),
+           "generators": int(m.cmeta.nobj_gen + m.cmeta.ncon_gen), "kernels": f"nvrtc-specialised ({m.cmeta.n_kernels_specialised})" if m.cmeta.n_kernels_specialised else "interpreter",
+           "engine_note": m.L.iexa_engine_note(m.h).decode()[:120], "n_gpus": ctx.world,
+           "per_callback": per,
+           "cons+jac+hess": {"ms": tot_ms, "evals/s": 1e3 / tot_ms, "bytes": int(tot_b), "GB/s": tot_b / (tot_ms * 1e-3) / 1e9,
+                             "frac": tot_b / (tot_ms * 1e-3) / 1e9 / (peak * ctx.world),
+                             "timing": f"sum of the three per-launch means ({reps} launches each, CUDA events, L2 flushed before every launch, max over ranks)"},
+           "cons+jac+hess_back_to_back": {"ms": warm_ms, "evals/s": 1e3 / warm_ms,
+                                          "note": "no flush between launches: part of the working set stays in the 126 MB L2 (what a solver iteration sees; not a roofline number)"},
+           "parity": parity, "build_s": {"lowering": t_core, "plan+upload+nvrtc": t_plan}}
+    del m, x, y, c, jv, hv, g, calls
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -178,33 +397,30 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-    import torch.distributed as dist
     import iexa_b200 as ex
-    from iexa_b200 import models
+    from iexa_b200.model import bind
+    ctx = Ctx()
+    torch, dist = ctx.torch, ctx.dist
+    world, rank, local_rank, dev = ctx.world, ctx.rank, ctx.local_rank, ctx.dev
+    barrier = ctx.barrier
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
+    t0 = time.perf_counter()
     core = args.build(args.supports)
+    t_core = time.perf_counter() - t0
     flags = ex.lib.IEXA_F_NO_SPECIALISE if args.interp else ex.lib.IEXA_F_DEFAULT
+    t0 = time.perf_counter()
     m = ex.ExaModel(core, device=local_rank, rank=rank, world=world, flags=flags)
-    rng = np.random.default_rng(0)
-    x_h = np.where(np.isfinite(core.x0_vec), core.x0_vec, 0.0) + 0.1 * rng.uniform(-1, 1, core.nvar)
-    y_full = rng.uniform(-1, 1, core.ncon)
-    # this rank's multipliers, in its local row layout
-    segs = (ex.lib.Segment * 4096)()
-    nseg = m.L.iexa_segments(m.h, 0, segs, 4096)
-    y_h = np.zeros(max(m.loc_ncon, 1))
-    for s in segs[:nseg]:
-        y_h[s.local_start:s.local_start + s.length] = y_full[s.global_start:s.global_start + s.length]
+    t_plan = time.perf_counter() - t0
+    x_h, y_full = eval_point(core)
+    y_h = to_local(ex, m, 0, y_full, m.loc_ncon)     # this rank's multipliers, in its local row layout
     x = torch.from_numpy(x_h).to(dev)
     y = torch.from_numpy(y_h).to(dev)
     c = torch.empty(max(m.loc_ncon, 1), dtype=torch.float64, device=dev)
@@ -213,18 +429,12 @@ def main():
 
     # buffers are bound once (raw pointers + stream), like a Julia ccall on CuArray pointers: every
     # callback below is exactly one call into the C ABI
-    from iexa_b200.model import bind
     f_cons = bind(m, "cons", x, c)
     f_jac = bind(m, "jac_coord", x, jv)
     f_hess = bind(m, "hess_coord", x, hv, y, 1.0)
 
     def step():
         f_cons(); f_jac(); f_hess()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -234,7 +444,7 @@ def main():
         sampler.start()
     # (1) the timed region: EXACTLY K steps between two events on the launching (current torch) stream —
     #     nothing else is enqueued between the callbacks, as in a solver iteration
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = ctx.ev(), ctx.ev()
     barrier()
     t_wall = time.perf_counter()
     e0.record()
@@ -249,7 +459,7 @@ def main():
     #     (an event between two kernels keeps the next one from being launched ahead — PDL — so this pass
     #     is a little slower than (1); its per-kernel durations are what the roofline is quoted on)
     nb = max(3, min(args.steps, 100))
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(nb)]
+    ev = [[ctx.ev() for _ in range(4)] for _ in range(nb)]
     for i in range(nb):
         ev[i][0].record(); f_cons()
         ev[i][1].record(); f_jac()
@@ -257,11 +467,15 @@ def main():
         ev[i][3].record()
     barrier()
     per = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in ev]).mean(axis=0)  # ms
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tmax.item()) / args.steps
+    per = ctx.max_over_ranks(per)
+    ms_per_step = float(ctx.max_over_ranks(total_ms)[0]) / args.steps
     value = 1e3 / ms_per_step
+    names = ["cons", "jac_coord", "hess_coord"]
+    which = [ex.lib.CB_CONS, ex.lib.CB_JAC, ex.lib.CB_HESS]
+    bytes_loc = np.array([float(ex.algorithmic_bytes(m, w)) for w in which])
+    bytes_cb = ctx.sum_over_ranks(bytes_loc)
+    launches_step = int(sum(ex.launches_per_call(m, w) for w in which))
+    bytes_meta.update(nnzj=int(m.meta.nnzj), nnzh=int(m.meta.nnzh), nspec=int(m.cmeta.n_kernels_specialised))
 
     # ---- e2e: the same step through the C ABI with HOST buffers (pinned), copies inside the call
     e2e = None
@@ -288,67 +502,83 @@ def main():
         for _ in range(n_e2e):
             step_host()
         barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        h2d = 8 * (m.meta.nvar + m.loc_ncon)
+        dt = float(ctx.max_over_ranks((time.perf_counter() - t0) / n_e2e)[0])
+        h2d = int(m.L.iexa_host_x_bytes(m.h)) + 8 * m.loc_ncon
         d2h = 8 * (m.loc_ncon + m.loc_nnzj + m.loc_nnzh)
-        e2e = {"value": 1.0 / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "steps": n_e2e, "note": "host (pinned) buffers through iexa_cons/iexa_jac_coord/iexa_hess_coord; PCIe copies inside the timed region; x uploaded once per eval (new_x), y once, c + Jacobian + Hessian values downloaded"}
+        e2e = {"value": 1.0 / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": n_e2e, "note": "host (pinned) buffers through iexa_cons/iexa_jac_coord/iexa_hess_coord; PCIe copies inside the timed region; only the "
+                                       "parts of x this rank READS are uploaded (iexa_x_ranges), once per eval (new_x); y once; c + Jacobian + Hessian values downloaded; "
+                                       "bytes are per rank"}
+        del xp, yp, cp, jp, hp, h_cons, h_jac, h_hess
+
+    # ---- matrix-free products: fused kernels (no COO values materialised), per-call ms + roofline
+    products = None
+    if not args.no_products:
+        rng = np.random.default_rng(5)
+        v = torch.from_numpy(rng.uniform(-1, 1, core.nvar)).to(dev)
+        w_full = rng.uniform(-1, 1, core.ncon)
+        w = torch.from_numpy(to_local(ex, m, 0, w_full, m.loc_ncon)).to(dev)
+        Jv = torch.empty(max(m.loc_ncon, 1), dtype=torch.float64, device=dev)
+        Jtw = torch.empty(m.meta.nvar, dtype=torch.float64, device=dev)
+        Hv = torch.empty(m.meta.nvar, dtype=torch.float64, device=dev)
+        pcalls = [bind(m, "jprod", x, Jv, v=v), bind(m, "jtprod", x, Jtw, v=w), bind(m, "hprod", x, Hv, y, 1.0, v=v)]
+        pms = per_callback_ms(ctx, pcalls, max(5, min(args.steps, 50)), flush=False)
+        pb = ctx.sum_over_ranks([float(ex.algorithmic_bytes(m, wch)) for wch in (ex.lib.CB_JPROD, ex.lib.CB_JTPROD, ex.lib.CB_HPROD)])
+        products = {}
+        for n, t, bts, wch in zip(("jprod", "jtprod", "hprod"), pms, pb, (ex.lib.CB_JPROD, ex.lib.CB_JTPROD, ex.lib.CB_HPROD)):
+            gbs = bts / (t * 1e-3) / 1e9
+            products[n] = {"ms": float(t), "bytes": int(bts), "GB/s": gbs, "frac": gbs / (peak * world), "launches": int(ex.launches_per_call(m, wch))}
+        products["note"] = ("fused first / second order programs with a product epilogue; algorithmic bytes = the inputs those programs load + the touched part "
+                            "of v (and y) + every entry of the result once; jprod! has no atomics (bit-reproducible); jtprod!/hprod!: single-writer blocks stored "
+                            "directly in a first launch, the remaining contributions added with atomics in a second, ordered launch"
+                            + ("; world > 1: per-rank partial sums, no all-reduce in this number" if world > 1 else ""))
+        products["engine_note"] = m.L.iexa_engine_note(m.h).decode()[:120]
+        del v, w, Jv, Jtw, Hv, pcalls
+
+    # ---- solver iteration: obj + grad! + cons! + jac_coord! + hess_coord! + COO->CSR of both matrices, device-resident,
+    #      with (N > 1) the x halo exchange and the all-reduces INSIDE the timed step (ESCAPE34/utils.jl:7,23 `ad_time`)
+    iteration = None
+    if not args.no_iteration:
+        iteration = measure_iteration(ctx, ex, m, core, x, y, c, jv, hv, args, peak)
 
     # ---- NON-TARGET cost, reported separately: getting a new iterate to the ranks when the solver lives
-    #      on GPU 0.  (a) NCCL broadcast of the whole x; (b) only the ranges each rank READS (iexa_x_ranges: its own
-    #      supports of every variable block + shared variables + halos), packed, sent point to point, unpacked.
+    #      on GPU 0: NCCL broadcast of the whole x, vs the halo exchange a distributed solver does (inside `iteration`)
     xdist = None
     if world > 1:
-        n = m.L.iexa_x_ranges(m.h, None, 0)
-        segs = (ex.lib.Segment * max(n, 1))()
-        m.L.iexa_x_ranges(m.h, segs, n)
-        mine = [(s.global_start, s.length) for s in segs[:n]]
-        allr = [None] * world
-        dist.all_gather_object(allr, mine)
-
         def timed(fn, reps=11):
-            for _ in range(4):          # first calls set up NCCL point-to-point channels
+            for _ in range(4):
                 fn()
             ts = []
             for _ in range(reps):
                 barrier()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a, b = ctx.ev(), ctx.ev()
                 a.record(); fn(); b.record()
                 barrier()
-                t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ts.append(float(t.item()))
+                ts.append(float(ctx.max_over_ranks(a.elapsed_time(b))[0]))
             return float(np.median(ts))
+        n = m.L.iexa_x_ranges(m.h, None, 0)
+        segs = (ex.lib.Segment * max(n, 1))()
+        m.L.iexa_x_ranges(m.h, segs, n)
+        xdist = {"broadcast_whole_x_ms": timed(lambda: dist.broadcast(x, src=0)), "x_bytes": int(8 * m.meta.nvar),
+                 "read_fraction_per_rank": sum(s.length for s in segs[:n]) / m.meta.nvar,
+                 "note": "non-target: a solver that lives on GPU 0 broadcasts x; a distributed solver exchanges the shared slice and the shard-boundary halos only (timed inside `iteration`)"}
 
-        def scatter_ranges():
-            if rank == 0:
-                ops = []
-                for r in range(1, world):
-                    buf = torch.cat([x[s0:s0 + ln] for s0, ln in allr[r]])
-                    ops.append(dist.P2POp(dist.isend, buf, r))
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-            else:
-                tot = sum(ln for _, ln in mine)
-                buf = torch.empty(tot, dtype=torch.float64, device=dev)
-                for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, buf, 0)]):
-                    w.wait()
-                o = 0
-                for s0, ln in mine:
-                    x[s0:s0 + ln] = buf[o:o + ln]; o += ln
-
-        from iexa_b200.dist import ShardedExaModel
-        sm = ShardedExaModel.wrap(m)
-        _, recv, _ = sm.x_partition()
-        halo = torch.tensor([sum(hi - lo for v in recv.values() for lo, hi in v)], device=dev)
-        dist.all_reduce(halo)
-        xdist = {"broadcast_whole_x_ms": timed(lambda: dist.broadcast(x, src=0)),
-                 "scatter_read_ranges_ms": timed(scatter_ranges),
-                 "halo_exchange_ms": timed(lambda: sm.exchange_x(x)), "halo_entries_all_ranks": int(halo.item()),
-                 "x_bytes": int(8 * m.meta.nvar), "read_fraction_per_rank": sum(ln for _, ln in mine) / m.meta.nvar,
-                 "note": "non-target: a solver that lives on GPU 0 broadcasts x or scatters the ranges each rank reads; a distributed solver (each rank owns its part of x, ShardedExaModel.exchange_x) exchanges the shared slice and the shard-boundary halos only"}
+    # ---- the other BASELINE configurations at their named sizes
+    workloads = None
+    if not args.no_workloads:
+        del m, x, y, c, jv, hv, f_cons, f_jac, f_hess
+        torch.cuda.empty_cache()
+        workloads = {}
+        only = set(args.only_workloads.split(",")) if args.only_workloads else None
+        for wname, spec in WORKLOADS.items():
+            if only and wname not in only:
+                continue
+            try:
+                workloads[wname] = measure_workload(ctx, ex, wname, spec, peak)
+            except Exception as e:   # one broken workload must not take the headline down
+                workloads[wname] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
+        m = None
 
     if rank != 0:
         if world > 1:
@@ -356,60 +586,160 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (largest share of the step), measured live above
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    names = ["cons", "jac_coord", "hess_coord"]
-    which = [ex.lib.CB_CONS, ex.lib.CB_JAC, ex.lib.CB_HESS]
-    bytes_cb = [ex.algorithmic_bytes(m, w) for w in which]
     dom = int(np.argmax(per))
     achieved = bytes_cb[dom] / (per[dom] * 1e-3) / 1e9
     traffic = None
     tf = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tf):
+    if os.path.exists(tf) and world == 1:
         try:
             traffic = json.load(open(tf)).get(names[dom])
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": f"iexa_cb_{names[dom].split('_')[0]}", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+    roofline = {"bound": "hbm", "kernel": f"iexa_cb_{names[dom].split('_')[0]}", "achieved": achieved, "peak": peak * world,
+                "unit": "GB/s", "frac": achieved / (peak * world), "traffic": traffic, "peak_kind": peak_kind + (f" x {world} GPUs" if world > 1 else ""),
                 "algorithmic_bytes_per_launch": int(bytes_cb[dom]), "avg_launch_ms": float(per[dom]),
-                "per_callback": {n: {"ms": float(t), "GB/s": b / (t * 1e-3) / 1e9, "frac": b / (t * 1e-3) / 1e9 / peak,
+                "per_callback": {n: {"ms": float(t), "GB/s": b / (t * 1e-3) / 1e9, "frac": b / (t * 1e-3) / 1e9 / (peak * world),
                                      "bytes": int(b)} for n, t, b in zip(names, per, bytes_cb)},
                 "all_three": {"bytes": int(sum(bytes_cb)), "GB/s": sum(bytes_cb) / (ms_per_step * 1e-3) / 1e9,
-                              "frac": sum(bytes_cb) / (ms_per_step * 1e-3) / 1e9 / peak,
+                              "frac": sum(bytes_cb) / (ms_per_step * 1e-3) / 1e9 / (peak * world),
                               "note": "whole step of the timed region (two events around K steps)"},
                 "timing": f"per-kernel durations: CUDA events around every launch in a second live pass of {nb} steps "
                           "right after the timed region (events between the callbacks would serialise the "
-                          "programmatic dependent launches the timed region uses)"}
+                          "programmatic dependent launches the timed region uses); bytes summed and times max-ed over the ranks"}
 
     cpu = None
     if not args.no_cpu and world == 1:
-        v1, t1 = cpu_eval_rate(args.build, int(m.meta.ncon), args.cpu_sample, 1)
-        cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"oracle (C restatement of ExaModels' sequential per-support AD) on {args.cpu_sample} of "
-                         f"{args.supports} public supports ({t1:.2f} s/eval measured), scaled linearly; ExaModels' "
-                         f"CPU backend is sequential (Julia threads = 1)"}
+        # the FULL named configuration, no sampling: one eval on one thread (ExaModels' CPU backend is sequential: Julia
+        # threads = 1), then the same with every host thread (OpenMP over supports)
+        from oracle.oracle import OracleModel
+        om = OracleModel(core)
+        nthr = host_threads()
+        tall = oracle_eval_seconds(om, x_h, y_full, nthr, reps=3, warm=1)
+        t1 = oracle_eval_seconds(om, x_h, y_full, 1, reps=1, warm=0)
+        cpu = {"value": 1.0 / min(t1), "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"oracle (C restatement of ExaModels' sequential per-support AD) on the FULL configuration ({args.supports} public supports): "
+                         f"one eval on 1 thread = {min(t1):.2f} s (ExaModels' CPU backend is sequential: Julia threads = 1); no sampling, no scaling",
+               "all_cores": {"value": 1.0 / min(tall), "unit": UNIT, "cores": nthr, "seconds_per_eval": min(tall),
+                             "sample": "same model, OpenMP over supports, best of 3 full evals"}}
+        del om
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload_name, "supports": args.supports, "nvar": int(m.meta.nvar), "ncon": int(m.meta.ncon),
-                   "nnzj": int(m.meta.nnzj), "nnzh": int(m.meta.nnzh), "sharding": f"contiguous support blocks x{world}",
-                   "l2": "inputs larger than L2 (x = %.0f MB, outputs %.1f GB per eval)" % (m.meta.nvar * 8 / 1e6, (m.loc_nnzj + m.loc_nnzh + m.loc_ncon) * 8 / 1e9),
-                   "kernels": "interpreter" if args.interp else f"nvrtc-specialised ({m.cmeta.n_kernels_specialised})"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "x_distribution": xdist,
-        "gpu_launches": int(args.steps * sum(ex.launches_per_call(m, w) for w in which)),
+        "config": workload_config(args.workload_name, args.supports, core.nvar, core.ncon, bytes_meta["nnzj"], bytes_meta["nnzh"]),
+        "engine": {"sharding": f"contiguous support blocks x{world}", "kernels": "interpreter" if args.interp else f"nvrtc-specialised ({bytes_meta['nspec']})",
+                   "build_s": {"lowering": t_core, "plan+upload+nvrtc": t_plan}},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "products": products, "iteration": iteration,
+        "x_distribution": xdist, "workloads": workloads,
+        "gpu_launches": int(args.steps * launches_step),
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+bytes_meta = {}
+
+
+def measure_iteration(ctx, ex, m, core, x, y, c, jv, hv, args, peak):
+    """obj + grad! + cons! + jac_coord! + hess_coord! + iexa_csr_apply(J) + iexa_csr_apply(H) per step, device-resident.
+    N > 1: every step starts with the x halo exchange (each rank owns a part of the iterate; shared variables and shard
+    boundaries are pushed over NVLink) and contains the all-reduce of the objective and of the shared gradient slice."""
+    torch, dist = ctx.torch, ctx.dist
+    from iexa_b200.model import bind
+    from iexa_b200.dist import ShardedExaModel
+    dev, world = ctx.dev, ctx.world
+    L = m.L
+    st = torch.cuda.current_stream(dev).cuda_stream
+    g = torch.empty(m.meta.nvar, dtype=torch.float64, device=dev)
+    f_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+    sm = ShardedExaModel.wrap(m)
+    peer = sm.enable_peer_halo(x) if world > 1 else False
+    # CSR handles of THIS rank's COO slices (rows are global numbers; a rank's CSR has entries in its own rows only)
+    csr = []
+    t0 = time.perf_counter()
+    for whichm, nnz, fn, nrows in ((0, m.loc_nnzj, ex.jac_structure_, m.meta.ncon), (1, m.loc_nnzh, ex.hess_structure_, m.meta.nvar)):
+        if nnz == 0:
+            csr.append(None)
+            continue
+        r = torch.zeros(nnz, dtype=torch.int32, device=dev); cc = torch.zeros_like(r)
+        fn(m, r, cc)
+        keys = torch.zeros(nnz, dtype=torch.int32, device=dev)
+        ex.lib.check(L, L.iexa_coo_locality(m.h, whichm, keys.data_ptr(), 1, st))
+        torch.cuda.synchronize()
+        h = C.c_void_p()
+        ex.lib.check(L, L.iexa_csr_create_keyed(C.byref(h), nrows, m.meta.nvar, nnz, r.data_ptr(), cc.data_ptr(), 4,
+                                                keys.data_ptr() if whichm == 1 else None, 1, ctx.local_rank))
+        outv = torch.empty(L.iexa_csr_nnz(h), dtype=torch.float64, device=dev)
+        csr.append((h, outv))
+        del r, cc, keys
+    t_csr = time.perf_counter() - t0
+    f_grad = bind(m, "grad", x, g)
+    f_cons, f_jac, f_hess = bind(m, "cons", x, c), bind(m, "jac_coord", x, jv), bind(m, "hess_coord", x, hv, y, 1.0)
+    vp = C.c_void_p
+    xp, fp = vp(x.data_ptr()), vp(f_dev.data_ptr())
+    srcs = (jv, hv)
+
+    def step():
+        if world > 1:
+            sm.exchange_x(x)
+        L.iexa_obj_device(m.h, xp, fp, vp(st))
+        f_grad()
+        if world > 1:
+            sm.allreduce_obj_grad_(f_dev, g)
+        f_cons(); f_jac(); f_hess()
+        for k in range(2):
+            if csr[k] is not None:
+                L.iexa_csr_apply(csr[k][0], vp(srcs[k].data_ptr()), vp(csr[k][1].data_ptr()), 1, vp(st))
+
+    for _ in range(3):
+        step()
+    ctx.barrier()
+    n = max(5, min(args.steps, 50))
+    a, b = ctx.ev(), ctx.ev()
+    ctx.barrier()
+    a.record()
+    for _ in range(n):
+        step()
+    b.record()
+    ctx.barrier()
+    ms = float(ctx.max_over_ranks(a.elapsed_time(b) / n)[0])
+    # components, each timed alone (events around every call; no flush: config 3 streams far more than the L2 holds)
+    comp_calls = [lambda: L.iexa_obj_device(m.h, xp, fp, vp(st)), f_grad, f_cons, f_jac, f_hess]
+    comp_names = ["obj", "grad", "cons", "jac_coord", "hess_coord"]
+    for k, nm in ((0, "csr_apply_jac"), (1, "csr_apply_hess")):
+        if csr[k] is not None:
+            comp_calls.append(lambda k=k: L.iexa_csr_apply(csr[k][0], vp(srcs[k].data_ptr()), vp(csr[k][1].data_ptr()), 1, vp(st)))
+            comp_names.append(nm)
+    if world > 1:
+        comp_calls += [lambda: sm.exchange_x(x), lambda: sm.allreduce_obj_grad_(f_dev, g)]
+        comp_names += ["x_halo_exchange", "allreduce_obj+shared_grad"]
+    cms = per_callback_ms(ctx, comp_calls, max(5, min(args.steps, 30)), flush=False)
+    byt = [float(ex.algorithmic_bytes(m, w)) for w in (ex.lib.CB_OBJ, ex.lib.CB_GRAD, ex.lib.CB_CONS, ex.lib.CB_JAC, ex.lib.CB_HESS)]
+    for k in range(2):
+        if csr[k] is not None:
+            nnz, cn = (m.loc_nnzj, m.loc_nnzh)[k], int(L.iexa_csr_nnz(csr[k][0]))
+            byt.append(float(8 * nnz + 8 * cn + 4 * cn + (0 if cn == nnz and k == 0 else 4 * nnz + 4 * cn)))
+    tot_b = float(ctx.sum_over_ranks(sum(byt))[0])
+    out = {"ms": ms, "iterations/s": 1e3 / ms, "steps": n, "n_gpus": world,
+           "what": "obj + grad! + cons! + jac_coord! + hess_coord! + iexa_csr_apply(Jacobian) + iexa_csr_apply(Hessian), device-resident, one x"
+                   + ("; every step starts with the x halo exchange and contains the all-reduce of the objective and of the shared gradient slice" if world > 1 else ""),
+           "bytes": int(tot_b), "GB/s": tot_b / (ms * 1e-3) / 1e9, "frac": tot_b / (ms * 1e-3) / 1e9 / (peak * world),
+           "components_ms": {nm: float(t) for nm, t in zip(comp_names, cms)},
+           "csr_setup_s": t_csr, "halo_entries_this_rank": int(sm.halo_entries()) if world > 1 else 0,
+           "collectives": ("x halo exchange and [objective, shared gradient slice] all-reduce as single kernels over NVLink peer memory (csrc/halo.cu, CUDA IPC); "
+                           f"shared gradient entries: {'all of g (NCCL)' if sm.shared_all else len(sm.shared_idx)}; peer status {sm.peer_status()}") if peer
+                          else ("NCCL point-to-point halo exchange + NCCL all-reduce (torch.distributed)" if world > 1 else "none (one GPU)"),
+           "reference_analogue": "ad_time of ESCAPE34/utils.jl:7,23 (time inside the NLPModels callbacks per solve) — per iteration"}
+    sm.close_peer_halo()
+    for k in range(2):
+        if csr[k] is not None:
+            L.iexa_csr_destroy(csr[k][0])
+    del csr, g
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

@@ -231,12 +231,20 @@ int64_t iexa_segments(const iexa_plan *p, int32_t which, iexa_segment *out, int6
  * one rank (finite / shared variables and shard-boundary halos): the slice that must be
  * all-reduced after iexa_grad.  Returns the count; fills up to cap.                    */
 int64_t iexa_shared_vars(const iexa_plan *p, int64_t *out, int64_t cap);
+/* the same set as merged, sorted ranges (global_start == local_start, 0-based).  Covers shifted references at the shard
+ * boundaries ((y[i+1]-y[i])^2: the boundary entry is written by both neighbours), indices of product / restricted
+ * iterators (w[s]*z[t]^2 over (t, s): every z[t] is written by every rank) and constant indices.  Conservative: an
+ * entry may be listed although one rank contributes to it, never the other way round.                          */
+int64_t iexa_shared_ranges(const iexa_plan *p, iexa_segment *out, int64_t cap);
 /* the parts of x this rank's callbacks READ: its own supports of every variable block, the replicated finite /
  * shared variables and the halo of shifted references (y[i-1] of finite differences, the lower-bound / internal
  * nodes of collocation elements) at the shard boundaries — merged, sorted ranges (global_start == local_start,
  * 0-based; a conservative cover).  A distributed solver keeps only these ranges of x current on this rank
  * (halo exchange instead of a broadcast of the whole iterate).  Returns the count; fills up to cap.            */
 int64_t iexa_x_ranges(const iexa_plan *p, iexa_segment *out, int64_t cap);
+
+/* bytes of x a host-memory callback uploads on this rank: 8*nvar when world == 1, else the iexa_x_ranges only      */
+int64_t iexa_host_x_bytes(const iexa_plan *p);
 
 /* ---- byte accounting used by bench.py's roofline: ALGORITHMIC bytes of
  *      one call of each callback, computed from the finalised plan.
@@ -284,6 +292,32 @@ int64_t iexa_csr_nnz(const iexa_csr *h);
 int32_t iexa_csr_pattern(const iexa_csr *h, int32_t *rowptr, int32_t *colind, int32_t memspace);
 int32_t iexa_csr_apply(iexa_csr *h, const double *coo_vals, double *csr_vals, int32_t memspace,
                        void *stream);
+
+/* ---- x halo exchange + small all-reduce over NVLink peer memory (one process per GPU, CUDA IPC) — csrc/halo.cu.
+ *      A sharded solver keeps on every rank only the part of the iterate it owns; before the callbacks of a new iterate
+ *      each rank PUSHES the shared variables and the shard-boundary halos it owns straight into its readers' x buffers
+ *      (peer stores) — one small kernel per rank, flags in peer memory, no host synchronisation, no staging copies.
+ *      Which entries go where follows from iexa_x_ranges of all ranks (dist.py: x_partition).  Replaces the NCCL
+ *      point-to-point exchange (0.12 ms for 180 doubles on 8 GPUs); sharded analogue of the x every callback of
+ *      ext/InfiniteExaModelsMadNLP.jl:49-50 receives.
+ *      Setup: create; export the handles of MY x buffer and flag block; ship them to every peer (torch.distributed);
+ *      connect each peer's handles; set_sends / set_recvs.  exchange and allreduce_small are COLLECTIVE (every rank,
+ *      same order) and asynchronous on `stream`.  Waits inside the kernels are bounded (~4 s): iexa_halo_status != 0
+ *      reports an expired wait instead of a hung GPU.                                                              */
+typedef struct iexa_halo iexa_halo;
+int32_t iexa_halo_create(iexa_halo **out, int32_t device, int32_t rank, int32_t world);
+int32_t iexa_halo_export(iexa_halo *h, const void *x_dev, unsigned char *handle_x /*64 B*/, int64_t *x_offset,
+                         unsigned char *handle_flags /*64 B*/);
+int32_t iexa_halo_connect(iexa_halo *h, int32_t peer, const unsigned char *handle_x, int64_t x_offset,
+                          const unsigned char *handle_flags);
+/* lo_hi: n_ranges pairs [lo, hi), 0-based global positions of x that this rank owns and `peer` reads              */
+int32_t iexa_halo_set_sends(iexa_halo *h, int32_t peer, int64_t n_ranges, const int64_t *lo_hi);
+int32_t iexa_halo_set_recvs(iexa_halo *h, int32_t n_peers, const int32_t *peers);
+int32_t iexa_halo_exchange(iexa_halo *h, const double *x_dev, void *stream);
+/* buf[0..n) <- sum over ranks, n <= 1024, in place; summed in rank order: deterministic, bit-identical on all ranks */
+int32_t iexa_halo_allreduce_small(iexa_halo *h, double *buf_dev, int32_t n, void *stream);
+int64_t iexa_halo_status(iexa_halo *h);
+int32_t iexa_halo_destroy(iexa_halo *h);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libiexa_b200.so")
-SOURCES = ["api.cpp", "codegen.cpp", "engine.cu", "csr.cu"]
+SOURCES = ["api.cpp", "codegen.cpp", "engine.cu", "csr.cu", "halo.cu"]
 HEADERS = ["dag.hpp", "gen.hpp", "plan.hpp", "exec.hpp", "engine.hpp", "codegen.hpp", "../../include/iexa.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=default", "--expt-relaxed-constexpr"]

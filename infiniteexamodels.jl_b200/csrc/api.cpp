@@ -284,72 +284,84 @@ int64_t iexa_segments(const iexa_plan *p, int32_t which, iexa_segment *out, int6
   return n;
 }
 
-int64_t iexa_shared_vars(const iexa_plan *p, int64_t *out, int64_t cap) {
-  // variables referenced through a CONSTANT index by an objective generator with more than one
-  // support, or by any generator whose support range is split across ranks: their gradient
-  // entries are partial sums on every rank.  (Halo entries of shifted references such as
-  // y[i-1] are covered because each objective generator touches x only through its own k.)
+// Gradient entries that receive contributions from MORE THAN ONE rank: for every rank r the cover U_r of the variable
+// indices its share [k0_r, k1_r) of every objective generator reaches through any first-order slot (Plan::index_range —
+// shifted references y[i-1] at the shard boundaries, (k / div) % mod indices of product or restricted iterators and
+// constant indices are all index ranges); shared = union over r < r' of U_r ∩ U_r'.  Every rank computes the same set
+// from the plan alone.  The cover is conservative: an entry may be listed although a single rank contributes to it
+// (the others then add zero), never the other way round.
+static std::vector<std::pair<int64_t, int64_t>> shared_ranges(const iexa::Plan &P) { // [lo, hi] 1-based inclusive, merged
+  typedef std::pair<int64_t, int64_t> Iv;
+  auto merge = [](std::vector<Iv> &v) {
+    std::sort(v.begin(), v.end());
+    std::vector<Iv> m;
+    for (auto &r : v) {
+      if (!m.empty() && r.first <= m.back().second + 1) m.back().second = std::max(m.back().second, r.second);
+      else m.push_back(r);
+    }
+    v.swap(m);
+  };
+  std::vector<std::vector<Iv>> U(P.world);
+  for (int r = 0; r < P.world; ++r) {
+    for (auto &g : P.objs) {
+      int64_t k0, k1;
+      iexa::Plan::shard_range(g.K, r, P.world, k0, k1);
+      if (k1 <= k0) continue;
+      const iexa::Iterator &it = P.itrs[g.itr];
+      for (int32_t s : g.c.jac_slot) {
+        int64_t lo, hi;
+        P.index_range(it, g.c.int_cols, g.c.uidx[s], k0, k1, lo, hi);
+        lo = std::max<int64_t>(lo, 1); hi = std::min<int64_t>(hi, P.nvar);
+        if (lo <= hi) U[r].push_back({lo, hi});
+      }
+    }
+    merge(U[r]);
+  }
+  std::vector<Iv> sh;
+  for (int a = 0; a < P.world; ++a)
+    for (int b = a + 1; b < P.world; ++b) {
+      size_t i = 0, j = 0;
+      while (i < U[a].size() && j < U[b].size()) {
+        const int64_t lo = std::max(U[a][i].first, U[b][j].first), hi = std::min(U[a][i].second, U[b][j].second);
+        if (lo <= hi) sh.push_back({lo, hi});
+        if (U[a][i].second < U[b][j].second) ++i; else ++j;
+      }
+    }
+  merge(sh);
+  return sh;
+}
+
+int64_t iexa_shared_ranges(const iexa_plan *p, iexa_segment *out, int64_t cap) {
   if (!p || !p->plan.finalized) return -1;
-  const iexa::Plan &P = p->plan;
-  std::vector<int64_t> v;
-  for (auto &g : P.objs)
-    for (int32_t s : g.c.jac_slot)
-      if (g.c.uidx[s].terms.empty()) v.push_back(g.c.uidx[s].base);
-  std::sort(v.begin(), v.end());
-  v.erase(std::unique(v.begin(), v.end()), v.end());
-  for (size_t i = 0; i < v.size() && (int64_t)i < cap && out; ++i) out[i] = v[i];
-  return (int64_t)v.size();
+  auto sh = shared_ranges(p->plan);
+  for (size_t i = 0; i < sh.size() && (int64_t)i < cap && out; ++i) out[i] = iexa_segment{sh[i].first - 1, sh[i].first - 1, sh[i].second - sh[i].first + 1};
+  return (int64_t)sh.size();
+}
+
+int64_t iexa_shared_vars(const iexa_plan *p, int64_t *out, int64_t cap) {
+  if (!p || !p->plan.finalized) return -1;
+  auto sh = shared_ranges(p->plan);
+  int64_t n = 0;
+  for (auto &r : sh)
+    for (int64_t i = r.first; i <= r.second; ++i) { if (out && n < cap) out[n] = i; ++n; }
+  return n;
 }
 
 int64_t iexa_x_ranges(const iexa_plan *p, iexa_segment *out, int64_t cap) {
   if (!p || !p->plan.finalized) return -1;
   const iexa::Plan &P = p->plan;
-  std::vector<std::pair<int64_t, int64_t>> iv; // [lo, hi] 1-based, inclusive
-  auto scan = [&](const iexa::Generator &g) {
-    if (g.k1 <= g.k0) return;
-    const iexa::Iterator &it = P.itrs[g.itr];
-    std::vector<uint8_t> used(g.c.uidx.size(), 0);
-    for (size_t s = 0; s < used.size(); ++s)
-      used[s] = (s < g.c.x_slots_val.size() && g.c.x_slots_val[s]) || (s < g.c.x_slots_d1.size() && g.c.x_slots_d1[s]) ||
-                (s < g.c.x_slots_d2.size() && g.c.x_slots_d2[s]);
-    for (int32_t s : g.c.jac_slot) used[s] = 1;
-    for (auto &pr : g.c.hess_slot) { used[pr.first] = 1; used[pr.second] = 1; }
-    for (size_t s = 0; s < used.size(); ++s) {
-      if (!used[s]) continue;
-      const iexa::IndexExpr &e = g.c.uidx[s];
-      int64_t lo = e.base, hi = e.base;
-      for (auto &t : e.terms) {
-        const iexa::ColRef &r = it.int_cols[g.c.int_cols[t.first]];
-        const iexa::HostColumn &c = P.columns[r.col];
-        // positions j = (k / div) % mod visited by k in [k0, k1)
-        int64_t q0 = g.k0 / r.div, q1 = (g.k1 - 1) / r.div, j0 = 0, j1 = r.mod - 1;
-        if (q1 - q0 + 1 < r.mod && q0 % r.mod <= q1 % r.mod) { j0 = q0 % r.mod; j1 = q1 % r.mod; }
-        int64_t vmin, vmax;
-        if (c.affine) {
-          const int64_t a0 = c.ab * (j0 / c.ac), a1 = c.ab * (j1 / c.ac), dm = c.ad * (c.ac - 1);
-          vmin = c.aa + std::min(a0, a1) + std::min<int64_t>(0, dm);
-          vmax = c.aa + std::max(a0, a1) + std::max<int64_t>(0, dm);
-        } else {
-          vmin = vmax = c.ivals[j0];
-          for (int64_t j = j0; j <= j1; ++j) { vmin = std::min<int64_t>(vmin, c.ivals[j]); vmax = std::max<int64_t>(vmax, c.ivals[j]); }
-        }
-        lo += t.second >= 0 ? t.second * vmin : t.second * vmax;
-        hi += t.second >= 0 ? t.second * vmax : t.second * vmin;
-      }
-      lo = std::max<int64_t>(lo, 1); hi = std::min<int64_t>(hi, P.nvar);
-      if (lo <= hi) iv.emplace_back(lo, hi);
-    }
-  };
-  for (auto &g : P.objs) scan(g);
-  for (auto &g : P.cons) scan(g);
-  std::sort(iv.begin(), iv.end());
-  std::vector<std::pair<int64_t, int64_t>> m;
-  for (auto &r : iv) {
-    if (!m.empty() && r.first <= m.back().second + 1) m.back().second = std::max(m.back().second, r.second);
-    else m.push_back(r);
-  }
+  std::vector<std::pair<int64_t, int64_t>> m = P.x_read_ranges();
   for (size_t i = 0; i < m.size() && (int64_t)i < cap && out; ++i) out[i] = iexa_segment{m[i].first - 1, m[i].first - 1, m[i].second - m[i].first + 1};
   return (int64_t)m.size();
+}
+
+int64_t iexa_host_x_bytes(const iexa_plan *p) {
+  if (!p || !p->plan.finalized) return -1;
+  const iexa::Plan &P = p->plan;
+  if (P.world == 1) return 8 * P.nvar;
+  int64_t n = 0;
+  for (auto &r : P.x_read_ranges()) n += r.second - r.first + 1;
+  return 8 * n;
 }
 
 // ---- algorithmic bytes --------------------------------------------------------

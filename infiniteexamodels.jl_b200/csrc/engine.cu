@@ -730,6 +730,13 @@ class CudaEngine : public Engine {
       return IEXA_OK;
     }
     CK(stage.ensure((size_t)n * 8));
+    if (is_x && plan_.world > 1) {
+      // sharded: only the parts of x this rank READS cross PCIe (own supports of every block, shared variables, halos);
+      // the rest of the staging buffer is never addressed by this rank's kernels
+      if (x_ranges_.empty()) x_ranges_ = plan_.x_read_ranges();
+      for (auto &r : x_ranges_)
+        CK(cudaMemcpyAsync(stage.as<double>() + (r.first - 1), src + (r.first - 1), (size_t)(r.second - r.first + 1) * 8, cudaMemcpyHostToDevice, st));
+    } else
     CK(cudaMemcpyAsync(stage.p, src, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     if (is_x) {
       stage_x_valid_ = true;
@@ -746,6 +753,7 @@ class CudaEngine : public Engine {
     return same_x_ ? (int)IEXA_MEM_HOST : memspace;
   }
   bool same_x_ = false, stage_x_valid_ = false;
+  std::vector<std::pair<int64_t, int64_t>> x_ranges_; // 1-based inclusive (Plan::x_read_ranges)
   cudaEvent_t stage_x_event_ = nullptr; cudaStream_t stage_x_stream_ = nullptr;
   int out(double *dst, const double *dev, int64_t n, int memspace, cudaStream_t st, std::string &err) {
     if (memspace == IEXA_MEM_DEVICE) return IEXA_OK;

@@ -244,19 +244,21 @@ struct Plan {
     return v;
   }
 
+  // contiguous support blocks; generators shorter than the world (length-1 generators: point constraints,
+  // non-measure objective terms) go one support per rank starting at rank 0
+  static void shard_range(int64_t K, int64_t r, int64_t w, int64_t &k0, int64_t &k1) {
+    if (K < w) { k0 = std::min<int64_t>(r, K); k1 = std::min<int64_t>(r + 1, K); return; }
+    k0 = (K * r) / w;
+    k1 = (K * (r + 1)) / w;
+  }
+
   void layout(int32_t rank_, int32_t world_) {
     if (world_ < 1 || rank_ < 0 || rank_ >= world_) throw std::invalid_argument("bad rank/world");
     check_index_bounds();
     rank = rank_; world = world_;
     nnzj = nnzh = nnzg = 0;
     loc_ncon = loc_nnzj = loc_nnzh = 0;
-    auto range = [&](Generator &g) {
-      // contiguous support blocks; generators shorter than the world (length-1 generators: point constraints,
-      // non-measure objective terms) go one support per rank starting at rank 0
-      if (g.K < world) { g.k0 = std::min<int64_t>(rank, g.K); g.k1 = std::min<int64_t>(rank + 1, g.K); return; }
-      g.k0 = (g.K * rank) / world;
-      g.k1 = (g.K * (rank + 1)) / world;
-    };
+    auto range = [&](Generator &g) { shard_range(g.K, rank, world, g.k0, g.k1); };
     for (auto &g : objs) {
       range(g);
       g.og = nnzg; nnzg += g.K * g.c.o1step;
@@ -536,6 +538,38 @@ struct Plan {
       last = expect_div;
     }
     return s != 0 && last >= K;
+  }
+
+  // the parts of x this rank's callbacks READ (1-based inclusive, merged, sorted): its own supports of every variable block,
+  // the replicated finite / shared variables and the halo of shifted references at the shard boundaries (a cover)
+  std::vector<std::pair<int64_t, int64_t>> x_read_ranges() const {
+    std::vector<std::pair<int64_t, int64_t>> iv;
+    auto scan = [&](const Generator &g) {
+      if (g.k1 <= g.k0) return;
+      const Iterator &it = itrs[g.itr];
+      std::vector<uint8_t> used(g.c.uidx.size(), 0);
+      for (size_t s = 0; s < used.size(); ++s)
+        used[s] = (s < g.c.x_slots_val.size() && g.c.x_slots_val[s]) || (s < g.c.x_slots_d1.size() && g.c.x_slots_d1[s]) ||
+                  (s < g.c.x_slots_d2.size() && g.c.x_slots_d2[s]);
+      for (int32_t s : g.c.jac_slot) used[s] = 1;
+      for (auto &pr : g.c.hess_slot) { used[pr.first] = 1; used[pr.second] = 1; }
+      for (size_t s = 0; s < used.size(); ++s) {
+        if (!used[s]) continue;
+        int64_t lo, hi;
+        index_range(it, g.c.int_cols, g.c.uidx[s], g.k0, g.k1, lo, hi);
+        lo = std::max<int64_t>(lo, 1); hi = std::min<int64_t>(hi, nvar);
+        if (lo <= hi) iv.emplace_back(lo, hi);
+      }
+    };
+    for (auto &g : objs) scan(g);
+    for (auto &g : cons) scan(g);
+    std::sort(iv.begin(), iv.end());
+    std::vector<std::pair<int64_t, int64_t>> m;
+    for (auto &r : iv) {
+      if (!m.empty() && r.first <= m.back().second + 1) m.back().second = std::max(m.back().second, r.second);
+      else m.push_back(r);
+    }
+    return m;
   }
 
   // every x / theta index a tape can produce must stay inside [1, nvar] / [1, npar]: the kernels address

@@ -33,12 +33,7 @@ class ShardedExaModel:
         self.model = _m.ExaModel(core, device=0 if device is None else device, rank=self.rank, world=self.world,
                                  flags=flags, library=library)
         self.meta = self.model.meta
-        m = self.model
-        n = m.L.iexa_shared_vars(m.h, None, 0)
-        idx = np.zeros(max(n, 1), dtype=np.int64)
-        if n > 0:
-            m.L.iexa_shared_vars(m.h, idx.ctypes.data, n)
-        self.shared_idx = idx[:n] - 1  # 0-based variable indices whose gradient entries are partial sums
+        self._init_shared()
         self._ev = evaluator  # tests inject a host evaluator; default: the CUDA engine
         self._shared_t = None
 
@@ -51,13 +46,24 @@ class ShardedExaModel:
         self.dist, self.torch, self.group = dist, torch, group
         self.rank, self.world = model.rank, model.world
         self.model, self.meta = model, model.meta
-        n = model.L.iexa_shared_vars(model.h, None, 0)
-        idx = np.zeros(max(n, 1), dtype=np.int64)
-        if n > 0:
-            model.L.iexa_shared_vars(model.h, idx.ctypes.data, n)
-        self.shared_idx = idx[:n] - 1
+        self._init_shared()
         self._ev, self._shared_t = None, None
         return self
+
+    def _init_shared(self):
+        """0-based variable indices whose gradient entries are partial sums on several ranks (iexa_shared_ranges: shared /
+        finite variables, shard-boundary entries of shifted references, variables indexed through product or restricted
+        iterators).  ``shared_all``: the set covers most of g — all-reduce the whole vector instead of a gathered slice."""
+        m = self.model
+        n = m.L.iexa_shared_ranges(m.h, None, 0)
+        segs = (_lib.Segment * max(n, 1))()
+        m.L.iexa_shared_ranges(m.h, segs, n)
+        self.shared_ranges = [(s.global_start, s.global_start + s.length) for s in segs[:n]]
+        total = sum(hi - lo for lo, hi in self.shared_ranges)
+        self.shared_all = total > 0.25 * max(self.meta.nvar, 1)
+        self.shared_idx = (np.concatenate([np.arange(lo, hi, dtype=np.int64) for lo, hi in self.shared_ranges])
+                           if (self.shared_ranges and not self.shared_all) else np.zeros(0, dtype=np.int64))
+        self._peer = None
 
     # ---- layout ---------------------------------------------------------------------------------
     def segments(self, which: int):
@@ -138,13 +144,106 @@ class ShardedExaModel:
         self._partition = (owned_all[self.rank], {q: v for q, v in recv.items() if v}, {r: v for r, v in send.items() if v})
         return self._partition
 
+    # ---- NVLink peer-memory path (csrc/halo.cu): one small kernel per rank and exchange ---------------------------
+    def enable_peer_halo(self, x) -> bool:
+        """map the peers' x buffers and flag blocks (CUDA IPC) so that ``exchange_x(x)`` and the small all-reduces run as
+        single kernels over NVLink peer memory.  ``x`` (a CUDA tensor) must be THE iterate buffer of this rank from now on.
+        Collective.  Returns False (and keeps the NCCL path) when IPC is not available for this buffer."""
+        torch, dist = self.torch, self.dist
+        if self.world == 1 or not (isinstance(x, torch.Tensor) and x.is_cuda):
+            return False
+        m = self.model
+        L = m.L
+        h = C.c_void_p()
+        ok = L.iexa_halo_create(C.byref(h), x.device.index, self.rank, self.world) == 0
+        hx, hf, off = (C.c_ubyte * 64)(), (C.c_ubyte * 64)(), C.c_int64()
+        ok = ok and L.iexa_halo_export(h, C.c_void_p(x.data_ptr()), hx, C.byref(off), hf) == 0
+        mine = (bytes(hx), int(off.value), bytes(hf), bool(ok))
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine, group=self.group)
+        if not all(a[3] for a in allh):
+            if ok:
+                L.iexa_halo_destroy(h)
+            return False
+        for q, (bx, o, bf, _) in enumerate(allh):
+            if q == self.rank:
+                continue
+            ax, af = (C.c_ubyte * 64).from_buffer_copy(bx), (C.c_ubyte * 64).from_buffer_copy(bf)
+            if L.iexa_halo_connect(h, q, ax, o, af) != 0:
+                ok = False
+        _, recv, send = self.x_partition()
+        for r, ivs in send.items():
+            a = np.ascontiguousarray(np.array(ivs, dtype=np.int64).reshape(-1))
+            ok = ok and L.iexa_halo_set_sends(h, r, len(ivs), a.ctypes.data) == 0
+        rp = np.ascontiguousarray(np.array(sorted(recv), dtype=np.int32))
+        ok = ok and L.iexa_halo_set_recvs(h, len(rp), rp.ctypes.data if len(rp) else None) == 0
+        flag = torch.tensor([1.0 if ok else 0.0], device=x.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if flag.item() < 1.0:
+            L.iexa_halo_destroy(h)
+            return False
+        self._peer = (h, x.data_ptr())
+        self._red = torch.zeros(1024, dtype=torch.float64, device=x.device)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        return True
+
+    def peer_status(self) -> int:
+        return int(self.model.L.iexa_halo_status(self._peer[0])) if self._peer else 0
+
+    def halo_entries(self) -> int:
+        _, recv, _ = self.x_partition()
+        return sum(hi - lo for v in recv.values() for lo, hi in v)
+
+    def close_peer_halo(self):
+        if self._peer:
+            self.model.L.iexa_halo_destroy(self._peer[0])
+            self._peer = None
+
+    def allreduce_obj_grad_(self, f_dev, g):
+        """the collective part of obj + grad! in ONE reduction: [f, g[shared]] summed over the ranks, in place (f_dev: 1-element
+        CUDA tensor holding this rank's objective partial, g: this rank's dense gradient partial).  Small payloads go
+        through the peer-memory all-reduce (deterministic, one kernel), larger ones through NCCL."""
+        if self.world == 1:
+            return
+        torch, dist = self.torch, self.dist
+        if self.shared_all:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+            if self._peer:
+                _lib.check(self.model.L, self.model.L.iexa_halo_allreduce_small(self._peer[0], C.c_void_p(f_dev.data_ptr()), 1,
+                                                                                 C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)))
+            else:
+                dist.all_reduce(f_dev, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        ns = len(self.shared_idx)
+        if self._shared_t is None or self._shared_t.device != g.device:
+            self._shared_t = torch.from_numpy(self.shared_idx).to(g.device)
+        if self._peer and ns + 1 <= 1024:
+            buf = self._red[:ns + 1]
+            buf[0:1] = f_dev
+            if ns:
+                buf[1:] = g[self._shared_t]
+            _lib.check(self.model.L, self.model.L.iexa_halo_allreduce_small(self._peer[0], C.c_void_p(buf.data_ptr()), ns + 1,
+                                                                             C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)))
+        else:
+            buf = torch.cat([f_dev, g[self._shared_t]]) if ns else f_dev
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        f_dev.copy_(buf[0:1])
+        if ns:
+            g[self._shared_t] = buf[1:]
+
     def exchange_x(self, x):
         """make every range of x this rank READS current, given that each rank holds current values on the ranges it
-        OWNS: point-to-point sends of the shared slice and the shard-boundary halos (NCCL over NVLink on GPUs) — the
-        distributed solver's alternative to broadcasting the whole iterate."""
+        OWNS: the shared slice and the shard-boundary halos cross ranks — pushed straight into the readers' x over NVLink
+        peer memory by one small kernel (after ``enable_peer_halo``), else NCCL point-to-point sends — the distributed
+        solver's alternative to broadcasting the whole iterate."""
         if self.world == 1:
             return x
         torch, dist = self.torch, self.dist
+        if self._peer and isinstance(x, torch.Tensor) and x.data_ptr() == self._peer[1]:
+            _lib.check(self.model.L, self.model.L.iexa_halo_exchange(self._peer[0], C.c_void_p(x.data_ptr()),
+                                                                      C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+            return x
         _, recv, send = self.x_partition()
         xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(x)
         key = str(xt.device)
@@ -234,7 +333,10 @@ class ShardedExaModel:
             self._ev.grad_(x, g)
         else:
             _m.grad_(self.model, x, g)
-        if self.world > 1 and len(self.shared_idx):
+        if self.world > 1 and self.shared_all:
+            gt = g if isinstance(g, self.torch.Tensor) else self.torch.from_numpy(g)
+            self.dist.all_reduce(gt, op=self.dist.ReduceOp.SUM, group=self.group)
+        elif self.world > 1 and len(self.shared_idx):
             torch, dist = self.torch, self.dist
             gt = g if isinstance(g, torch.Tensor) else torch.from_numpy(g)
             if self._shared_t is None or self._shared_t.device != gt.device:

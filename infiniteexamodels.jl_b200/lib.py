@@ -35,8 +35,10 @@ SYMBOLS = [
     "iexa_add_obj", "iexa_finalize", "iexa_get_meta", "iexa_get_vector", "iexa_set_vector",
     "iexa_set_par", "iexa_set_par_stream", "iexa_get_par", "iexa_jac_structure", "iexa_hess_structure", "iexa_obj",
     "iexa_grad", "iexa_cons", "iexa_jac_coord", "iexa_hess_coord", "iexa_jprod", "iexa_jtprod",
-    "iexa_hprod", "iexa_obj_device", "iexa_host_register", "iexa_host_unregister", "iexa_segments", "iexa_shared_vars", "iexa_x_ranges", "iexa_algorithmic_bytes",
+    "iexa_hprod", "iexa_obj_device", "iexa_host_register", "iexa_host_unregister", "iexa_segments", "iexa_shared_vars", "iexa_shared_ranges", "iexa_host_x_bytes", "iexa_x_ranges", "iexa_algorithmic_bytes",
     "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_set_class_mode", "iexa_debug_codegen_compile",
+    "iexa_halo_create", "iexa_halo_export", "iexa_halo_connect", "iexa_halo_set_sends", "iexa_halo_set_recvs", "iexa_halo_exchange",
+    "iexa_halo_allreduce_small", "iexa_halo_status", "iexa_halo_destroy",
     "iexa_csr_create", "iexa_csr_create_keyed", "iexa_coo_locality", "iexa_csr_destroy", "iexa_csr_nnz", "iexa_csr_pattern", "iexa_csr_apply",
 ]
 
@@ -83,6 +85,8 @@ def _declare(L):
     sig("iexa_segments", _i64, _vp, _i32, _vp, _i64)
     sig("iexa_shared_vars", _i64, _vp, _vp, _i64)
     sig("iexa_x_ranges", _i64, _vp, _vp, _i64)
+    sig("iexa_shared_ranges", _i64, _vp, _vp, _i64)
+    sig("iexa_host_x_bytes", _i64, _vp)
     sig("iexa_algorithmic_bytes", _i64, _vp, _i32)
     sig("iexa_launches_per_call", _i32, _vp, _i32)
     sig("iexa_engine_note", C.c_char_p, _vp)
@@ -96,6 +100,15 @@ def _declare(L):
     sig("iexa_csr_nnz", _i64, _vp)
     sig("iexa_csr_pattern", _i32, _vp, _vp, _vp, _i32)
     sig("iexa_csr_apply", _i32, _vp, _vp, _vp, _i32, _vp)
+    sig("iexa_halo_create", _i32, C.POINTER(_vp), _i32, _i32, _i32)
+    sig("iexa_halo_export", _i32, _vp, _vp, _vp, C.POINTER(_i64), _vp)
+    sig("iexa_halo_connect", _i32, _vp, _i32, _vp, _i64, _vp)
+    sig("iexa_halo_set_sends", _i32, _vp, _i32, _i64, _vp)
+    sig("iexa_halo_set_recvs", _i32, _vp, _i32, _vp)
+    sig("iexa_halo_exchange", _i32, _vp, _vp, _vp)
+    sig("iexa_halo_allreduce_small", _i32, _vp, _vp, _i32, _vp)
+    sig("iexa_halo_status", _i64, _vp)
+    sig("iexa_halo_destroy", _i32, _vp)
     # test-only entry points of tests/hostcheck (absent from the product library)
     sig("hostcheck_eval", _i32, _vp, _i32, _vp, _vp, _dbl, _vp)
     sig("hostcheck_eval_local", _i32, _vp, _i32, _vp, _vp, _dbl, _vp)

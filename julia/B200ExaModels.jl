@@ -232,6 +232,13 @@ function set_parameter!(m::B200ExaModel, offset0::Integer, vals::AbstractArray{F
     check(ccall((:iexa_set_par, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), m.plan.h, offset0, length(v), v))
 end
 
+"the same update enqueued on the task-local CUDA stream (ordered like a callback: no device synchronisation)"
+function set_parameter_async!(m::B200ExaModel, offset0::Integer, vals::AbstractArray{Float64})
+    v = collect(vec(vals))
+    check(ccall((:iexa_set_par_stream, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Cvoid}),
+                m.plan.h, offset0, length(v), v, CUDA.stream().handle))
+end
+
 "`model.θ` (infiniteopt_backend.jl:479)"
 function Base.getproperty(m::B200ExaModel, s::Symbol)
     if s === :θ
@@ -282,6 +289,17 @@ function shared_vars(m::B200ExaModel)
     return out
 end
 
+"the same set as merged 0-based ranges (shard-boundary entries of shifted references and product-iterator indices included)"
+function shared_ranges(m::B200ExaModel)
+    n = ccall((:iexa_shared_ranges, LIB), Int64, (Ptr{Cvoid}, Ptr{IexaSegment}, Int64), m.plan.h, C_NULL, 0)
+    out = Vector{IexaSegment}(undef, max(n, 0))
+    n > 0 && ccall((:iexa_shared_ranges, LIB), Int64, (Ptr{Cvoid}, Ptr{IexaSegment}, Int64), m.plan.h, out, n)
+    return out
+end
+
+"bytes of x a host-memory callback uploads on this rank (the read ranges only when the model is sharded)"
+host_x_bytes(m::B200ExaModel) = ccall((:iexa_host_x_bytes, LIB), Int64, (Ptr{Cvoid},), m.plan.h)
+
 "the ranges of x this rank reads (own supports + shared variables + halos): what a distributed solver keeps current here"
 function x_ranges(m::B200ExaModel)
     n = ccall((:iexa_x_ranges, LIB), Int64, (Ptr{Cvoid}, Ptr{IexaSegment}, Int64), m.plan.h, C_NULL, 0)
@@ -289,6 +307,45 @@ function x_ranges(m::B200ExaModel)
     n > 0 && ccall((:iexa_x_ranges, LIB), Int64, (Ptr{Cvoid}, Ptr{IexaSegment}, Int64), m.plan.h, out, n)
     return out
 end
+
+# ---- x halo exchange + small all-reduce over NVLink peer memory (csrc/halo.cu; one Julia process per GPU) ---------------
+# Setup (collective): h = PeerHalo(device, rank, world); (hx, off, hf) = export_handles(h, x); ship them to every peer (MPI.jl /
+# Distributed); connect!(h, peer, hx_peer, off_peer, hf_peer); set_sends!/set_recvs! from the ranks' x_ranges.
+mutable struct PeerHalo
+    h::Ptr{Cvoid}
+end
+function PeerHalo(device::Integer, rank::Integer, world::Integer)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:iexa_halo_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32, Int32, Int32), r, device, rank, world))
+    p = PeerHalo(r[])
+    finalizer(p -> ccall((:iexa_halo_destroy, LIB), Int32, (Ptr{Cvoid},), p.h), p)
+    return p
+end
+function export_handles(p::PeerHalo, x::CuArray{Float64})
+    hx = zeros(UInt8, 64); hf = zeros(UInt8, 64); off = Ref{Int64}(0)
+    GC.@preserve x check(ccall((:iexa_halo_export, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}, Ref{Int64}, Ptr{UInt8}),
+                               p.h, _ptr(x), hx, off, hf))
+    return hx, off[], hf
+end
+connect!(p::PeerHalo, peer::Integer, hx::Vector{UInt8}, off::Integer, hf::Vector{UInt8}) =
+    check(ccall((:iexa_halo_connect, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}, Int64, Ptr{UInt8}), p.h, peer, hx, off, hf))
+"lo_hi: 0-based [lo, hi) pairs of x this rank owns and `peer` reads"
+set_sends!(p::PeerHalo, peer::Integer, lo_hi::Vector{Int64}) =
+    check(ccall((:iexa_halo_set_sends, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Ptr{Int64}), p.h, peer, length(lo_hi) ÷ 2, lo_hi))
+set_recvs!(p::PeerHalo, peers::Vector{Int32}) =
+    check(ccall((:iexa_halo_set_recvs, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}), p.h, length(peers), peers))
+"collective: push the shared variables / shard-boundary halos this rank owns into its readers' x (one kernel, no host sync)"
+function exchange!(p::PeerHalo, x::CuArray{Float64})
+    GC.@preserve x check(ccall((:iexa_halo_exchange, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), p.h, _ptr(x), _st(x)))
+    return x
+end
+"collective: buf .= sum over ranks (length <= 1024), summed in rank order — objective + shared gradient slice in one kernel"
+function allreduce_small!(p::PeerHalo, buf::CuArray{Float64})
+    GC.@preserve buf check(ccall((:iexa_halo_allreduce_small, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}),
+                                 p.h, _ptr(buf), length(buf), _st(buf)))
+    return buf
+end
+status(p::PeerHalo) = ccall((:iexa_halo_status, LIB), Int64, (Ptr{Cvoid},), p.h)
 
 # ---- KKT assembly: COO -> CSR value map for cuDSS (replaces MadNLPGPU's transfer! kernel) ------------------------------
 mutable struct CsrMap

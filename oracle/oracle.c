@@ -64,6 +64,7 @@ typedef struct {
   int *comp1, *comp2;       /* occurrence -> compressed slot (0-based) */
   int *slot1_idx;           /* slot -> canonical index id */
   int *slot2_i, *slot2_j;
+  int borrowed;             /* iterator columns belong to the caller (orc_add_gen_borrow) */
 } ogen;
 
 typedef struct {
@@ -113,8 +114,8 @@ void orc_free(omodel *m) {
   for (int i = 0; i < m->ngen; ++i) {
     ogen *g = &m->g[i];
     free(g->nd); free(g->kind); free(g->c1); free(g->c2); free(g->idx); free(g->canon);
-    for (int j = 0; j < g->n_int; ++j) free(g->ic[j]);
-    for (int j = 0; j < g->n_fp; ++j) free(g->fc[j]);
+    for (int j = 0; j < g->n_int && !g->borrowed; ++j) free(g->ic[j]);
+    for (int j = 0; j < g->n_fp && !g->borrowed; ++j) free(g->fc[j]);
     free(g->ic); free(g->fc); free(g->comp1); free(g->comp2);
     free(g->slot1_idx); free(g->slot2_i); free(g->slot2_j);
   }
@@ -204,9 +205,9 @@ static int compress(const plist *l, int **comp, int **sa, int **sb) {
   return ns;
 }
 
-int orc_add_gen(omodel *m, int is_obj, const onode *nodes, int n_nodes, const oindex *idx, int n_idx,
-                int64_t K, int n_int, const int64_t *const *icols, int n_fp, const double *const *fcols,
-                double lcon, double ucon) {
+static int add_gen(omodel *m, int is_obj, const onode *nodes, int n_nodes, const oindex *idx, int n_idx,
+                   int64_t K, int n_int, const int64_t *const *icols, int n_fp, const double *const *fcols,
+                   double lcon, double ucon, int borrow) {
   if (m->ngen == m->cap) { m->cap = m->cap ? 2 * m->cap : 16; m->g = (ogen *)realloc(m->g, sizeof(ogen) * (size_t)m->cap); }
   ogen *g = &m->g[m->ngen];
   memset(g, 0, sizeof *g);
@@ -219,8 +220,15 @@ int orc_add_gen(omodel *m, int is_obj, const onode *nodes, int n_nodes, const oi
   g->n_int = n_int; g->n_fp = n_fp;
   g->ic = (int64_t **)malloc(sizeof(void *) * (size_t)(n_int + 1));
   g->fc = (double **)malloc(sizeof(void *) * (size_t)(n_fp + 1));
-  for (int j = 0; j < n_int; ++j) { g->ic[j] = (int64_t *)malloc(sizeof(int64_t) * (size_t)(K + 1)); memcpy(g->ic[j], icols[j], sizeof(int64_t) * (size_t)K); }
-  for (int j = 0; j < n_fp; ++j) { g->fc[j] = (double *)malloc(sizeof(double) * (size_t)(K + 1)); memcpy(g->fc[j], fcols[j], sizeof(double) * (size_t)K); }
+  g->borrowed = borrow;
+  for (int j = 0; j < n_int; ++j) {
+    if (borrow) { g->ic[j] = (int64_t *)icols[j]; continue; }
+    g->ic[j] = (int64_t *)malloc(sizeof(int64_t) * (size_t)(K + 1)); memcpy(g->ic[j], icols[j], sizeof(int64_t) * (size_t)K);
+  }
+  for (int j = 0; j < n_fp; ++j) {
+    if (borrow) { g->fc[j] = (double *)fcols[j]; continue; }
+    g->fc[j] = (double *)malloc(sizeof(double) * (size_t)(K + 1)); memcpy(g->fc[j], fcols[j], sizeof(double) * (size_t)K);
+  }
   g->kind = (int *)calloc((size_t)n_nodes, sizeof(int));
   g->c1 = (int *)calloc((size_t)n_nodes, sizeof(int));
   g->c2 = (int *)calloc((size_t)n_nodes, sizeof(int));
@@ -246,6 +254,18 @@ int orc_add_gen(omodel *m, int is_obj, const onode *nodes, int n_nodes, const oi
   free(l1.a); free(l1.b); free(l2.a); free(l2.b);
   m->ngen++;
   return m->ngen - 1;
+}
+
+int orc_add_gen(omodel *m, int is_obj, const onode *nodes, int n_nodes, const oindex *idx, int n_idx,
+                int64_t K, int n_int, const int64_t *const *icols, int n_fp, const double *const *fcols,
+                double lcon, double ucon) {
+  return add_gen(m, is_obj, nodes, n_nodes, idx, n_idx, K, n_int, icols, n_fp, fcols, lcon, ucon, 0);
+}
+/* same, but the iterator columns stay owned by the caller (generators over the same iterator share them) */
+int orc_add_gen_borrow(omodel *m, int is_obj, const onode *nodes, int n_nodes, const oindex *idx, int n_idx,
+                       int64_t K, int n_int, const int64_t *const *icols, int n_fp, const double *const *fcols,
+                       double lcon, double ucon) {
+  return add_gen(m, is_obj, nodes, n_nodes, idx, n_idx, K, n_int, icols, n_fp, fcols, lcon, ucon, 1);
 }
 
 /* offsets (nlp.jl restatement): rows and Jacobian slots over constraint generators in emission

@@ -39,6 +39,8 @@ def lib():
         L.orc_set_theta.argtypes = [vp, i64, i64, vp]
         L.orc_add_gen.argtypes = [vp, i32, vp, i32, vp, i32, i64, i32, vp, i32, vp, dbl, dbl]
         L.orc_add_gen.restype = i32
+        L.orc_add_gen_borrow.argtypes = L.orc_add_gen.argtypes
+        L.orc_add_gen_borrow.restype = i32
         L.orc_finalize.argtypes = [vp]
         for f in ("orc_ncon", "orc_nnzj", "orc_nnzh"):
             getattr(L, f).argtypes = [vp]
@@ -87,16 +89,21 @@ class OracleModel:
         self.lvar, self.uvar = core.lvar_vec.copy(), core.uvar_vec.copy()
         lcon, ucon = [], []
         self._keep = []
+        cols = {}   # iterator -> materialised columns, shared by every generator over it (kept alive by self._keep)
         for g in core.gens:
-            ic, fc = g.itr.materialise()
-            ic = [np.ascontiguousarray(c, dtype=np.int64) for c in ic]
-            fc = [np.ascontiguousarray(c, dtype=np.float64) for c in fc]
-            icp = (C.c_void_p * max(len(ic), 1))(*[c.ctypes.data for c in ic])
-            fcp = (C.c_void_p * max(len(fc), 1))(*[c.ctypes.data for c in fc])
+            if id(g.itr) not in cols:
+                ic, fc = g.itr.materialise()
+                ic = [np.ascontiguousarray(c, dtype=np.int64) for c in ic]
+                fc = [np.ascontiguousarray(c, dtype=np.float64) for c in fc]
+                icp = (C.c_void_p * max(len(ic), 1))(*[c.ctypes.data for c in ic])
+                fcp = (C.c_void_p * max(len(fc), 1))(*[c.ctypes.data for c in fc])
+                cols[id(g.itr)] = (ic, fc, icp, fcp)
+                self._keep.append((g.itr, ic, fc, icp, fcp))
+            ic, fc, icp, fcp = cols[id(g.itr)]
             nodes = np.ascontiguousarray(g.tape.nodes)
             index = np.ascontiguousarray(g.tape.index)
-            L.orc_add_gen(self.h, int(g.is_obj), _p(nodes), len(nodes), _p(index), len(index),
-                          g.itr.K, len(ic), icp, len(fc), fcp, g.lcon, g.ucon)
+            L.orc_add_gen_borrow(self.h, int(g.is_obj), _p(nodes), len(nodes), _p(index), len(index),
+                                 g.itr.K, len(ic), icp, len(fc), fcp, g.lcon, g.ucon)
             if not g.is_obj:
                 lcon.append(np.full(g.itr.K, g.lcon)); ucon.append(np.full(g.itr.K, g.ucon))
         L.orc_finalize(self.h)

@@ -43,7 +43,36 @@ def _case_core(case):
     if case.startswith("fuzz"):
         import test_fuzz
         return test_fuzz.random_model(int(case[4:]), K1=130, K2=4)[0]
+    if case in ("probe_shift", "probe_product"):
+        return _probe(case)
     return {"ode_5x5": models.ode_5x5, "quadrotor": lambda: models.quadrotor(13, "oc"), "farmer": lambda: models.farmer(23)}[case]()
+
+
+def _probe(case):
+    """objectives whose gradient entries are written by several ranks WITHOUT a constant index (the shared set must come
+    from index ranges, not from constant indices): (A) (y[i+1] - y[i])^2 over i = 1..T-1 — the entry at every shard
+    boundary is written by both neighbours; (B) w[s] * z[t]^2 over the product iterator (t, s) — every z[t] is written
+    by every rank that holds some scenario s."""
+    import numpy as np
+    from iexa_b200.core import ExaCore, Itr
+    from iexa_b200.expr import DataSource, abs2
+    core = ExaCore(minimize=True)
+    ds = DataSource()
+    T = 17
+    if case == "probe_shift":
+        y = core.add_var(T, start=0.3)
+        it = Itr(T - 1, {"group_idx1": np.arange(1, T)}, {"c": np.linspace(1, 2, T - 1)})
+        i = ds.group_idx1.idx()
+        core.add_obj(ds.c * abs2(y[i + 1] - y[i]), it)
+        core.add_con(y[ds.group_idx1], Itr(T, {"group_idx1": np.arange(1, T + 1)}, {}), -1.0, 1.0)
+    else:
+        S = 5
+        z = core.add_var(T, start=0.4)
+        it_t = Itr(T, {"group_idx1": np.arange(1, T + 1)}, {})
+        it_s = Itr(S, {"group_idx2": np.arange(1, S + 1)}, {"w": np.linspace(0.5, 1.5, S)})
+        core.add_obj(ds.w * abs2(z[ds.group_idx1]), Itr.product([it_t, it_s]))
+        core.add_con(z[ds.group_idx1], it_t, -1.0, 1.0)
+    return core
 
 
 def _worker(rank, world, port, case, q):
@@ -76,7 +105,7 @@ def _worker(rank, world, port, case, q):
         cover = 0
         for s0, ln in sm.x_ranges():
             xp[s0:s0 + ln] = x[s0:s0 + ln]; cover += ln
-        assert world == 1 or case == "ode_5x5" or case.startswith("fuzz") or cover < core.nvar, "x ranges are not a proper subset"
+        assert world == 1 or case in ("ode_5x5", "probe_product") or case.startswith("fuzz") or cover < core.nvar, "x ranges are not a proper subset"
         c2 = sm.cons_(xp, np.zeros(max(sm.model.loc_ncon, 1)))
         jv2 = sm.jac_coord_(xp, np.zeros(max(sm.model.loc_nnzj, 1)))
         hv2 = sm.hess_coord_(xp, yl, np.zeros(max(sm.model.loc_nnzh, 1)), 0.7)
@@ -100,14 +129,25 @@ def _worker(rank, world, port, case, q):
         assert np.array_equal(d, y[gcon.row_offset:gcon.row_offset + gcon.itr.K]), "gather_rows"
         # owned gradient entries: sum over ranks of the per-rank g must double-count ONLY the shared slice
         gsum = torch.from_numpy(g.copy()); dist.all_reduce(gsum)
+        shared = np.arange(core.nvar) if sm.shared_all else sm.shared_idx
+        # ... and PER RANK: a non-shared entry is either complete on this rank (it is the only contributor) or exactly zero —
+        # never a partial sum (ShardedExaModel.grad_'s contract; a rank-sum check alone is blind to that)
+        from oracle.oracle import OracleModel
+        ref = OracleModel(core).grad(x)
+        excl = np.ones(core.nvar, dtype=bool); excl[shared] = False
+        tol = 1e-13 + 1e-12 * np.abs(ref)
+        whole, zero = np.abs(g - ref) <= tol, g == 0.0
+        assert (whole | zero)[excl].all(), f"rank {rank}: partial sums outside the shared set at {np.flatnonzero(excl & ~(whole | zero))[:8]}"
+        assert (np.abs(g - ref) <= tol)[shared].all(), f"rank {rank}: shared entries incomplete after grad_"
         if rank == 0:
-            q.put(dict(f=f, gfull=gfull, c=cg, j=jg, h=hg, gsum=gsum.numpy(), shared=sm.shared_idx, g=g,
+            q.put(dict(f=f, gfull=gfull, c=cg, j=jg, h=hg, gsum=gsum.numpy(), shared=shared, g=g,
                        loc=(sm.model.loc_ncon, sm.model.loc_nnzj, sm.model.loc_nnzh)))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,world", [("ode_5x5", 2), ("quadrotor", 2), ("quadrotor", 3), ("farmer", 2), ("fuzz7", 3), ("fuzz11", 2)])
+@pytest.mark.parametrize("case,world", [("ode_5x5", 2), ("quadrotor", 2), ("quadrotor", 3), ("farmer", 2), ("fuzz7", 3), ("fuzz11", 2),
+                                        ("probe_shift", 2), ("probe_shift", 3), ("probe_product", 2)])
 def test_sharded_evaluation_matches_oracle(case, world, hostcheck_lib):
     import torch.multiprocessing as mp
     sys.path.insert(0, ROOT)
@@ -149,5 +189,7 @@ def test_sharded_evaluation_matches_oracle(case, world, hostcheck_lib):
     assert np.allclose(res["g"][sh], ref[sh], rtol=1e-12, atol=1e-13)
     expect = ref.copy(); expect[sh] *= world
     assert np.allclose(res["gsum"], expect, rtol=1e-12, atol=1e-13)
-    if case in ("ode_5x5", "farmer"):
-        assert len(sh) >= 1  # z / the first-stage x are shared by every support
+    if case in ("ode_5x5", "probe_shift", "probe_product"):
+        assert len(sh) >= 1  # z is shared by every support; shard-boundary / product-iterator entries
+    if case == "farmer":
+        assert len(sh) == 0  # the first-stage x enter the objective through length-1 generators only: all on rank 0
