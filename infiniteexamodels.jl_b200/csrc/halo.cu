@@ -7,9 +7,9 @@
 // for 180 doubles, more than the sharded evaluation itself (0.07 ms).  Here every rank maps its peers' x buffers and a
 // small flag block into its address space once (cudaIpc*), and one exchange is ONE small kernel per rank:
 //
-//   1. ack   : tell every owner I receive from that I have finished reading the halo of the previous epoch
-//              (stream order: all my callbacks of the previous iterate precede this kernel);
-//   2. push  : for every reader of mine — wait for its ack, store my boundary values straight into ITS x at their global
+//   1. ready : tell every owner I receive from that my x is ready to take the halo of THIS epoch (stream order: all my
+//              callbacks of the previous iterate, and whatever rewrote my part of x since, precede this kernel);
+//   2. push  : for every reader of mine — wait for its ready flag, store my boundary values straight into ITS x at their global
 //              positions (peer stores over NVLink), __threadfence_system(), raise my flag in its flag block;
 //   3. wait  : until every owner I receive from has raised its flag for this epoch.
 //
@@ -39,7 +39,7 @@ constexpr int MAX_WORLD = 64;
 // flag block of one rank (device memory, mapped by every peer)
 struct Block {
   unsigned long long data_flag[MAX_WORLD];      // [src]    src has pushed its halo of epoch (value) into my x
-  unsigned long long ack_flag[MAX_WORLD];       // [reader] reader has finished reading the halo of epoch (value) I pushed
+  unsigned long long ack_flag[MAX_WORLD];       // [reader] reader's x is ready to receive the halo of epoch (value)
   unsigned long long red_flag[2][MAX_WORLD];    // [parity][src]
   unsigned long long status;                    // != 0: a bounded wait expired
   double red_buf[2][MAX_WORLD][RED_MAX];
@@ -77,13 +77,13 @@ __device__ bool wait_ge(const unsigned long long *p, unsigned long long want, un
 __global__ void __launch_bounds__(256) halo_exchange_kernel(Dev d, const double *__restrict__ x, unsigned long long epoch) {
   Block *me = d.blk[d.rank];
   const int tid = threadIdx.x;
-  // 1. acks (nothing is waited for before them: no circular wait between ranks)
-  if (tid < d.nrecv_peers) st_flag(&d.blk[d.recv_peers[tid]]->ack_flag[d.rank], epoch - 1);
+  // 1. ready flags (nothing is waited for before them: no circular wait between ranks)
+  if (tid < d.nrecv_peers) st_flag(&d.blk[d.recv_peers[tid]]->ack_flag[d.rank], epoch);
   // 2. pushes: one reader after the other (a reader gets a few dozen doubles)
   __shared__ int ok;
   for (int sp = 0; sp < d.nsend_peers; ++sp) {
     const int peer = d.send_peers[sp];
-    if (tid == 0) ok = wait_ge(&me->ack_flag[peer], epoch - 1, &me->status, 1000 + peer) ? 1 : 0;
+    if (tid == 0) ok = wait_ge(&me->ack_flag[peer], epoch, &me->status, 1000 + peer) ? 1 : 0;
     __syncthreads();
     if (ok) {
       double *__restrict__ px = d.x[peer];

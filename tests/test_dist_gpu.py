@@ -30,5 +30,6 @@ def test_sharded_callbacks_over_nccl_and_peer_memory(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-3000:]
+    err = "\n".join(l for l in r.stderr.splitlines() if not l.startswith(("W1", "W0", "*", "Setting OMP")))
+    assert r.returncode == 0, r.stdout[-3000:] + "\n" + err[-6000:]
     assert r.stdout.count(" OK ") >= 5, r.stdout[-3000:]
