@@ -132,6 +132,20 @@ int32_t iexa_version(void);
 int32_t iexa_plan_create(iexa_plan **out, int32_t minimize);
 int32_t iexa_plan_destroy(iexa_plan *p);
 
+/* Plan options — set BEFORE the first iexa_add_con / iexa_add_obj.
+ *   IEXA_OPT_SLOT_ORDER: the order in which the symbolic reverse passes meet the Var leaves decides which COO slot a
+ *     variable (pair) gets inside a generator.  ExaModels 0.11.2 (Project.toml:23; reached from transform.jl:458,559,597)
+ *     is absent from the reference tree, so its order is a hypothesis — it is therefore DATA here, not
+ *     code: LEFT_TO_RIGHT (default; children inner1 then inner2) or RIGHT_TO_LEFT (inner2 then inner1).  A dump of the
+ *     real package (julia/dump_golden.jl) only has to name the policy; kernels do not change.
+ *   IEXA_OPT_STRICT_IEEE: 1 = structural zeros are multiplied at run time (0*x, 0/x are not folded unless x is a literal),
+ *     so NaN / Inf propagate through the derivative formulas exactly as in a run-time AD that multiplies the numbers
+ *     (tests/test_nan_semantics.py: NaN pattern identical to the oracle on poisoned inputs for every BASELINE config);
+ *     0 (default) folds them: identical results for finite inputs, a subset of the NaNs otherwise.               */
+enum { IEXA_OPT_SLOT_ORDER = 1, IEXA_OPT_STRICT_IEEE = 2 };
+enum { IEXA_SLOT_ORDER_LEFT_TO_RIGHT = 0, IEXA_SLOT_ORDER_RIGHT_TO_LEFT = 1 };
+int32_t iexa_set_option(iexa_plan *p, int32_t key, int64_t value);
+
 /* ExaModels.add_var  — transform.jl:113 (finite), :154 (infinite + derivative vars).
  * x0/lvar/uvar may be NULL (0, -inf, +inf).  offset_out: 0-based offset of the block. */
 int32_t iexa_add_var(iexa_plan *p, int64_t n, const double *x0, const double *lvar,

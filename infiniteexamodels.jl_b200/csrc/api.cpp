@@ -50,6 +50,24 @@ int32_t iexa_plan_destroy(iexa_plan *p) {
   GUARD_END
 }
 
+int32_t iexa_set_option(iexa_plan *p, int32_t key, int64_t value) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (p->plan.finalized || !p->plan.objs.empty() || !p->plan.cons.empty())
+    return fail(IEXA_ERR_STATE, "options must be set before the first generator is added");
+  switch (key) {
+    case IEXA_OPT_SLOT_ORDER:
+      if (value != IEXA_SLOT_ORDER_LEFT_TO_RIGHT && value != IEXA_SLOT_ORDER_RIGHT_TO_LEFT) return fail(IEXA_ERR_INVALID, "unknown slot-order policy");
+      p->plan.opt_slot_order = (int)value;
+      return IEXA_OK;
+    case IEXA_OPT_STRICT_IEEE:
+      p->plan.opt_strict = value != 0;
+      return IEXA_OK;
+    default: return fail(IEXA_ERR_INVALID, "unknown option");
+  }
+  GUARD_END
+}
+
 int32_t iexa_add_var(iexa_plan *p, int64_t n, const double *x0, const double *lvar, const double *uvar,
                      int64_t *offset_out) {
   GUARD_BEGIN

@@ -73,6 +73,11 @@ inline double host_unary(int32_t op, double x) {
 class Dag {
  public:
   std::vector<DNode> nodes;
+  // IEEE-strict mode: 0*x and 0/x are NOT folded to 0 unless x is a literal, so a structural zero times Inf / NaN
+  // evaluates to NaN exactly like a run-time AD that multiplies the numbers (ExaModels' reverse passes compute
+  // adj2*y^2 + adj*h with literal zeros in y / h).  Everything else that is folded is exact for every input:
+  // x+0, x*1, x*(-1), x/1, pow(x,1), pow(x,2) = x*x, and pow(x,0) = 1 (IEEE: also for NaN and Inf).
+  bool strict = false;
 
   int cnst(double c) { return intern(D_CONST, 0, 0, c); }
   int field(int col) { return intern(D_FIELD, col, 0, 0.0); }
@@ -111,8 +116,8 @@ class Dag {
   }
   int mul(int a, int b) {
     if (is_const(a) && is_const(b)) return cnst(cval(a) * cval(b));
-    // exact for finite operands; a structural zero of the reference evaluates to 0 as well
-    if (is_c(a, 0.0) || is_c(b, 0.0)) return cnst(0.0);
+    // exact for finite operands only: kept as a multiplication in strict mode
+    if (!strict && (is_c(a, 0.0) || is_c(b, 0.0))) return cnst(0.0);
     if (is_c(a, 1.0)) return b;
     if (is_c(b, 1.0)) return a;
     if (is_c(a, -1.0)) return neg(b);
@@ -123,7 +128,7 @@ class Dag {
   int div(int a, int b) {
     if (is_const(a) && is_const(b)) return cnst(cval(a) / cval(b));
     if (is_c(b, 1.0)) return a;
-    if (is_c(a, 0.0)) return cnst(0.0);
+    if (!strict && is_c(a, 0.0)) return cnst(0.0);
     return intern(D_DIV, a, b, 0.0);
   }
   int neg(int a) {

@@ -662,7 +662,7 @@ class CudaEngine : public Engine {
         int64_t n = G.k1 - G.k0;
         const int64_t SB = spec_block();
         int64_t nb = (n + SB - 1) / SB;
-        const int64_t ninst = G.is_class ? ((int64_t)G.inst_gens.size() + class_chunk() - 1) / class_chunk() : 1; // class groups: one block row per CHUNK of instances
+        const int64_t ninst = G.is_class ? ((int64_t)G.n_inst() + class_chunk() - 1) / class_chunk() : 1; // class groups: one block row per CHUNK of instances
         for (int64_t q = 0; q < ninst; ++q)
           for (int64_t b = 0; b < nb; ++b) ord.push_back(Ord{(b + 0.5) / (double)nb, gi, (int32_t)(q * nb + b)});
       }

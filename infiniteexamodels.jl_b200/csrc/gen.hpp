@@ -156,10 +156,17 @@ class GenCompiler {
     g.hv_slot = po.hv_slot;
   }
   bool is_obj_ = false; // objective generators have no rows: no jv / jtv programs
+  // Slot-ORDER policy (iexa_set_option IEXA_OPT_SLOT_ORDER).  The order in which the reverse passes meet the Var leaves
+  // decides which COO slot a variable (pair) gets; ExaModels' order is a hypothesis here until a dump of the real package
+  // exists ("parity unpinned") — so it is DATA: 0 = children left to right (inner1 then inner2), 1 = right
+  // to left (inner2 then inner1; cross pairs (inner2-leaf, inner1-leaf)).  Oracle and product honour the same value.
+  int order_ = 0;
+  void set_options(int slot_order, bool strict) { order_ = slot_order; dag_.strict = strict || dag_.strict; }
 
  private:
   void init(const iexa_node *nodes, const iexa_index *idx, int32_t n_idx) {
     if (n_ <= 0) throw std::invalid_argument("empty tape");
+    if (const char *e = getenv("IEXA_STRICT_IEEE")) dag_.strict = e[0] == '1';
     g.tape.assign(nodes, nodes + n_);
     if (n_idx > 0) g.raw_idx.assign(idx, idx + n_idx);
     canon_indices(idx, n_idx);
@@ -418,7 +425,10 @@ class GenCompiler {
     switch (in.kind) {
       case K_VAR: emit1(g.idx_map[g.tape[t].a], adj); break;
       case K_UN: jr(in.c1, dag_.mul(adj, in.y1)); break;
-      case K_BIN: jr(in.c1, dag_.mul(adj, in.y1)); jr(in.c2, dag_.mul(adj, in.y2)); break;
+      case K_BIN:
+        if (order_ == 0) { jr(in.c1, dag_.mul(adj, in.y1)); jr(in.c2, dag_.mul(adj, in.y2)); }
+        else { jr(in.c2, dag_.mul(adj, in.y2)); jr(in.c1, dag_.mul(adj, in.y1)); }
+        break;
       default: break;
     }
   }
@@ -441,19 +451,38 @@ class GenCompiler {
     } else s = it->second;
     slot2_[s] = dag_.add(slot2_[s], value);
   }
-  void hr0(int t, int adj, int adj2) {
+  // hrpass0: the top-level pass carries NO second-order adjoint ("adj2 == 0, no cross term"): through
+  // +, -, const*subtree only the first-order adjoint is pushed down, and the FIRST nonlinear node hands its children
+  // adj*h directly — not 0*y^2 + adj*h, which would turn an infinite local partial into NaN where the reference has none
+  void hr0(int t, int adj) {
     const Info &in = info_[t];
     Dag &d = dag_;
     switch (in.pass) {
-      case P_KEEP: hr0(in.c1, adj, adj2); return;
-      case P_FLIP: hr0(in.c1, d.neg(adj), adj2); return;
-      case P_SCALE: hr0(in.c1, d.mul(adj, in.y1), d.mul(adj2, d.sq(in.y1))); return;
-      case P_ADD: hr0(in.c1, adj, adj2); hr0(in.c2, adj, adj2); return;
-      case P_SUB: hr0(in.c1, adj, adj2); hr0(in.c2, d.neg(adj), adj2); return;
+      case P_KEEP: hr0(in.c1, adj); return;
+      case P_FLIP: hr0(in.c1, d.neg(adj)); return;
+      case P_SCALE: hr0(in.c1, d.mul(adj, in.y1)); return;
+      case P_ADD: case P_SUB: {
+        const int a2 = in.pass == P_SUB ? d.neg(adj) : adj;
+        if (order_ == 0) { hr0(in.c1, adj); hr0(in.c2, a2); } else { hr0(in.c2, a2); hr0(in.c1, adj); }
+        return;
+      }
       default: break;
     }
-    if (in.kind == K_VAR || in.kind == K_CONSTCLASS) return; // linear leaf: no Hessian slot
-    hr(t, adj, adj2);
+    switch (in.kind) { // linear leaves: no Hessian slot
+      case K_UN: hr(in.c1, d.mul(adj, in.y1), d.mul(adj, in.h11)); break;
+      case K_BIN:
+        if (order_ == 0) {
+          hr(in.c1, d.mul(adj, in.y1), d.mul(adj, in.h11));
+          hr(in.c2, d.mul(adj, in.y2), d.mul(adj, in.h22));
+          hdr(in.c1, in.c2, d.mul(adj, in.h12));
+        } else {
+          hr(in.c2, d.mul(adj, in.y2), d.mul(adj, in.h22));
+          hr(in.c1, d.mul(adj, in.y1), d.mul(adj, in.h11));
+          hdr(in.c2, in.c1, d.mul(adj, in.h12));
+        }
+        break;
+      default: break;
+    }
   }
   void hr(int t, int adj, int adj2) {
     const Info &in = info_[t];
@@ -465,47 +494,52 @@ class GenCompiler {
         break;
       case K_BIN: {
         int cross = d.add(d.mul(d.mul(adj2, in.y1), in.y2), d.mul(adj, in.h12));
-        hr(in.c1, d.mul(adj, in.y1), d.add(d.mul(adj2, d.sq(in.y1)), d.mul(adj, in.h11)));
-        hr(in.c2, d.mul(adj, in.y2), d.add(d.mul(adj2, d.sq(in.y2)), d.mul(adj, in.h22)));
-        hdr(in.c1, in.c2, cross);
+        if (order_ == 0) {
+          hr(in.c1, d.mul(adj, in.y1), d.add(d.mul(adj2, d.sq(in.y1)), d.mul(adj, in.h11)));
+          hr(in.c2, d.mul(adj, in.y2), d.add(d.mul(adj2, d.sq(in.y2)), d.mul(adj, in.h22)));
+          hdr(in.c1, in.c2, cross);
+        } else {
+          hr(in.c2, d.mul(adj, in.y2), d.add(d.mul(adj2, d.sq(in.y2)), d.mul(adj, in.h22)));
+          hr(in.c1, d.mul(adj, in.y1), d.add(d.mul(adj2, d.sq(in.y1)), d.mul(adj, in.h11)));
+          hdr(in.c2, in.c1, cross);
+        }
         break;
       }
       default: break;
     }
   }
+  // cross pass over two subtrees: every (leaf of t1, leaf of t2) pair, children visited in the policy's order
   void hdr(int t1, int t2, int adj) {
     const Info &a = info_[t1], &b = info_[t2];
     Dag &d = dag_;
     if (a.kind == K_VAR && b.kind == K_VAR) {
       int32_t u1 = g.idx_map[g.tape[t1].a], u2 = g.idx_map[g.tape[t2].a];
       emit2(u1, u2, d.mul(adj, d.sel2(u1, u2)));
-    } else if (a.kind == K_UN && b.kind == K_UN) {
-      hdr(a.c1, b.c1, d.mul(d.mul(adj, a.y1), b.y1));
-    } else if (a.kind == K_UN && b.kind == K_BIN) {
-      hdr(a.c1, b.c1, d.mul(d.mul(adj, a.y1), b.y1));
-      hdr(a.c1, b.c2, d.mul(d.mul(adj, a.y1), b.y2));
-    } else if (a.kind == K_BIN && b.kind == K_UN) {
-      hdr(a.c1, b.c1, d.mul(d.mul(adj, a.y1), b.y1));
-      hdr(a.c2, b.c1, d.mul(d.mul(adj, a.y2), b.y1));
-    } else if (a.kind == K_BIN && b.kind == K_BIN) {
-      hdr(a.c1, b.c1, d.mul(d.mul(adj, a.y1), b.y1));
-      hdr(a.c1, b.c2, d.mul(d.mul(adj, a.y1), b.y2));
-      hdr(a.c2, b.c1, d.mul(d.mul(adj, a.y2), b.y1));
-      hdr(a.c2, b.c2, d.mul(d.mul(adj, a.y2), b.y2));
-    } else if (a.kind == K_VAR && b.kind == K_UN) {
-      hdr(t1, b.c1, d.mul(adj, b.y1));
-    } else if (a.kind == K_VAR && b.kind == K_BIN) {
-      hdr(t1, b.c1, d.mul(adj, b.y1));
-      hdr(t1, b.c2, d.mul(adj, b.y2));
-    } else if (a.kind == K_UN && b.kind == K_VAR) {
-      hdr(a.c1, t2, d.mul(adj, a.y1));
-    } else if (a.kind == K_BIN && b.kind == K_VAR) {
-      hdr(a.c1, t2, d.mul(adj, a.y1));
-      hdr(a.c2, t2, d.mul(adj, a.y2));
+      return;
     }
+    // (child, local partial) lists; a Var leaf stands for itself with partial 1
+    int ca[2], ya[2], na = 0, cb[2], yb[2], nb = 0;
+    auto kids = [&](const Info &n, int t, int *c, int *y, int &cnt) {
+      if (n.kind == K_VAR) { c[0] = t; y[0] = -1; cnt = 1; }
+      else if (n.kind == K_UN) { c[0] = n.c1; y[0] = n.y1; cnt = 1; }
+      else if (n.kind == K_BIN) {
+        if (order_ == 0) { c[0] = n.c1; y[0] = n.y1; c[1] = n.c2; y[1] = n.y2; }
+        else { c[0] = n.c2; y[0] = n.y2; c[1] = n.c1; y[1] = n.y1; }
+        cnt = 2;
+      } else cnt = 0;
+    };
+    kids(a, t1, ca, ya, na);
+    kids(b, t2, cb, yb, nb);
+    for (int i = 0; i < na; ++i)
+      for (int j = 0; j < nb; ++j) {
+        int v = adj;
+        if (ya[i] >= 0) v = d.mul(v, ya[i]);
+        if (yb[j] >= 0) v = d.mul(v, yb[j]);
+        hdr(ca[i], cb[j], v);
+      }
   }
   void second_order() {
-    if (!g.is_null) hr0(n_ - 1, dag_.w(wid_), dag_.cnst(0.0));
+    if (!g.is_null) hr0(n_ - 1, dag_.w(wid_));
     g.o2step = (int32_t)g.hess_slot.size();
   }
 

@@ -102,14 +102,26 @@ struct Group {
   // literal constants, index bases and output offsets, which become per-instance table entries.
   // This is what turns the reference's "one generator per bus / branch constraint" launch storm
   // (ESCAPE34/opf.jl:150-283) into a handful of kernel bodies with an instance axis.
+  // FUSED classes: classes with the same number of instances over the same iterator whose q-th instances read the same
+  // variables (the P / Q flow rows and the thermal limit of ONE branch: vm[f], vm[t], va[f], va[t], p, q) become the
+  // members of ONE class group — instance q evaluates the q-th generator of every member class in one program, so the
+  // shared loads and the sin / cos of the angle difference are done once per branch and scenario instead of once per row.
   bool is_class = false;
-  std::vector<int32_t> inst_gens;   // generator index of every instance (members[0] == inst_gens[0])
-  std::vector<int32_t> cpar_nodes;  // tape node ids whose literal differs between instances
+  std::vector<int32_t> inst_gens;   // [instance q][member j] -> generator index, flattened q * members.size() + j
+  std::vector<int64_t> inst_base;   // [instance q][group index slot] -> index base of that instance, flattened
+  std::vector<int32_t> cpar_nodes;  // per-instance constant c: tape node id ...
+  std::vector<int32_t> cpar_member; // ... of member cpar_member[c]
+  size_t n_inst() const { return members.empty() ? 0 : inst_gens.size() / members.size(); }
+  int32_t inst_gen(size_t q, size_t j) const { return inst_gens[q * members.size() + j]; }
 };
 
 struct Plan {
   bool minimize = true;
   bool finalized = false;
+  // iexa_set_option: slot-order policy of the symbolic passes (gen.hpp: GenCompiler::order_) and IEEE-strict folding
+  // (dag.hpp: Dag::strict); both must be chosen before the first generator is added
+  int opt_slot_order = 0;
+  bool opt_strict = false;
   std::vector<double> x0, lvar, uvar, theta;
   std::vector<HostColumn> columns;
   std::vector<Iterator> itrs;
@@ -202,6 +214,7 @@ struct Plan {
     const Iterator &it = itrs[itr];
     GenCompiler gc(nodes, n, idx, n_idx, (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size());
     gc.is_obj_ = is_obj;
+    gc.set_options(opt_slot_order, opt_strict);
     gc.compile();
     Generator g;
     g.itr = itr;
@@ -311,46 +324,101 @@ struct Plan {
           if (!classes.count(key)) order.push_back(key);
           classes[key].push_back((int32_t)gi);
         }
+        // super-classes: lists of classes whose q-th instances are fused (see Group::is_class)
+        std::vector<std::vector<const std::vector<int32_t> *>> supers;
+        const bool fuse = !getenv("IEXA_NO_CLASS_FUSION");
         for (const std::string &key : order) {
           const std::vector<int32_t> &inst = classes[key];
           if (inst.size() < min_inst) continue;
-          const Generator &g0 = gens[inst[0]];
+          bool placed = false;
+          for (size_t si = supers.size(); fuse && si-- > 0 && !placed;) {
+            auto &S = supers[si];
+            const Generator &a0 = gens[(*S[0])[0]], &b0 = gens[inst[0]];
+            if (a0.itr != b0.itr || S[0]->size() != inst.size()) continue;
+            int s1 = 0, s2 = 0;
+            size_t nodes = 0;
+            for (auto *c : S) { const Generator &g = gens[(*c)[0]]; s1 += g.c.o1step | 1; s2 += g.c.o2step | 1; nodes += g.c.tape.size(); }
+            if (s1 + (b0.c.o1step | 1) > max_slots || s2 + (b0.c.o2step | 1) > max_slots || 12 * (nodes + b0.c.tape.size()) > max_dag_nodes) continue;
+            // the q-th instances must share variables the same way for EVERY q: every pair of index slots that coincides
+            // in instance 0 (same terms, same base) coincides in all instances; and at least one pair does
+            bool shares = false, ok = true;
+            for (auto *c : S) {
+              const Generator &ga = gens[(*c)[0]];
+              for (size_t u = 0; u < ga.c.uidx.size() && ok; ++u)
+                for (size_t w = 0; w < b0.c.uidx.size() && ok; ++w) {
+                  if (!(ga.c.uidx[u] == b0.c.uidx[w])) continue;
+                  if (ga.c.int_cols.size() != b0.c.int_cols.size() || ga.c.int_cols != b0.c.int_cols) { ok = false; break; } // term column slots must mean the same columns
+                  shares = true;
+                  for (size_t q = 1; q < inst.size() && ok; ++q)
+                    ok = gens[(*c)[q]].c.uidx[u].base == gens[inst[q]].c.uidx[w].base;
+                }
+            }
+            if (ok && shares) { S.push_back(&inst); placed = true; }
+          }
+          if (!placed) supers.push_back({&inst});
+        }
+        for (auto &S : supers) {
+          const size_t m = S.size(), ninst = S[0]->size();
+          const Generator &g0 = gens[(*S[0])[0]];
           const Iterator &it = itrs[g0.itr];
           groups.emplace_back();
           Group &G = groups.back();
           G.is_obj = pass == 0; G.itr = g0.itr; G.K = g0.K; G.k0 = g0.k0; G.k1 = g0.k1;
-          G.is_class = true; G.inst_gens = inst; G.members.push_back(inst[0]);
-          // literals that differ between instances become parameters
-          std::vector<int32_t> cpar(g0.c.tape.size(), -1);
-          for (size_t n = 0; n < g0.c.tape.size(); ++n) {
-            if (g0.c.tape[n].op != IEXA_OP_CONST) continue;
-            bool same = true;
-            for (int32_t gi : inst) if (std::memcmp(&gens[gi].c.tape[n].c, &g0.c.tape[n].c, 8) != 0) { same = false; break; }
-            if (!same) { cpar[n] = (int32_t)G.cpar_nodes.size(); G.cpar_nodes.push_back((int32_t)n); }
-          }
+          G.is_class = true;
+          G.inst_gens.resize(ninst * m);
+          for (size_t q = 0; q < ninst; ++q) for (size_t j = 0; j < m; ++j) G.inst_gens[q * m + j] = (*S[j])[q];
           Dag dag;
-          GenCompiler gc(g0.c.tape.data(), (int32_t)g0.c.tape.size(), g0.c.raw_idx.data(), (int32_t)g0.c.raw_idx.size(),
-                         (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size(), G.ctx, dag, 0);
-          gc.cpar_of_node = &cpar;
-          gc.differentiate();
-          // a parameter that happens to be 0/1 in g0 must not have been folded: slot counts must match
-          if ((int)gc.slot1().size() != g0.c.o1step || (int)gc.slot2().size() != g0.c.o2step)
-            throw std::logic_error("shape class: sparsity of the parametrised program differs from its instances");
-          G.jac_slot.push_back(gc.g.jac_slot);
-          std::vector<int> o0{gc.val_root()};
-          G.outmap[0].push_back({0, 0});
-          for (size_t c = 0; c < gc.slot1().size(); ++c) G.outmap[1].push_back({0, (int32_t)c});
-          for (size_t c = 0; c < gc.slot2().size(); ++c) G.outmap[2].push_back({0, (int32_t)c});
-          G.prog[0] = schedule(dag, o0, G.ctx.uidx.size(), G.x_slots[0]);
-          G.prog[1] = schedule(dag, gc.slot1(), G.ctx.uidx.size(), G.x_slots[1]);
-          G.prog[2] = schedule(dag, gc.slot2(), G.ctx.uidx.size(), G.x_slots[2]);
-          {
+          std::vector<MemberSlots> mslots;
+          std::vector<int> o0;
+          std::vector<std::vector<int>> o12(2);
+          std::vector<std::vector<int32_t>> own2grp(m);
+          std::vector<std::vector<int32_t>> cpars(m);
+          for (size_t j = 0; j < m; ++j) {
+            const std::vector<int32_t> &inst = *S[j];
+            const Generator &gj = gens[inst[0]];
+            G.members.push_back(inst[0]);
+            // literals that differ between instances become parameters
+            std::vector<int32_t> &cpar = cpars[j];
+            cpar.assign(gj.c.tape.size(), -1);
+            for (size_t n = 0; n < gj.c.tape.size(); ++n) {
+              if (gj.c.tape[n].op != IEXA_OP_CONST) continue;
+              bool same = true;
+              for (int32_t gi : inst) if (std::memcmp(&gens[gi].c.tape[n].c, &gj.c.tape[n].c, 8) != 0) { same = false; break; }
+              if (!same) { cpar[n] = (int32_t)G.cpar_nodes.size(); G.cpar_nodes.push_back((int32_t)n); G.cpar_member.push_back((int32_t)j); }
+            }
+            GenCompiler gc(gj.c.tape.data(), (int32_t)gj.c.tape.size(), gj.c.raw_idx.data(), (int32_t)gj.c.raw_idx.size(),
+                           (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size(), G.ctx, dag, (int)j);
+            gc.cpar_of_node = &cpar;
+            gc.set_options(opt_slot_order, opt_strict);
+            gc.differentiate();
+            // a parameter that happens to be 0/1 in instance 0 must not have been folded: slot counts must match
+            if ((int)gc.slot1().size() != gj.c.o1step || (int)gc.slot2().size() != gj.c.o2step)
+              throw std::logic_error("shape class: sparsity of the parametrised program differs from its instances");
+            own2grp[j].assign(gj.c.uidx.size(), -1);
+            for (size_t i = 0; i < gj.c.idx_map.size(); ++i) own2grp[j][gj.c.idx_map[i]] = gc.g.idx_map[i];
+            G.jac_slot.push_back(gc.g.jac_slot);
+            o0.push_back(gc.val_root());
+            G.outmap[0].push_back({(int32_t)j, 0});
+            for (size_t c = 0; c < gc.slot1().size(); ++c) { o12[0].push_back(gc.slot1()[c]); G.outmap[1].push_back({(int32_t)j, (int32_t)c}); }
+            for (size_t c = 0; c < gc.slot2().size(); ++c) { o12[1].push_back(gc.slot2()[c]); G.outmap[2].push_back({(int32_t)j, (int32_t)c}); }
             MemberSlots ms;
-            ms.s1 = gc.slot1(); ms.s2 = gc.slot2(); ms.jac_slot = gc.g.jac_slot; ms.hess_slot = gc.g.hess_slot; ms.wid = 0;
-            finish_products(G, dag, {ms});
+            ms.s1 = gc.slot1(); ms.s2 = gc.slot2(); ms.jac_slot = gc.g.jac_slot; ms.hess_slot = gc.g.hess_slot; ms.wid = (int)j;
+            mslots.push_back(std::move(ms));
           }
+          const size_t nis = G.ctx.uidx.size();
+          G.inst_base.assign(ninst * nis, 0);
+          for (size_t q = 0; q < ninst; ++q)
+            for (size_t j = 0; j < m; ++j) {
+              const Generator &gq = gens[(*S[j])[q]];
+              for (size_t u = 0; u < own2grp[j].size(); ++u)
+                if (own2grp[j][u] >= 0) G.inst_base[q * nis + own2grp[j][u]] = gq.c.uidx[u].base;
+            }
+          G.prog[0] = schedule(dag, o0, nis, G.x_slots[0]);
+          G.prog[1] = schedule(dag, o12[0], nis, G.x_slots[1]);
+          G.prog[2] = schedule(dag, o12[1], nis, G.x_slots[2]);
+          finish_products(G, dag, mslots);
           G.dag_nodes = dag.nodes.size();
-          for (int32_t gi : inst) taken[gi] = 1;
+          for (auto *c : S) for (int32_t gi : *c) taken[gi] = 1;
         }
       }
       std::map<int32_t, int> open; // itr -> group index
@@ -387,6 +455,7 @@ struct Plan {
         int mpos = (int)G.members.size();
         GenCompiler gc(g.c.tape.data(), (int32_t)g.c.tape.size(), g.c.raw_idx.data(), (int32_t)g.c.raw_idx.size(),
                        (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size(), G.ctx, *dags[li], mpos);
+        gc.set_options(opt_slot_order, opt_strict);
         gc.differentiate();
         G.members.push_back((int32_t)gi);
         G.jac_slot.push_back(gc.g.jac_slot);

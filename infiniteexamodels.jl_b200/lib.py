@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 IEXA_MEM_HOST, IEXA_MEM_DEVICE, IEXA_MEM_HOST_SAME_X = 0, 1, 2
 IEXA_F_DEFAULT, IEXA_F_NO_SPECIALISE, IEXA_F_NO_DEVICE = 0, 1, 2
+IEXA_OPT_SLOT_ORDER, IEXA_OPT_STRICT_IEEE = 1, 2
 CB_OBJ, CB_GRAD, CB_CONS, CB_JAC, CB_HESS, CB_JPROD, CB_JTPROD, CB_HPROD = range(8)
 
 
@@ -30,7 +31,7 @@ class Segment(C.Structure):
 
 # every symbol include/iexa.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "iexa_last_error", "iexa_version", "iexa_plan_create", "iexa_plan_destroy", "iexa_add_var",
+    "iexa_last_error", "iexa_version", "iexa_plan_create", "iexa_plan_destroy", "iexa_set_option", "iexa_add_var",
     "iexa_add_par", "iexa_patch_var", "iexa_itr_base", "iexa_itr_product", "iexa_add_con",
     "iexa_add_obj", "iexa_finalize", "iexa_get_meta", "iexa_get_vector", "iexa_set_vector",
     "iexa_set_par", "iexa_set_par_stream", "iexa_get_par", "iexa_jac_structure", "iexa_hess_structure", "iexa_obj",
@@ -55,6 +56,7 @@ def _declare(L):
     sig("iexa_version", _i32)
     sig("iexa_plan_create", _i32, C.POINTER(_vp), _i32)
     sig("iexa_plan_destroy", _i32, _vp)
+    sig("iexa_set_option", _i32, _vp, _i32, _i64)
     sig("iexa_add_var", _i32, _vp, _i64, _vp, _vp, _vp, C.POINTER(_i64))
     sig("iexa_add_par", _i32, _vp, _i64, _vp, C.POINTER(_i64))
     sig("iexa_patch_var", _i32, _vp, _i32, _i64, _dbl)

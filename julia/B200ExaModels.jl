@@ -226,6 +226,10 @@ function NLPModels.hprod!(m::B200ExaModel, x::AbstractVector, y::AbstractVector,
     return Hv
 end
 
+"plan options (before the first generator): key 1 = slot-order policy (0 left to right, 1 right to left), key 2 = strict IEEE"
+set_option!(h::Ptr{Cvoid}, key::Integer, value::Integer) =
+    check(ccall((:iexa_set_option, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), h, key, value))
+
 "`ExaModels.set_parameter!(core, param, vals)` (infiniteopt_backend.jl:522,546): in place, no rebuild"
 function set_parameter!(m::B200ExaModel, offset0::Integer, vals::AbstractArray{Float64})
     v = collect(vec(vals))

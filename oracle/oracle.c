@@ -65,12 +65,14 @@ typedef struct {
   int *slot1_idx;           /* slot -> canonical index id */
   int *slot2_i, *slot2_j;
   int borrowed;             /* iterator columns belong to the caller (orc_add_gen_borrow) */
+  int order;                /* slot-order policy: 0 children left to right, 1 right to left (Appendix A.2 is a hypothesis) */
 } ogen;
 
 typedef struct {
   int ngen, cap; ogen *g;
   int64_t nvar, ncon, nnzj, nnzh, npar;
   double *theta;
+  int order;                /* policy given to generators added from now on */
 } omodel;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -108,6 +110,11 @@ int orc_max_threads(void) {
 }
 
 omodel *orc_create(void) { return (omodel *)calloc(1, sizeof(omodel)); }
+/* slot-order policy of the generators added AFTER this call: 0 = inner1 then inner2, 1 = inner2 then inner1 */
+void orc_set_slot_order(omodel *m, int order) { m->order = order ? 1 : 0; }
+/* first / second child of a binary node in the policy's visiting order */
+#define KID1(g, t) ((g)->order ? (g)->c2[t] : (g)->c1[t])
+#define KID2(g, t) ((g)->order ? (g)->c1[t] : (g)->c2[t])
 
 void orc_free(omodel *m) {
   if (!m) return;
@@ -147,30 +154,29 @@ static void sym_first(const ogen *g, int t, plist *out) {
   switch (g->kind[t]) {
     case KD_VAR: pl_push(out, g->canon[g->nd[t].a], 0); break;
     case KD_UN: sym_first(g, g->c1[t], out); break;
-    case KD_BIN: sym_first(g, g->c1[t], out); sym_first(g, g->c2[t], out); break;
+    case KD_BIN: sym_first(g, KID1(g, t), out); sym_first(g, KID2(g, t), out); break;
     default: break;
   }
 }
-static void sym_hdr(const ogen *g, int t1, int t2, plist *out) {
-  int k1 = g->kind[t1], k2 = g->kind[t2];
-  if (k1 == KD_VAR && k2 == KD_VAR) { pl_push(out, g->canon[g->nd[t1].a], g->canon[g->nd[t2].a]); return; }
-  if (k1 == KD_UN && k2 == KD_UN) { sym_hdr(g, g->c1[t1], g->c1[t2], out); return; }
-  if (k1 == KD_UN && k2 == KD_BIN) { sym_hdr(g, g->c1[t1], g->c1[t2], out); sym_hdr(g, g->c1[t1], g->c2[t2], out); return; }
-  if (k1 == KD_BIN && k2 == KD_UN) { sym_hdr(g, g->c1[t1], g->c1[t2], out); sym_hdr(g, g->c2[t1], g->c1[t2], out); return; }
-  if (k1 == KD_BIN && k2 == KD_BIN) {
-    sym_hdr(g, g->c1[t1], g->c1[t2], out); sym_hdr(g, g->c1[t1], g->c2[t2], out);
-    sym_hdr(g, g->c2[t1], g->c1[t2], out); sym_hdr(g, g->c2[t1], g->c2[t2], out); return;
+/* children of a node for the cross pass: a Var leaf stands for itself */
+static int kids(const ogen *g, int t, int *c) {
+  switch (g->kind[t]) {
+    case KD_VAR: c[0] = t; return 1;
+    case KD_UN: c[0] = g->c1[t]; return 1;
+    case KD_BIN: c[0] = KID1(g, t); c[1] = KID2(g, t); return 2;
+    default: return 0;
   }
-  if (k1 == KD_VAR && k2 == KD_UN) { sym_hdr(g, t1, g->c1[t2], out); return; }
-  if (k1 == KD_VAR && k2 == KD_BIN) { sym_hdr(g, t1, g->c1[t2], out); sym_hdr(g, t1, g->c2[t2], out); return; }
-  if (k1 == KD_UN && k2 == KD_VAR) { sym_hdr(g, g->c1[t1], t2, out); return; }
-  if (k1 == KD_BIN && k2 == KD_VAR) { sym_hdr(g, g->c1[t1], t2, out); sym_hdr(g, g->c2[t1], t2, out); return; }
+}
+static void sym_hdr(const ogen *g, int t1, int t2, plist *out) {
+  if (g->kind[t1] == KD_VAR && g->kind[t2] == KD_VAR) { pl_push(out, g->canon[g->nd[t1].a], g->canon[g->nd[t2].a]); return; }
+  int a[2], b[2], na = kids(g, t1, a), nb = kids(g, t2, b);
+  for (int i = 0; i < na; ++i) for (int j = 0; j < nb; ++j) sym_hdr(g, a[i], b[j], out);
 }
 static void sym_hr(const ogen *g, int t, plist *out) {
   switch (g->kind[t]) {
     case KD_VAR: { int u = g->canon[g->nd[t].a]; pl_push(out, u, u); break; }
     case KD_UN: sym_hr(g, g->c1[t], out); break;
-    case KD_BIN: sym_hr(g, g->c1[t], out); sym_hr(g, g->c2[t], out); sym_hdr(g, g->c1[t], g->c2[t], out); break;
+    case KD_BIN: sym_hr(g, KID1(g, t), out); sym_hr(g, KID2(g, t), out); sym_hdr(g, KID1(g, t), KID2(g, t), out); break;
     default: break;
   }
 }
@@ -184,8 +190,8 @@ static int passthrough(const ogen *g, int t) {
 static void sym_hr0(const ogen *g, int t, plist *out) {
   if (g->kind[t] == KD_VAR || g->kind[t] == KD_CONST) return;
   if (passthrough(g, t)) {
-    sym_hr0(g, g->c1[t], out);
-    if (g->kind[t] == KD_BIN) sym_hr0(g, g->c2[t], out);
+    if (g->kind[t] == KD_BIN) { sym_hr0(g, KID1(g, t), out); sym_hr0(g, KID2(g, t), out); }
+    else sym_hr0(g, g->c1[t], out);
     return;
   }
   sym_hr(g, t, out);
@@ -211,7 +217,7 @@ static int add_gen(omodel *m, int is_obj, const onode *nodes, int n_nodes, const
   if (m->ngen == m->cap) { m->cap = m->cap ? 2 * m->cap : 16; m->g = (ogen *)realloc(m->g, sizeof(ogen) * (size_t)m->cap); }
   ogen *g = &m->g[m->ngen];
   memset(g, 0, sizeof *g);
-  g->n = n_nodes; g->is_obj = is_obj; g->K = K; g->lcon = lcon; g->ucon = ucon;
+  g->n = n_nodes; g->is_obj = is_obj; g->K = K; g->lcon = lcon; g->ucon = ucon; g->order = m->order;
   g->nd = (onode *)malloc(sizeof(onode) * (size_t)n_nodes); memcpy(g->nd, nodes, sizeof(onode) * (size_t)n_nodes);
   g->n_idx = n_idx;
   g->idx = (oindex *)malloc(sizeof(oindex) * (size_t)(n_idx + 1)); if (n_idx) memcpy(g->idx, idx, sizeof(oindex) * (size_t)n_idx);
@@ -407,7 +413,10 @@ static void jrpass(fctx *c, int t, double adj) {
       break;
     }
     case KD_UN: jrpass(c, g->c1[t], adj * c->t[t].y1); break;
-    case KD_BIN: jrpass(c, g->c1[t], adj * c->t[t].y1); jrpass(c, g->c2[t], adj * c->t[t].y2); break;
+    case KD_BIN:
+      if (!g->order) { jrpass(c, g->c1[t], adj * c->t[t].y1); jrpass(c, g->c2[t], adj * c->t[t].y2); }
+      else { jrpass(c, g->c2[t], adj * c->t[t].y2); jrpass(c, g->c1[t], adj * c->t[t].y1); }
+      break;
     default: break;
   }
 }
@@ -435,29 +444,23 @@ static void emit2(sctx *c, int t1, int t2, double val, int diag_leaf) {
       break;
   }
 }
+/* local partial w.r.t. the i-th child IN VISITING ORDER (kids()); a tape may name the same node as both children */
+static double kid_partial(const ogen *g, const anode *T, int t, int i) {
+  if (g->kind[t] == KD_VAR) return 1.0;
+  if (g->kind[t] == KD_UN) return T[t].y1;
+  return ((i == 0) != (g->order != 0)) ? T[t].y1 : T[t].y2;
+}
 static void hdrpass(sctx *c, int t1, int t2, double adj) {
   const ogen *g = c->g; const anode *T = c->t;
-  int k1 = g->kind[t1], k2 = g->kind[t2];
-  if (k1 == KD_VAR && k2 == KD_VAR) { emit2(c, t1, t2, adj, 0); return; }
-  if (k1 == KD_UN && k2 == KD_UN) { hdrpass(c, g->c1[t1], g->c1[t2], adj * T[t1].y1 * T[t2].y1); return; }
-  if (k1 == KD_UN && k2 == KD_BIN) {
-    hdrpass(c, g->c1[t1], g->c1[t2], adj * T[t1].y1 * T[t2].y1);
-    hdrpass(c, g->c1[t1], g->c2[t2], adj * T[t1].y1 * T[t2].y2); return;
-  }
-  if (k1 == KD_BIN && k2 == KD_UN) {
-    hdrpass(c, g->c1[t1], g->c1[t2], adj * T[t1].y1 * T[t2].y1);
-    hdrpass(c, g->c2[t1], g->c1[t2], adj * T[t1].y2 * T[t2].y1); return;
-  }
-  if (k1 == KD_BIN && k2 == KD_BIN) {
-    hdrpass(c, g->c1[t1], g->c1[t2], adj * T[t1].y1 * T[t2].y1);
-    hdrpass(c, g->c1[t1], g->c2[t2], adj * T[t1].y1 * T[t2].y2);
-    hdrpass(c, g->c2[t1], g->c1[t2], adj * T[t1].y2 * T[t2].y1);
-    hdrpass(c, g->c2[t1], g->c2[t2], adj * T[t1].y2 * T[t2].y2); return;
-  }
-  if (k1 == KD_VAR && k2 == KD_UN) { hdrpass(c, t1, g->c1[t2], adj * T[t2].y1); return; }
-  if (k1 == KD_VAR && k2 == KD_BIN) { hdrpass(c, t1, g->c1[t2], adj * T[t2].y1); hdrpass(c, t1, g->c2[t2], adj * T[t2].y2); return; }
-  if (k1 == KD_UN && k2 == KD_VAR) { hdrpass(c, g->c1[t1], t2, adj * T[t1].y1); return; }
-  if (k1 == KD_BIN && k2 == KD_VAR) { hdrpass(c, g->c1[t1], t2, adj * T[t1].y1); hdrpass(c, g->c2[t1], t2, adj * T[t1].y2); return; }
+  if (g->kind[t1] == KD_VAR && g->kind[t2] == KD_VAR) { emit2(c, t1, t2, adj, 0); return; }
+  int a[2], b[2], na = kids(g, t1, a), nb = kids(g, t2, b);
+  for (int i = 0; i < na; ++i)
+    for (int j = 0; j < nb; ++j) {
+      double v = adj;
+      if (g->kind[t1] != KD_VAR) v *= kid_partial(g, T, t1, i);
+      if (g->kind[t2] != KD_VAR) v *= kid_partial(g, T, t2, j);
+      hdrpass(c, a[i], b[j], v);
+    }
 }
 static void hrpass(sctx *c, int t, double adj, double adj2) {
   const ogen *g = c->g; const anode *n = &c->t[t];
@@ -466,30 +469,48 @@ static void hrpass(sctx *c, int t, double adj, double adj2) {
     case KD_UN: hrpass(c, g->c1[t], adj * n->y1, adj2 * (n->y1 * n->y1) + adj * n->h11); break;
     case KD_BIN: {
       double cross = adj2 * n->y1 * n->y2 + adj * n->h12;
-      hrpass(c, g->c1[t], adj * n->y1, adj2 * (n->y1 * n->y1) + adj * n->h11);
-      hrpass(c, g->c2[t], adj * n->y2, adj2 * (n->y2 * n->y2) + adj * n->h22);
-      hdrpass(c, g->c1[t], g->c2[t], cross);
+      if (!g->order) {
+        hrpass(c, g->c1[t], adj * n->y1, adj2 * (n->y1 * n->y1) + adj * n->h11);
+        hrpass(c, g->c2[t], adj * n->y2, adj2 * (n->y2 * n->y2) + adj * n->h22);
+        hdrpass(c, g->c1[t], g->c2[t], cross);
+      } else {
+        hrpass(c, g->c2[t], adj * n->y2, adj2 * (n->y2 * n->y2) + adj * n->h22);
+        hrpass(c, g->c1[t], adj * n->y1, adj2 * (n->y1 * n->y1) + adj * n->h11);
+        hdrpass(c, g->c2[t], g->c1[t], cross);
+      }
       break;
     }
     default: break;
   }
 }
-static void hrpass0(sctx *c, int t, double adj, double adj2) {
+/* top-level pass: NO second-order adjoint (Appendix A.4: "adj2 == 0, no cross term") — through +, -, const*subtree only
+ * the first-order adjoint travels; the first nonlinear node hands its children adj*h (not 0*y*y + adj*h) */
+static void hrpass0(sctx *c, int t, double adj) {
   const ogen *g = c->g; const anode *n = &c->t[t];
   if (g->kind[t] == KD_VAR || g->kind[t] == KD_CONST) return;
   if (passthrough(g, t)) {
     int op = g->nd[t].op;
     if (g->kind[t] == KD_BIN) {
-      hrpass0(c, g->c1[t], adj, adj2);
-      hrpass0(c, g->c2[t], op == OP_SUB ? -adj : adj, adj2);
+      if (!g->order) { hrpass0(c, g->c1[t], adj); hrpass0(c, g->c2[t], op == OP_SUB ? -adj : adj); }
+      else { hrpass0(c, g->c2[t], op == OP_SUB ? -adj : adj); hrpass0(c, g->c1[t], adj); }
     } else if (op == OP_MUL) {
-      hrpass0(c, g->c1[t], adj * n->y1, adj2 * (n->y1 * n->y1));
+      hrpass0(c, g->c1[t], adj * n->y1);
     } else {
-      hrpass0(c, g->c1[t], n->y1 < 0 ? -adj : adj, adj2);
+      hrpass0(c, g->c1[t], n->y1 < 0 ? -adj : adj);
     }
     return;
   }
-  hrpass(c, t, adj, adj2);
+  if (g->kind[t] == KD_UN) {
+    hrpass(c, g->c1[t], adj * n->y1, adj * n->h11);
+  } else if (!g->order) {
+    hrpass(c, g->c1[t], adj * n->y1, adj * n->h11);
+    hrpass(c, g->c2[t], adj * n->y2, adj * n->h22);
+    hdrpass(c, g->c1[t], g->c2[t], adj * n->h12);
+  } else {
+    hrpass(c, g->c2[t], adj * n->y2, adj * n->h22);
+    hrpass(c, g->c1[t], adj * n->y1, adj * n->h11);
+    hdrpass(c, g->c2[t], g->c1[t], adj * n->h12);
+  }
 }
 
 /* ---- NLPModels-level entry points ----------------------------------------------------------- */
@@ -609,7 +630,7 @@ void orc_hess_structure(const omodel *m, int64_t *rows, int64_t *cols) {
       anode *t = (anode *)calloc((size_t)g->n, sizeof(anode)); /* structure needs no values */
       for (int64_t k = 0; k < g->K; ++k) {
         sctx c = {g, t, k, 0, 0, g->o2 + g->o2step * k, rows, cols, 0, 0, 2};
-        hrpass0(&c, g->n - 1, 0.0, 0.0);
+        hrpass0(&c, g->n - 1, 0.0);
       }
       free(t);
     }
@@ -629,7 +650,7 @@ void orc_hess_coord(const omodel *m, const double *x, const double *y, double si
         for (int64_t k = 0; k < g->K; ++k) {
           forward(m, g, k, x, t, 1);
           sctx c = {g, t, k, 0, vals, g->o2 + g->o2step * k, 0, 0, 0, 0, 0};
-          hrpass0(&c, g->n - 1, g->is_obj ? sigma : y[g->o0 + k], 0.0);
+          hrpass0(&c, g->n - 1, g->is_obj ? sigma : y[g->o0 + k]);
         }
         free(t);
       }
@@ -647,7 +668,7 @@ void orc_hprod(const omodel *m, const double *x, const double *y, const double *
       for (int64_t k = 0; k < g->K; ++k) {
         forward(m, g, k, x, t, 1);
         sctx c = {g, t, k, 0, 0, 0, 0, 0, v, hv, 3};
-        hrpass0(&c, g->n - 1, g->is_obj ? sigma : y[g->o0 + k], 0.0);
+        hrpass0(&c, g->n - 1, g->is_obj ? sigma : y[g->o0 + k]);
       }
       free(t);
     }

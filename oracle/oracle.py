@@ -41,6 +41,7 @@ def lib():
         L.orc_add_gen.restype = i32
         L.orc_add_gen_borrow.argtypes = L.orc_add_gen.argtypes
         L.orc_add_gen_borrow.restype = i32
+        L.orc_set_slot_order.argtypes = [vp, i32]
         L.orc_finalize.argtypes = [vp]
         for f in ("orc_ncon", "orc_nnzj", "orc_nnzh"):
             getattr(L, f).argtypes = [vp]
@@ -78,10 +79,11 @@ def max_threads() -> int:
 class OracleModel:
     """CPU evaluation of an ``ExaCore`` description with the restated ExaModels algorithm."""
 
-    def __init__(self, core):
+    def __init__(self, core, slot_order: int = 0):
         L = lib()
         self.L = L
         self.h = L.orc_create()
+        L.orc_set_slot_order(self.h, int(slot_order))   # the slot-ORDER policy is data (0: inner1 then inner2, 1: reversed)
         self.nvar = core.nvar
         theta = np.ascontiguousarray(core.theta_vec, dtype=np.float64)
         L.orc_set_dims(self.h, core.nvar, core.npar, _p(theta))

@@ -47,14 +47,16 @@ static int64_t g_int_col(const Plan &P, const Group &G, int32_t slot, int64_t k)
   const HostColumn &c = P.columns[r.col];
   return c.ival(j);
 }
-static int64_t g_index(const Plan &P, const Group &G, int32_t islot, int64_t k, const Generator *inst = nullptr) {
+// inst: instance number of a shape-class group (-1: ordinary group)
+static int64_t g_index(const Plan &P, const Group &G, int32_t islot, int64_t k, int64_t inst = -1) {
   const IndexExpr &e = G.ctx.uidx[islot];
-  int64_t v = inst ? inst->c.uidx[islot].base : e.base; // shape class: the instance's own base
+  int64_t v = inst >= 0 ? G.inst_base[inst * G.ctx.uidx.size() + islot] : e.base; // shape class: the instance's own base
   for (auto &t : e.terms) v += t.second * g_int_col(P, G, t.first, k);
   return v;
 }
 static void run_group(const Plan &P, const Group &G, const Program &pr, int64_t k, const double *x, const double *y,
-                      double sigma, std::vector<double> &r, double *out, const Generator *inst = nullptr, const double *v = nullptr) {
+                      double sigma, std::vector<double> &r, double *out, int64_t inst = -1, const double *v = nullptr) {
+  const std::vector<Generator> &gens_ = G.is_obj ? P.objs : P.cons;
   r.resize(pr.nreg > 0 ? pr.nreg : 1);
   for (const Instr &I : pr.code) {
     switch (I.op) {
@@ -63,9 +65,9 @@ static void run_group(const Plan &P, const Group &G, const Program &pr, int64_t 
       case D_LOADP: r[I.dst] = P.theta[g_index(P, G, I.a, k, inst) - 1]; break;
       case D_LOADV: r[I.dst] = v[g_index(P, G, I.a, k, inst) - 1]; break;
       case D_SELNE: r[I.dst] = g_index(P, G, I.a, k, inst) != g_index(P, G, I.b, k, inst) ? 1.0 : 0.0; break;
-      case D_W: r[I.dst] = G.is_obj ? sigma : (y ? y[(inst ? *inst : P.member(G, I.a)).o0 + k] : 0.0); break;
+      case D_W: r[I.dst] = G.is_obj ? sigma : (y ? y[(inst >= 0 ? gens_[G.inst_gen(inst, I.a)] : P.member(G, I.a)).o0 + k] : 0.0); break;
       case D_SEL2: r[I.dst] = g_index(P, G, I.a, k, inst) == g_index(P, G, I.b, k, inst) ? 2.0 : 1.0; break;
-      case D_CPAR: r[I.dst] = inst->c.tape[G.cpar_nodes[I.a]].c; break;
+      case D_CPAR: r[I.dst] = gens_[G.inst_gen(inst, G.cpar_member[I.a])].c.tape[G.cpar_nodes[I.a]].c; break;
       case D_OUT: out[I.dst] = I.a >= 0 ? r[I.a] : pr.cpool[~I.a]; break;
       default: {
         double a = I.a >= 0 ? r[I.a] : pr.cpool[~I.a];
@@ -159,14 +161,14 @@ int32_t hostcheck_eval_groups(iexa_plan *p, int32_t which, const double *x, cons
     const Program &pr = G.prog[prog];
     tmp.assign(pr.nout > 0 ? pr.nout : 1, 0.0);
     const std::vector<Generator> &gens = G.is_obj ? P.objs : P.cons;
-    const size_t ninst = G.is_class ? G.inst_gens.size() : 1;
+    const size_t ninst = G.is_class ? G.n_inst() : 1;
     for (size_t ii = 0; ii < ninst; ++ii)
     for (int64_t k = 0; k < G.K; ++k) {
-      const Generator *inst = G.is_class ? &gens[G.inst_gens[ii]] : nullptr;
+      const int64_t inst = G.is_class ? (int64_t)ii : -1;
       run_group(P, G, pr, k, x, y, sigma, r, tmp.data(), inst);
       for (size_t j = 0; j < G.outmap[prog].size(); ++j) {
         int m = G.outmap[prog][j].first, c = G.outmap[prog][j].second;
-        const Generator &g = inst ? *inst : P.member(G, m);
+        const Generator &g = inst >= 0 ? gens[G.inst_gen(ii, m)] : P.member(G, m);
         switch (which) {
           case 0: out[0] += tmp[j]; break;
           case 1: out[g_index(P, G, G.jac_slot[m][c], k, inst) - 1] += tmp[j]; break;
@@ -224,15 +226,15 @@ int32_t hostcheck_prod(iexa_plan *p, int32_t which, int32_t use_groups, const do
     if (which != 5) { st[3]++; if (phase == 0) st[0]++; }
     tmp.assign(pr.nout > 0 ? pr.nout : 1, 0.0);
     const std::vector<Generator> &gens = G.is_obj ? P.objs : P.cons;
-    const size_t ninst = G.is_class ? G.inst_gens.size() : 1;
+    const size_t ninst = G.is_class ? G.n_inst() : 1;
     // J'v: D_W(member) reads v[row of member] — hand v in as y
     const double *wy = which == 6 ? v : y;
     for (size_t ii = 0; ii < ninst; ++ii)
     for (int64_t k = 0; k < G.K; ++k) {
-      const Generator *inst = G.is_class ? &gens[G.inst_gens[ii]] : nullptr;
+      const int64_t inst = G.is_class ? (int64_t)ii : -1;
       run_group(P, G, pr, k, x, wy, sigma, r, tmp.data(), inst, v);
       for (size_t j = 0; j < G.outmap[prog].size(); ++j) {
-        if (which == 5) { const Generator &g = inst ? *inst : P.member(G, G.outmap[prog][j].first); out[g.o0 + k] = tmp[j]; continue; }
+        if (which == 5) { const Generator &g = inst >= 0 ? gens[G.inst_gen(ii, G.outmap[prog][j].first)] : P.member(G, G.outmap[prog][j].first); out[g.o0 + k] = tmp[j]; continue; }
         const int64_t i = g_index(P, G, G.outmap[prog][j].second, k, inst) - 1;
         const bool direct = phase == 0 && G.scat_direct[w][j];
         if (direct) { out[i] = tmp[j]; if (ii == 0 && k == 0) st[1]++; } else out[i] += tmp[j];

@@ -44,8 +44,12 @@ hv = torch.zeros(max(m.meta.nnzh, 1), dtype=torch.float64, device="cuda")
 g = torch.zeros(m.meta.nvar, dtype=torch.float64, device="cuda")
 
 
-def timeit(fn, n=50):
-    for _ in range(3):
+REPS = int(os.environ.get("IEXA_QB_REPS", "50"))   # profiling runs (ncu --set full): IEXA_QB_REPS=1
+
+
+def timeit(fn, n=None):
+    n = REPS if n is None else n
+    for _ in range(3 if REPS > 2 else 1):
         fn()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

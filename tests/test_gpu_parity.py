@@ -308,3 +308,54 @@ def test_opf_shape_classes_and_budget_fallback(oracle_cache, monkeypatch):
         ex.hess_structure_(m, r, cc)
         ro, co = om.hess_structure()
         assert (r.cpu().numpy() == ro).all() and (cc.cpu().numpy() == co).all()
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("name", ["quadrotor_oc_40", "pandemic_50x4", "ode_5x5"])
+def test_callbacks_under_the_alternative_slot_order_policy(name, mode):
+    """IEXA_OPT_SLOT_ORDER = right-to-left (the alternative of SURVEY App. A.2): structure bit-exact and values at the
+    north-star tolerance against the oracle under the SAME policy — the slot order is data, the kernels are generated from it"""
+    import torch
+    from oracle.oracle import OracleModel
+    core = CASES[name]()
+    om = OracleModel(core, slot_order=1)
+    m = ex.ExaModel(core, device=0, flags=MODES[mode], slot_order=1)
+    x, y = eval_point(core, seed=8)
+    dev = torch.device("cuda:0")
+    xd, yd = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)
+    for fn, ref, n in ((ex.jac_structure_, om.jac_structure, om.nnzj), (ex.hess_structure_, om.hess_structure, om.nnzh)):
+        r = torch.zeros(max(n, 1), dtype=torch.int64, device=dev); c = torch.zeros_like(r)
+        fn(m, r, c)
+        ro, co = ref()
+        assert (r.cpu().numpy()[:n] == ro).all() and (c.cpu().numpy()[:n] == co).all()
+    z = lambda n: torch.full((max(n, 1),), 7.0, dtype=torch.float64, device=dev)
+    assert_close(ex.jac_coord_(m, xd, z(om.nnzj)).cpu().numpy()[: om.nnzj], om.jac_coord(x), "jac_coord")
+    assert_close(ex.hess_coord_(m, xd, yd, z(om.nnzh), 0.7).cpu().numpy()[: om.nnzh], om.hess_coord(x, y, 0.7), "hess_coord")
+    assert_close(ex.grad_(m, xd, z(om.nvar)).cpu().numpy(), om.grad(x), "grad")
+    rng = np.random.default_rng(5)
+    v = rng.uniform(-1, 1, om.nvar)
+    assert_close(ex.hprod_(m, xd, yd, torch.from_numpy(v).to(dev), z(om.nvar), 0.7).cpu().numpy(), om.hprod(x, y, v, 0.7), "hprod")
+
+
+@pytest.mark.parametrize("poison", [float("nan"), float("inf")])
+@pytest.mark.parametrize("name", ["quadrotor_oc_40", "pandemic_50x4"])
+def test_strict_ieee_mode_reproduces_the_oracles_nan_pattern_on_the_gpu(name, poison):
+    """IEXA_OPT_STRICT_IEEE: structural zeros are multiplied at run time — the NaN pattern of cons / jac_coord / hess_coord on a
+    poisoned x equals the oracle's (tests/test_nan_semantics.py does the same for every BASELINE config on the host executor)"""
+    import torch
+    from oracle.oracle import OracleModel
+    core = CASES[name]()
+    om = OracleModel(core)
+    m = ex.ExaModel(core, device=0, strict_ieee=True)
+    x, y = eval_point(core, seed=2)
+    rng = np.random.default_rng(1)
+    x[rng.choice(core.nvar, size=max(1, core.nvar // 10), replace=False)] = poison
+    dev = torch.device("cuda:0")
+    xd, yd = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)
+    z = lambda n: torch.full((max(n, 1),), 7.0, dtype=torch.float64, device=dev)
+    for got, ref in ((ex.cons_(m, xd, z(om.ncon)).cpu().numpy()[: om.ncon], om.cons(x)),
+                     (ex.jac_coord_(m, xd, z(om.nnzj)).cpu().numpy()[: om.nnzj], om.jac_coord(x)),
+                     (ex.hess_coord_(m, xd, yd, z(om.nnzh), 0.7).cpu().numpy()[: om.nnzh], om.hess_coord(x, y, 0.7))):
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), "NaN pattern differs from the oracle's"
+        fin = ~np.isnan(ref)
+        assert_close(got[fin], ref[fin], "finite entries")

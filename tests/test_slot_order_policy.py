@@ -1,0 +1,93 @@
+"""The COO slot ORDER inside a generator is DATA (iexa_set_option IEXA_OPT_SLOT_ORDER), honoured by the oracle and by the
+product alike: ExaModels' own order cannot be pinned here (the package is absent — SURVEY App. A.2), so the day a real
+dump disagrees with the default hypothesis only the policy value changes, not a kernel.  Under BOTH policies: structure
+bit-exact and values within the north-star tolerance between the plan compiler (per-generator programs and fused groups,
+host executor) and the oracle; the two policies give the same MATRICES (a permutation of the slots inside each support)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import iexa_b200 as ex
+from iexa_b200 import models
+from conftest import assert_close, eval_point
+
+CASES = {
+    "ode_5x5": lambda: models.ode_5x5(),
+    "quadrotor_oc": lambda: models.quadrotor(9, "oc"),
+    "pandemic": lambda: models.pandemic(7, 3),
+    "farmer": lambda: models.farmer(11),
+}
+
+
+def _opf():
+    from iexa_b200 import opf
+    from iexa_b200.transform import exa_core
+    return exa_core(opf.opf(None, num_supports=6))[0]
+
+
+CASES["opf_case3"] = _opf
+
+
+def _hc(L, m, fn, which, n, x, y=None, sig=1.0):
+    out = np.zeros(max(n, 1))
+    args = [m.h, which, x.ctypes.data, None if y is None else y.ctypes.data, sig, out.ctypes.data]
+    if fn == "hostcheck_eval_groups":
+        args.append(C.byref(C.c_int32()))
+    assert getattr(L, fn)(*args) == 0
+    return out[:n]
+
+
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("name", list(CASES))
+def test_product_and_oracle_agree_under_each_policy(name, order, hostcheck_lib):
+    from oracle.oracle import OracleModel
+    L = hostcheck_lib
+    core = CASES[name]()
+    om = OracleModel(core, slot_order=order)
+    m = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L, slot_order=order)
+    assert (m.meta.nnzj, m.meta.nnzh) == (om.nnzj, om.nnzh)
+    x, y = eval_point(core)
+    x = np.where(np.isfinite(x), x, 0.0)
+    for which, (ro, co) in ((0, om.jac_structure()), (1, om.hess_structure())):
+        r = np.zeros(max(len(ro), 1), dtype=np.int64); c = np.zeros_like(r)
+        assert L.hostcheck_structure(m.h, which, r.ctypes.data, c.ctypes.data) == 0
+        assert (r[:len(ro)] == ro).all() and (c[:len(co)] == co).all(), f"structure {which}"
+    for fn in ("hostcheck_eval", "hostcheck_eval_groups"):
+        assert_close(_hc(L, m, fn, 3, om.nnzj, x), om.jac_coord(x), "jac")
+        assert_close(_hc(L, m, fn, 4, om.nnzh, x, y, 0.7), om.hess_coord(x, y, 0.7), "hess")
+        assert_close(_hc(L, m, fn, 1, om.nvar, x), om.grad(x), "grad")
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_policies_permute_slots_but_not_the_matrices(name):
+    from oracle.oracle import OracleModel
+    import scipy.sparse as sp
+    core = CASES[name]()
+    x, y = eval_point(core)
+    x = np.where(np.isfinite(x), x, 0.0)
+    mats = []
+    structs = []
+    for order in (0, 1):
+        om = OracleModel(core, slot_order=order)
+        jr, jc = om.jac_structure(); hr, hc = om.hess_structure()
+        J = sp.coo_matrix((om.jac_coord(x), (jr - 1, jc - 1)), shape=(om.ncon, om.nvar)).tocsr()
+        H = sp.coo_matrix((om.hess_coord(x, y, 0.7), (hr - 1, hc - 1)), shape=(om.nvar, om.nvar)).tocsr()
+        mats.append((J, H)); structs.append((jr, jc, hr, hc))
+    for a, b in zip(mats[0], mats[1]):
+        d = abs(a - b)
+        assert d.max() <= 1e-12 * max(1.0, abs(a).max()) if d.nnz else True
+    if name in ("quadrotor_oc", "opf_case3"):  # trees with binary nodes over several variables: the ORDER really differs
+        assert any(not np.array_equal(u, v) for u, v in zip(structs[0], structs[1]))
+
+
+def test_options_are_frozen_once_a_generator_exists(hostcheck_lib):
+    L = hostcheck_lib
+    m = ex.ExaModel(models.farmer(3), flags=ex.lib.IEXA_F_NO_DEVICE, library=L)
+    assert L.iexa_set_option(m.h, ex.lib.IEXA_OPT_SLOT_ORDER, 1) != 0
+    h = C.c_void_p()
+    assert L.iexa_plan_create(C.byref(h), 1) == 0
+    assert L.iexa_set_option(h, ex.lib.IEXA_OPT_SLOT_ORDER, 7) != 0 and b"policy" in L.iexa_last_error()
+    assert L.iexa_set_option(h, 99, 0) != 0
+    assert L.iexa_set_option(h, ex.lib.IEXA_OPT_SLOT_ORDER, 1) == 0 and L.iexa_set_option(h, ex.lib.IEXA_OPT_STRICT_IEEE, 1) == 0
+    L.iexa_plan_destroy(h)
