@@ -162,6 +162,29 @@ int32_t iexa_patch_var(iexa_plan *p, int32_t which, int64_t i, double value);
  * Integer columns equal to 1..K are detected and never stored or loaded.              */
 int32_t iexa_itr_base(iexa_plan *p, int64_t K, int32_t n_int, const int64_t *const *int_cols,
                       int32_t n_fp, const double *const *fp_cols, int32_t *itr_out);
+/* ---- device-side transcription (src/transform.jl:2-38 iterators, :161-183 parameter functions, :618-633 measure
+ *      coefficients): columns described by a closed form are GENERATED on the device by a kernel — no K-long host array, no
+ *      upload — with numpy's / InfiniteOpt's arithmetic restated operation by operation, so the values are bit-identical to
+ *      the host path's.  int_cols[j] == NULL is the column 1..K.  gens[j].kind: 0 = data (fp_cols[j]);
+ *      IEXA_GEN_LINSPACE       v(j) = a + j*(b-a)/(n-1), v(n-1) = b, K == n        (supports of an independent parameter)
+ *      IEXA_GEN_LINSPACE_MID   that grid interleaved with its interval midpoints, K == 2n-1 (OrthogonalCollocation(3) nodes)
+ *      IEXA_GEN_TRAPEZOID      trapezoid weights of the earlier fp column `src` of this iterator (default integral)
+ *      IEXA_GEN_CONST          v(j) = a                                                                       */
+enum { IEXA_GEN_DATA = 0, IEXA_GEN_LINSPACE = 1, IEXA_GEN_LINSPACE_MID = 2, IEXA_GEN_TRAPEZOID = 3, IEXA_GEN_CONST = 4 };
+typedef struct iexa_colgen {
+  int32_t kind, src;
+  int64_t n;
+  double a, b;
+} iexa_colgen;
+int32_t iexa_itr_generated(iexa_plan *p, int64_t K, int32_t n_int, const int64_t *const *int_cols, int32_t n_fp,
+                           const iexa_colgen *gens, const double *const *fp_cols, int32_t *itr_out);
+/* ExaModels.add_par for a parameter FUNCTION (transform.jl:161-183) given as a tape over an iterator: the block of theta
+ * (one entry per support, iterator order) is evaluated on the device at iexa_finalize.  Leaves: CONST, FIELD, PAR.   */
+int32_t iexa_add_par_function(iexa_plan *p, const iexa_node *nodes, int32_t n_nodes, const iexa_index *idx,
+                              int32_t n_idx, int32_t itr, int64_t *offset_out);
+/* host copy of fp column `col` of base iterator `itr` as the DEVICE holds it (generated columns: downloaded)      */
+int32_t iexa_debug_get_column(iexa_plan *p, int32_t itr, int32_t col, double *out_host);
+
 /* Product iterator, first factor fastest (transform.jl:445, :541, :591, :670): columns are
  * the concatenation of the factors' columns; nothing is materialised.                 */
 int32_t iexa_itr_product(iexa_plan *p, int32_t n, const int32_t *itrs, int32_t *itr_out);
@@ -282,6 +305,9 @@ int64_t iexa_debug_codegen_source(const iexa_plan *p, char *buf, int64_t cap);
 /* regroup a host-only plan with (1) / without (0) shape canonicalisation before inspecting its source */
 int32_t iexa_debug_set_class_mode(iexa_plan *p, int32_t on);
 int32_t iexa_debug_codegen_compile(const iexa_plan *p, int64_t *cubin_bytes);
+/* compiled images are cached per process AND on disk ($IEXA_CACHE_DIR | $XDG_CACHE_HOME/iexa_b200 | ~/.cache/iexa_b200;
+ * IEXA_CACHE_DIR=off disables), keyed by the generated source: counts of NVRTC compilations / disk hits of this process */
+int32_t iexa_debug_cache_stats(int32_t *nvrtc_compiles, int32_t *disk_hits);
 
 /* ---- COO -> CSR value permutation feeding cuDSS (today MadNLPGPU's transfer! kernel,
  *      caller side of ext/InfiniteExaModelsMadNLP.jl:49-50).  Setup sorts the 1-based

@@ -15,6 +15,45 @@ import numpy as np
 from .expr import (Const, DataField, IndexExpr, Node, Par, Tape, Var, as_node, lower)
 
 
+# --- generated columns (device-side transcription) ----------------------------------------------------
+@dataclass
+class ColGen:
+    """An fp iterator column described by a closed form instead of data (include/iexa.h: iexa_colgen).  The engine
+    generates it ON the device; ``values(K, cols)`` is the numpy statement of the same arithmetic — what the host path
+    would have uploaded, and what the oracle reads."""
+    kind: int          # 1 LINSPACE, 2 LINSPACE_MID, 3 TRAPEZOID, 4 CONST
+    a: float = 0.0
+    b: float = 0.0
+    n: int = 0
+    src: Optional[str] = None   # TRAPEZOID: name of an earlier fp column of the same iterator
+
+    def values(self, K: int, cols: Dict[str, np.ndarray]) -> np.ndarray:
+        if self.kind == 1:
+            return np.linspace(self.a, self.b, self.n)
+        if self.kind == 2:
+            pub = np.linspace(self.a, self.b, self.n)
+            out = np.empty(2 * self.n - 1)
+            out[0::2] = pub
+            out[1::2] = 0.5 * (pub[:-1] + pub[1:])
+            return out
+        if self.kind == 3:
+            s = cols[self.src]
+            c = np.zeros_like(s)
+            d = np.diff(s)
+            c[:-1] += d / 2
+            c[1:] += d / 2
+            return c
+        if self.kind == 4:
+            return np.full(K, float(self.a))
+        raise ValueError(self.kind)
+
+
+def linspace_col(a, b, n): return ColGen(1, float(a), float(b), int(n))
+def linspace_mid_col(a, b, n): return ColGen(2, float(a), float(b), int(n))
+def trapezoid_col(src): return ColGen(3, src=src)
+def const_col(v): return ColGen(4, float(v))
+
+
 # --- iterators --------------------------------------------------------------------------------
 class Itr:
     """SoA form of the reference's ``Vector{NamedTuple}`` iterators (transform.jl:31).
@@ -30,12 +69,20 @@ class Itr:
         self.factors = factors
         self.ints: Dict[str, np.ndarray] = {}
         self.fps: Dict[str, np.ndarray] = {}
+        self.gens: Dict[str, ColGen] = {}     # fp columns generated on the device (their numpy values are in ``fps`` too)
+        self.iota: set = set()                # int columns given as None: 1..K, never materialised for the engine
         if factors is None:
             for k, v in (ints or {}).items():
+                if v is None:
+                    self.iota.add(k)
+                    v = np.arange(1, self.K + 1)
                 a = np.ascontiguousarray(v, dtype=np.int64)
                 assert a.shape == (self.K,), f"int column {k}: shape {a.shape} != ({self.K},)"
                 self.ints[k] = a
             for k, v in (fps or {}).items():
+                if isinstance(v, ColGen):
+                    self.gens[k] = v
+                    v = v.values(self.K, self.fps)
                 a = np.ascontiguousarray(v, dtype=np.float64)
                 assert a.shape == (self.K,), f"fp column {k}: shape {a.shape} != ({self.K},)"
                 self.fps[k] = a
@@ -171,6 +218,7 @@ class ExaCore:
         self.npar = 0
         self.ncon = 0
         self.gens: List[GenSpec] = []
+        self.par_functions = []           # (Parameter, Tape, Itr): blocks the engine evaluates on the device
         self._x0 = self._lvar = self._uvar = self._theta = None
 
     # -- add_var / add_par ------------------------------------------------------------------------
@@ -190,6 +238,18 @@ class ExaCore:
         self.nvar += n
         self._x0 = None
         return v
+
+    def add_par_function(self, expr, itr: "Itr") -> Parameter:
+        """a parameter function (transform.jl:161-183) as an EXPRESSION over the iterator's fields: the engine evaluates the
+        theta block on the device at finalize (iexa_add_par_function).  The host copy kept here (for the oracle) is the numpy
+        evaluation of the same expression."""
+        from .expr import eval_numpy
+        tape = self._lower(expr, itr)
+        _, fc = itr.materialise()
+        vals = eval_numpy(tape, fc, self.theta_vec if self.npar else np.zeros(0), itr.K)
+        p = self.add_par(vals)
+        self.par_functions.append((p, tape, itr))
+        return p
 
     def add_par(self, vals) -> Parameter:
         a = np.asarray(vals, dtype=np.float64)

@@ -111,6 +111,45 @@ int32_t iexa_itr_base(iexa_plan *p, int64_t K, int32_t n_int, const int64_t *con
   return IEXA_OK;
   GUARD_END
 }
+int32_t iexa_itr_generated(iexa_plan *p, int64_t K, int32_t n_int, const int64_t *const *int_cols, int32_t n_fp,
+                           const iexa_colgen *gens, const double *const *fp_cols, int32_t *itr_out) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (p->plan.finalized) return fail(IEXA_ERR_STATE, "plan already finalized");
+  if (n_int < 0 || n_fp < 0 || !itr_out || (n_fp > 0 && !gens)) return fail(IEXA_ERR_INVALID, "bad iterator arguments");
+  *itr_out = p->plan.itr_generated(K, n_int, int_cols, n_fp, gens, fp_cols);
+  return IEXA_OK;
+  GUARD_END
+}
+int32_t iexa_add_par_function(iexa_plan *p, const iexa_node *nodes, int32_t n_nodes, const iexa_index *idx, int32_t n_idx,
+                              int32_t itr, int64_t *offset_out) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (!nodes || n_idx < 0 || (n_idx > 0 && !idx)) return fail(IEXA_ERR_INVALID, "bad tape arguments");
+  int64_t off = p->plan.add_par_function(nodes, n_nodes, idx, n_idx, itr);
+  if (offset_out) *offset_out = off;
+  return IEXA_OK;
+  GUARD_END
+}
+int32_t iexa_debug_get_column(iexa_plan *p, int32_t itr, int32_t col, double *out_host) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (itr < 0 || itr >= (int32_t)p->plan.itrs.size() || !out_host) return fail(IEXA_ERR_INVALID, "bad iterator id");
+  const iexa::Iterator &it = p->plan.itrs[itr];
+  if (col < 0 || col >= (int32_t)it.fp_cols.size()) return fail(IEXA_ERR_INVALID, "bad fp column");
+  const iexa::ColRef &r = it.fp_cols[col];
+  const iexa::HostColumn &hc = p->plan.columns[r.col];
+  if (p->engine) {
+    std::string err;
+    int rc = p->engine->get_column(r.col, out_host, err);
+    if (rc) return fail(rc, err);
+    return IEXA_OK;
+  }
+  for (int64_t j = 0; j < hc.K; ++j) out_host[j] = hc.fp(j, p->plan.columns); // host-only plan: the same closed forms
+  return IEXA_OK;
+  GUARD_END
+}
+
 int32_t iexa_itr_product(iexa_plan *p, int32_t n, const int32_t *itrs, int32_t *itr_out) {
   GUARD_BEGIN
   NEED_PLAN(p);
@@ -484,6 +523,14 @@ int32_t iexa_debug_codegen_compile(const iexa_plan *p, int64_t *cubin_bytes) {
   if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
   return IEXA_OK;
   GUARD_END
+}
+
+int32_t iexa_debug_cache_stats(int32_t *nvrtc_compiles, int32_t *disk_hits) {
+  int a = 0, b = 0;
+  iexa::cache_stats(&a, &b);
+  if (nvrtc_compiles) *nvrtc_compiles = a;
+  if (disk_hits) *disk_hits = b;
+  return IEXA_OK;
 }
 
 const char *iexa_engine_note(const iexa_plan *p) { return (p && p->engine) ? p->engine->note() : ""; }

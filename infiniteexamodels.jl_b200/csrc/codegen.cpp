@@ -16,6 +16,8 @@
 #include "codegen.hpp"
 
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <cinttypes>
 #include <cstdio>
@@ -213,8 +215,11 @@ static bool pad_tiles() { const char *e = getenv("IEXA_PAD_TILES"); return e && 
 // Warp tiles: lane l writes its `step` slot values at wsm[l * stride + c].  With an EVEN step the 16 lanes of a half-warp
 // hit only 8 / 4 / 2 of the 16 64-bit banks (step 2, 6: 2-way, step 4: 4-way conflicts — ncu counted 5.9 M conflicts on
 // 4.7 M shared stores in jac of config 3, top stall mio_throttle); stride = step | 1 makes the writes conflict-free, the
-// copy-out reads element j at j + j / step.  IEXA_PAD_WARP_TILES=0 keeps stride = step.
-static bool pad_warp_tiles() { static bool v = [] { const char *e = getenv("IEXA_PAD_WARP_TILES"); return !(e && e[0] == '0'); }(); return v; }
+// copy-out reads element j at j + j / step.  Measured on B200 (round 2): time-neutral on config 3 (jac 0.2233 padded vs
+// 0.2225 ms) and slightly slower on the 118-bus OPF (hess 0.1278 vs 0.1248 ms) — the conflicts are real but the shared
+// memory pipe is not what bounds these kernels; the extra index arithmetic of the copy-out costs as much as the
+// conflicts did.  Off by default; IEXA_PAD_WARP_TILES=1 enables it.
+static bool pad_warp_tiles() { static bool v = [] { const char *e = getenv("IEXA_PAD_WARP_TILES"); return e && e[0] == '1'; }(); return v; }
 
 // Instances of a shape class handled by ONE block, one after the other (IEXA_CLASS_CHUNK, default 8).  A block that
 // evaluates a single small generator at 128 supports lives for three dependent memory latencies (work item -> instance
@@ -763,12 +768,86 @@ std::string Specialiser::generate_source(const Plan &plan, int set) { return iex
 static std::map<std::string, std::vector<char>> &cubin_cache() { static std::map<std::string, std::vector<char>> c; return c; }
 static std::mutex &cubin_cache_mutex() { static std::mutex m; return m; }
 
+// ---- persistent cubin cache -------------------------------------------------------------------------------------
+// NVRTC costs 1-5 s per model (config 3: 1.2 s of a 1.7 s iexa_finalize; 118-bus OPF: 4 s) and the generated text depends
+// only on the model's STRUCTURE, so the compiled image is also kept on disk, keyed by two independent 64-bit hashes of
+// (source, compiler options, NVRTC version): a re-run of the same model — every solve of a parameter study, every rank
+// of a multi-GPU job after the first — loads the image instead of compiling.  Directory: $IEXA_CACHE_DIR, else
+// $XDG_CACHE_HOME/iexa_b200, else ~/.cache/iexa_b200, else /tmp/iexa_b200-cache; IEXA_CACHE_DIR=off disables it.
+// Files are written to a temporary name and renamed (atomic for concurrent ranks); a file whose header does not match
+// the source length and second hash is ignored.
+static uint64_t fnv1a(const std::string &s, uint64_t h) {
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+  return h;
+}
+static std::string cache_dir() {
+  const char *e = getenv("IEXA_CACHE_DIR");
+  if (e && (std::string(e) == "off" || std::string(e) == "0")) return "";
+  std::string d;
+  if (e && *e) d = e;
+  else if (const char *x = getenv("XDG_CACHE_HOME")) d = std::string(x) + "/iexa_b200";
+  else if (const char *h = getenv("HOME")) d = std::string(h) + "/.cache/iexa_b200";
+  else d = "/tmp/iexa_b200-cache";
+  std::string cmd; // mkdir -p without <filesystem> (nvcc host compilers differ): create each prefix
+  for (size_t i = 1; i <= d.size(); ++i)
+    if (i == d.size() || d[i] == '/') { cmd = d.substr(0, i); ::mkdir(cmd.c_str(), 0700); }
+  return d;
+}
+struct CacheHeader { char magic[8]; uint64_t src_len, hash2, cubin_len; };
+static bool disk_cache_load(const std::string &key_text, std::vector<char> &cubin) {
+  const std::string dir = cache_dir();
+  if (dir.empty()) return false;
+  char name[64];
+  snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)fnv1a(key_text, 1469598103934665603ull));
+  std::ifstream f(dir + name, std::ios::binary);
+  if (!f) return false;
+  CacheHeader h{};
+  f.read((char *)&h, sizeof h);
+  if (!f || std::memcmp(h.magic, "IEXACB1", 8) != 0 || h.src_len != key_text.size() || h.hash2 != fnv1a(key_text, 0x9e3779b97f4a7c15ull) ||
+      h.cubin_len == 0 || h.cubin_len > (1ull << 30))
+    return false;
+  cubin.resize(h.cubin_len);
+  f.read(cubin.data(), (std::streamsize)h.cubin_len);
+  return (bool)f;
+}
+static void disk_cache_store(const std::string &key_text, const std::vector<char> &cubin) {
+  const std::string dir = cache_dir();
+  if (dir.empty() || cubin.empty()) return;
+  char name[64], tmp[96];
+  snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)fnv1a(key_text, 1469598103934665603ull));
+  snprintf(tmp, sizeof tmp, "%s.%ld.tmp", name, (long)getpid());
+  CacheHeader h{};
+  std::memcpy(h.magic, "IEXACB1", 8);
+  h.src_len = key_text.size(); h.hash2 = fnv1a(key_text, 0x9e3779b97f4a7c15ull); h.cubin_len = cubin.size();
+  {
+    std::ofstream f(dir + tmp, std::ios::binary | std::ios::trunc);
+    if (!f) return;
+    f.write((const char *)&h, sizeof h);
+    f.write(cubin.data(), (std::streamsize)cubin.size());
+    if (!f) { f.close(); ::remove((dir + tmp).c_str()); return; }
+  }
+  if (::rename((dir + tmp).c_str(), (dir + name).c_str()) != 0) ::remove((dir + tmp).c_str());
+}
+
+static int g_nvrtc_compiles = 0, g_disk_hits = 0; // reporting (iexa_debug_cache_stats)
+void cache_stats(int *compiles, int *disk_hits) { *compiles = g_nvrtc_compiles; *disk_hits = g_disk_hits; }
+
 bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string &err) {
   DynApi &a = api();
   {
     std::lock_guard<std::mutex> g(cubin_cache_mutex());
     auto it = cubin_cache().find(src);
     if (it != cubin_cache().end() && !getenv("IEXA_DUMP_DIR")) { cubin = it->second; return true; }
+  }
+  const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
+  std::string key_text = src;
+  for (const char *o : opts) { key_text += '\n'; key_text += o; }
+  if (!getenv("IEXA_DUMP_DIR") && disk_cache_load(key_text, cubin)) {
+    std::lock_guard<std::mutex> g(cubin_cache_mutex());
+    ++g_disk_hits;
+    if (cubin_cache().size() >= 64) cubin_cache().clear();
+    cubin_cache()[src] = cubin;
+    return true;
   }
   if (!a.load_nvrtc(err)) return false;
   // optional dump so that `ncu --import-source on` can attach the generated translation unit
@@ -783,7 +862,6 @@ bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string
   }
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, src.c_str(), name.c_str(), 0, nullptr, nullptr) != 0) { err = "nvrtcCreateProgram failed"; return false; }
-  const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
   int rc = a.nvrtcCompileProgram(prog, 4, opts);
   if (rc != 0) {
     size_t n = 0;
@@ -799,8 +877,10 @@ bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string
   cubin.resize(n);
   a.nvrtcGetCUBIN(prog, cubin.data());
   a.nvrtcDestroyProgram(&prog);
+  disk_cache_store(key_text, cubin);
   {
     std::lock_guard<std::mutex> g(cubin_cache_mutex());
+    ++g_nvrtc_compiles;
     if (cubin_cache().size() >= 64) cubin_cache().clear();
     cubin_cache()[src] = cubin;
   }

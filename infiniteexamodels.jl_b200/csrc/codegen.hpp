@@ -59,6 +59,7 @@ int spec_block(); // threads per block of the specialised kernels (env IEXA_BLOC
 int class_chunk(); // instances of a shape class per block (env IEXA_CLASS_CHUNK, default 8)
 GeneratedSource generate_source(const Plan &plan, int set = 0);
 bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string &err);
+void cache_stats(int *nvrtc_compiles, int *disk_hits); // of this process
 
 class Specialiser {
  public:

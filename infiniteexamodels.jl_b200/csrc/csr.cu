@@ -151,6 +151,20 @@ int grid_for(int64_t n) { int64_t b = (n + 255) / 256; return (int)(b < 1 ? 1 : 
     if (e_ != cudaSuccess) { g_csr_err = std::string(#call) + ": " + cudaGetErrorString(e_); return IEXA_ERR_CUDA; } \
   } while (0)
 
+// temporaries of the setup: freed on every exit path (an out-of-memory error at config-3 sizes must not leave several
+// GB of device memory behind on the device the solver needs)
+struct TmpBuf {
+  void *p = nullptr;
+  ~TmpBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+  void release() { if (p) cudaFree(p); p = nullptr; }
+  template <typename T> T *as() { return (T *)p; }
+};
+struct CsrOwner { // owns the handle (and through iexa_csr_destroy everything it holds) until the setup has succeeded
+  iexa_csr *h;
+  ~CsrOwner() { if (h) iexa_csr_destroy(h); }
+};
+
 extern "C" {
 
 int32_t iexa_csr_create(iexa_csr **out, int64_t nrows, int64_t ncols, int64_t nnz, const void *rows,
@@ -162,88 +176,90 @@ int32_t iexa_csr_create_keyed(iexa_csr **out, int64_t nrows, int64_t ncols, int6
                               const void *cols, int32_t idx_bytes, const int32_t *keys_in, int32_t memspace,
                               int32_t device) {
   if (!out || nnz < 0 || nrows < 0 || ncols <= 0 || (idx_bytes != 4 && idx_bytes != 8)) { g_csr_err = "bad arguments"; return IEXA_ERR_INVALID; }
+  *out = nullptr;
   if (nnz >= (1ll << 31)) { g_csr_err = "nnz exceeds int32 permutation range"; return IEXA_ERR_UNSUPPORTED; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); g_csr_err = "no CUDA device (no CPU fallback)"; return IEXA_ERR_CUDA; }
   CCK(cudaSetDevice(device));
-  iexa_csr *h = new iexa_csr();
+  CsrOwner own{new iexa_csr()};
+  iexa_csr *h = own.h;
   h->device = device; h->nrows = nrows; h->ncols = ncols; h->nnz = nnz;
-  void *dr = nullptr, *dc = nullptr;
+  TmpBuf dr, dc, keys, flag, ukeys, seg0b, first, dloc, perm2;
   const void *r = rows, *c = cols;
   if (memspace == IEXA_MEM_HOST && nnz > 0) {
-    CCK(cudaMalloc(&dr, (size_t)nnz * idx_bytes)); CCK(cudaMalloc(&dc, (size_t)nnz * idx_bytes));
-    CCK(cudaMemcpy(dr, rows, (size_t)nnz * idx_bytes, cudaMemcpyHostToDevice));
-    CCK(cudaMemcpy(dc, cols, (size_t)nnz * idx_bytes, cudaMemcpyHostToDevice));
-    r = dr; c = dc;
+    CCK(dr.alloc((size_t)nnz * idx_bytes)); CCK(dc.alloc((size_t)nnz * idx_bytes));
+    CCK(cudaMemcpy(dr.p, rows, (size_t)nnz * idx_bytes, cudaMemcpyHostToDevice));
+    CCK(cudaMemcpy(dc.p, cols, (size_t)nnz * idx_bytes, cudaMemcpyHostToDevice));
+    r = dr.p; c = dc.p;
   }
-  int64_t *keys = nullptr, *flag = nullptr, *ukeys = nullptr;
   size_t n1 = (size_t)(nnz > 0 ? nnz : 1);
-  CCK(cudaMalloc(&keys, n1 * 8)); CCK(cudaMalloc(&flag, n1 * 8));
+  CCK(keys.alloc(n1 * 8)); CCK(flag.alloc(n1 * 8));
   CCK(cudaMalloc(&h->perm, n1 * 4));
-  if (nnz > 0) {
-    if (idx_bytes == 4) make_keys<int32_t><<<grid_for(nnz), 256>>>(nnz, (const int32_t *)r, (const int32_t *)c, ncols, keys);
-    else make_keys<long long><<<grid_for(nnz), 256>>>(nnz, (const long long *)r, (const long long *)c, ncols, keys);
-    thrust::sequence(thrust::device, h->perm, h->perm + nnz);
-    thrust::stable_sort_by_key(thrust::device, keys, keys + nnz, h->perm);
-    head_flags<<<grid_for(nnz), 256>>>(nnz, keys, flag);
-    thrust::inclusive_scan(thrust::device, flag, flag + nnz, flag);
-    CCK(cudaMemcpy(&h->csr_nnz, flag + (nnz - 1), 8, cudaMemcpyDeviceToHost));
-  }
-  size_t nu = (size_t)(h->csr_nnz > 0 ? h->csr_nnz : 1);
-  int32_t *seg0 = nullptr; // segment starts in (row, col)-sorted order
-  CCK(cudaMalloc(&seg0, (nu + 1) * 4));
-  CCK(cudaMalloc(&h->colind, nu * 4));
-  CCK(cudaMalloc(&ukeys, nu * 8));
-  CCK(cudaMalloc(&h->rowptr, (size_t)(nrows + 1) * 4));
-  if (nnz > 0) {
-    fill_heads<<<grid_for(nnz), 256>>>(nnz, keys, flag, ncols, seg0, h->colind, ukeys);
-    const int32_t nnz32 = (int32_t)nnz;
-    CCK(cudaMemcpy(seg0 + h->csr_nnz, &nnz32, 4, cudaMemcpyHostToDevice));
-  } else {
-    int32_t z = 0;
-    CCK(cudaMemcpy(seg0, &z, 4, cudaMemcpyHostToDevice));
-  }
-  row_starts<<<grid_for(nrows + 1), 256>>>(nrows, ncols, ukeys, h->csr_nnz, h->rowptr);
-  CCK(cudaDeviceSynchronize());
-  cudaFree(keys); cudaFree(flag); cudaFree(ukeys);
-  // work order: CSR entries sorted by the COO position of their first source
-  const int64_t nuu = h->csr_nnz;
-  CCK(cudaMalloc(&h->order, nu * 4));
-  h->nodup = nuu == nnz && !keys_in; // with locality keys the work order is not the COO order
-  if (nuu > 0) {
-    int64_t *first = nullptr;
-    int32_t *dloc = nullptr;
-    const int32_t *loc = keys_in;
-    if (keys_in && memspace == IEXA_MEM_HOST) {
-      CCK(cudaMalloc(&dloc, n1 * 4));
-      CCK(cudaMemcpy(dloc, keys_in, (size_t)nnz * 4, cudaMemcpyHostToDevice));
-      loc = dloc;
+  try {
+    if (nnz > 0) {
+      if (idx_bytes == 4) make_keys<int32_t><<<grid_for(nnz), 256>>>(nnz, (const int32_t *)r, (const int32_t *)c, ncols, keys.as<int64_t>());
+      else make_keys<long long><<<grid_for(nnz), 256>>>(nnz, (const long long *)r, (const long long *)c, ncols, keys.as<int64_t>());
+      thrust::sequence(thrust::device, h->perm, h->perm + nnz);
+      thrust::stable_sort_by_key(thrust::device, keys.as<int64_t>(), keys.as<int64_t>() + nnz, h->perm);
+      head_flags<<<grid_for(nnz), 256>>>(nnz, keys.as<int64_t>(), flag.as<int64_t>());
+      thrust::inclusive_scan(thrust::device, flag.as<int64_t>(), flag.as<int64_t>() + nnz, flag.as<int64_t>());
+      CCK(cudaMemcpy(&h->csr_nnz, flag.as<int64_t>() + (nnz - 1), 8, cudaMemcpyDeviceToHost));
     }
-    CCK(cudaMalloc(&first, nu * 8));
-    first_source<<<grid_for(nuu), 256>>>(nuu, seg0, h->perm, loc, first);
-    thrust::sequence(thrust::device, h->order, h->order + nuu);
-    thrust::stable_sort_by_key(thrust::device, first, first + nuu, h->order);
-    cudaFree(first);
-    if (dloc) cudaFree(dloc);
-    if (!h->nodup) {
-      int32_t *perm2 = nullptr;
-      CCK(cudaMalloc(&h->seg, (nu + 1) * 4));
-      CCK(cudaMalloc(&perm2, n1 * 4));
-      seg_lengths<<<grid_for(nuu), 256>>>(nuu, seg0, h->order, h->seg);
-      CCK(cudaMemset(h->seg + nuu, 0, 4));
-      thrust::exclusive_scan(thrust::device, h->seg, h->seg + nuu + 1, h->seg);
-      regroup_sources<<<grid_for(nuu), 256>>>(nuu, seg0, h->order, h->perm, h->seg, perm2);
-      CCK(cudaDeviceSynchronize());
-      cudaFree(h->perm);
-      h->perm = perm2;
+    size_t nu = (size_t)(h->csr_nnz > 0 ? h->csr_nnz : 1);
+    CCK(seg0b.alloc((nu + 1) * 4)); // segment starts in (row, col)-sorted order
+    int32_t *seg0 = seg0b.as<int32_t>();
+    CCK(cudaMalloc(&h->colind, nu * 4));
+    CCK(ukeys.alloc(nu * 8));
+    CCK(cudaMalloc(&h->rowptr, (size_t)(nrows + 1) * 4));
+    if (nnz > 0) {
+      fill_heads<<<grid_for(nnz), 256>>>(nnz, keys.as<int64_t>(), flag.as<int64_t>(), ncols, seg0, h->colind, ukeys.as<int64_t>());
+      const int32_t nnz32 = (int32_t)nnz;
+      CCK(cudaMemcpy(seg0 + h->csr_nnz, &nnz32, 4, cudaMemcpyHostToDevice));
     } else {
-      CCK(cudaDeviceSynchronize());
-      cudaFree(h->perm); h->perm = nullptr; // identity in work order
+      int32_t z = 0;
+      CCK(cudaMemcpy(seg0, &z, 4, cudaMemcpyHostToDevice));
     }
+    row_starts<<<grid_for(nrows + 1), 256>>>(nrows, ncols, ukeys.as<int64_t>(), h->csr_nnz, h->rowptr);
+    CCK(cudaDeviceSynchronize());
+    keys.release(); flag.release(); ukeys.release();
+    // work order: CSR entries sorted by the COO position of their first source
+    const int64_t nuu = h->csr_nnz;
+    CCK(cudaMalloc(&h->order, nu * 4));
+    h->nodup = nuu == nnz && !keys_in; // with locality keys the work order is not the COO order
+    if (nuu > 0) {
+      const int32_t *loc = keys_in;
+      if (keys_in && memspace == IEXA_MEM_HOST) {
+        CCK(dloc.alloc(n1 * 4));
+        CCK(cudaMemcpy(dloc.p, keys_in, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+        loc = dloc.as<int32_t>();
+      }
+      CCK(first.alloc(nu * 8));
+      first_source<<<grid_for(nuu), 256>>>(nuu, seg0, h->perm, loc, first.as<int64_t>());
+      thrust::sequence(thrust::device, h->order, h->order + nuu);
+      thrust::stable_sort_by_key(thrust::device, first.as<int64_t>(), first.as<int64_t>() + nuu, h->order);
+      first.release(); dloc.release();
+      if (!h->nodup) {
+        CCK(cudaMalloc(&h->seg, (nu + 1) * 4));
+        CCK(perm2.alloc(n1 * 4));
+        seg_lengths<<<grid_for(nuu), 256>>>(nuu, seg0, h->order, h->seg);
+        CCK(cudaMemset(h->seg + nuu, 0, 4));
+        thrust::exclusive_scan(thrust::device, h->seg, h->seg + nuu + 1, h->seg);
+        regroup_sources<<<grid_for(nuu), 256>>>(nuu, seg0, h->order, h->perm, h->seg, perm2.as<int32_t>());
+        CCK(cudaDeviceSynchronize());
+        cudaFree(h->perm);
+        h->perm = perm2.as<int32_t>();
+        perm2.p = nullptr; // ownership moved into the handle
+      } else {
+        CCK(cudaDeviceSynchronize());
+        cudaFree(h->perm); h->perm = nullptr; // identity in work order
+      }
+    }
+  } catch (const std::exception &e) { // thrust reports allocation failures of its temporaries by throwing
+    cudaGetLastError();
+    g_csr_err = std::string("COO->CSR setup: ") + e.what();
+    return IEXA_ERR_CUDA;
   }
-  cudaFree(seg0);
-  if (dr) cudaFree(dr);
-  if (dc) cudaFree(dc);
+  own.h = nullptr;
   *out = h;
   return IEXA_OK;
 }

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 
@@ -195,6 +196,32 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__r
     __syncthreads();
   }
   if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// Device-side transcription: fp iterator columns described by a closed form (plan.hpp: HostColumn::gen_*).  numpy's /
+// InfiniteOpt's arithmetic restated operation by operation with explicitly rounded products and sums (no FMA
+// contraction), so the column is bit-identical to the one the host path would have uploaded.
+__device__ __forceinline__ double gen_pub(long long i, long long n, double a, double b, double step) {
+  return i == n - 1 ? b : __dadd_rn(a, __dmul_rn((double)i, step));
+}
+__global__ void __launch_bounds__(256) gen_column_kernel(int kind, long long K, long long n, double a, double b, double step,
+                                                         const double *__restrict__ src, double *__restrict__ out) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < K; j += (long long)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    switch (kind) {
+      case 1: v = n == 1 ? a : gen_pub(j, n, a, b, step); break;
+      case 2: v = (j & 1) ? __dmul_rn(0.5, __dadd_rn(gen_pub(j >> 1, n, a, b, step), gen_pub((j >> 1) + 1, n, a, b, step))) : gen_pub(j >> 1, n, a, b, step); break;
+      case 3: {
+        double c = 0.0;
+        if (j < K - 1) c = __ddiv_rn(__dsub_rn(src[j + 1], src[j]), 2.0);
+        if (j > 0) c = __dadd_rn(c, __ddiv_rn(__dsub_rn(src[j], src[j - 1]), 2.0));
+        v = c;
+        break;
+      }
+      case 4: v = a; break;
+    }
+    out[j] = v;
+  }
 }
 
 // zero-fill of the gradient entries no single-writer slot covers: ALL ranges in one launch (one cudaMemsetAsync per
@@ -476,6 +503,8 @@ class CudaEngine : public Engine {
   DevBuf leaf_, desc_, gens_, theta_, work_;
   DevBuf zero_ranges_;
   DevBuf partials_, fdev_, stage_x_, stage_y_, stage_v_, stage_out_, stage_a_, stage_b_, scratch_;
+  std::vector<std::unique_ptr<DevBuf>> gen_bufs_; // device-generated iterator columns
+  bool gen_failed_ = false;
   DevBuf scat_zero_[2];        // zero ranges of jtprod! / hprod! (Plan::scat_zero_ranges)
   int prod_max_nreg_[3] = {0, 0, 0}; // interpreter register file of the jv / jtv / hv programs
   bool prod_spec_tried_ = false;
@@ -496,15 +525,24 @@ class CudaEngine : public Engine {
     Plan &P = plan_;
     HostArena A; // leaf data
     std::vector<size_t> col_off(P.columns.size(), (size_t)-1);
-    auto need_col = [&](int32_t c) {
-      if (col_off[c] != (size_t)-1) return;
+    col_dev_ptr_.assign(P.columns.size(), nullptr);
+    std::vector<int32_t> gen_order; // generated columns in dependency order
+    std::function<void(int32_t)> need_col = [&](int32_t c) {
+      if (col_off[c] != (size_t)-1 || col_dev_ptr_[c]) return;
       const HostColumn &hc = P.columns[c];
       if (hc.is_int) { if (!hc.affine) col_off[c] = A.add(hc.ivals.data(), hc.ivals.size() * 4); }
-      else col_off[c] = A.add(hc.fvals.data(), hc.fvals.size() * 8);
+      else if (hc.gen_kind) { // generated on the device: own buffer, nothing uploaded
+        if (hc.gen_src >= 0) need_col(hc.gen_src);
+        gen_bufs_.emplace_back(new DevBuf());
+        if (gen_bufs_.back()->ensure((size_t)(hc.K > 0 ? hc.K : 1) * 8) != cudaSuccess) { cudaGetLastError(); gen_failed_ = true; return; }
+        col_dev_ptr_[c] = gen_bufs_.back()->p;
+        gen_order.push_back(c);
+      } else col_off[c] = A.add(hc.fvals.data(), hc.fvals.size() * 8);
     };
     std::vector<Generator *> all;
     for (auto &g : P.objs) all.push_back(&g);
     for (auto &g : P.cons) all.push_back(&g);
+    for (auto &g : P.pfuncs) all.push_back(&g); // parameter functions: value programs evaluated once, into theta
     struct Offs { size_t code[PROG__N], cpool[PROG__N], jac_slot, hess_slot, scat[2]; };
     std::vector<Offs> offs(all.size());
     for (size_t gi = 0; gi < all.size(); ++gi) {
@@ -528,12 +566,20 @@ class CudaEngine : public Engine {
       for (auto &pr2 : g.c.hess_slot) { hs.push_back(pr2.first); hs.push_back(pr2.second); }
       offs[gi].hess_slot = A.add(hs.data(), hs.size() * 4);
     }
+    if (gen_failed_) { err = "out of device memory for generated iterator columns"; return IEXA_ERR_CUDA; }
     CK(leaf_.ensure(A.bytes.size() + 16));
     CK(cudaMemcpy(leaf_.p, A.bytes.data(), A.bytes.size(), cudaMemcpyHostToDevice));
     char *lb = (char *)leaf_.p;
-    col_dev_ptr_.assign(P.columns.size(), nullptr);
     for (size_t c = 0; c < P.columns.size(); ++c)
       if (col_off[c] != (size_t)-1) col_dev_ptr_[c] = lb + col_off[c];
+    for (int32_t c : gen_order) { // produce the generated columns on the device (a TRAPEZOID column after its source)
+      const HostColumn &hc = P.columns[c];
+      const double step = hc.gen_n > 1 ? (hc.gen_b - hc.gen_a) / (double)(hc.gen_n - 1) : 0.0;
+      const int nb = (int)std::max<int64_t>(1, std::min<int64_t>((hc.K + 255) / 256, 148 * 8));
+      gen_column_kernel<<<nb, 256>>>(hc.gen_kind, hc.K, hc.gen_n, hc.gen_a, hc.gen_b, step,
+                                     hc.gen_src >= 0 ? (const double *)col_dev_ptr_[hc.gen_src] : nullptr, (double *)col_dev_ptr_[c]);
+      CK(cudaGetLastError());
+    }
 
     HostArena D; // descriptors (ColD / IdxD arrays)
     struct DOffs { size_t icol, fcol, idx; };
@@ -545,11 +591,11 @@ class CudaEngine : public Engine {
       for (int32_t s : g.c.int_cols) {
         const ColRef &r = it.int_cols[s];
         const HostColumn &hc = P.columns[r.col];
-        ic.push_back(ColD{hc.affine ? nullptr : (const void *)(lb + col_off[r.col]), r.div, r.mod, hc.aa, hc.ab, hc.ac, hc.ad});
+        ic.push_back(ColD{hc.affine ? nullptr : col_dev_ptr_[r.col], r.div, r.mod, hc.aa, hc.ab, hc.ac, hc.ad});
       }
       for (int32_t s : g.c.fp_cols) {
         const ColRef &r = it.fp_cols[s];
-        fc.push_back(ColD{(const void *)(lb + col_off[r.col]), r.div, r.mod, 0, 0, 1, 0});
+        fc.push_back(ColD{col_dev_ptr_[r.col], r.div, r.mod, 0, 0, 1, 0});
       }
       std::vector<IdxD> ix;
       for (auto &e : g.c.uidx) {
@@ -639,6 +685,24 @@ class CudaEngine : public Engine {
       table_[cb].nblocks = (int)(starts[cb + 1] - starts[cb]);
       table_[cb].max_nreg = mr[cb];
     }
+    // parameter functions: theta blocks evaluated on the device, one after the other (a later one may read an earlier
+    // one through PAR leaves), then mirrored into the host copy that iexa_get_par serves
+    for (size_t pi = 0; pi < P.pfuncs.size(); ++pi) {
+      const Generator &g = P.pfuncs[pi];
+      const int gi = nobj + ncon + (int)pi;
+      std::vector<WorkItem> pw;
+      for (int64_t b = 0; b * BLOCK < g.K; ++b) pw.push_back(WorkItem{gi, (int32_t)b});
+      if (pw.empty()) continue;
+      DevBuf wb;
+      CK(wb.ensure(pw.size() * sizeof(WorkItem)));
+      CK(cudaMemcpy(wb.p, pw.data(), pw.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+      Table T;
+      T.work = wb.as<WorkItem>(); T.nblocks = (int)pw.size(); T.max_nreg = g.c.val.nreg;
+      int rc = launch_interp(T, g.c.val.nreg, PROG_VAL, SINK_DENSE, nullptr, nullptr, nullptr, 1.0, theta_.as<double>(), nullptr, err);
+      if (rc) return rc;
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(P.theta.data() + g.o0, theta_.as<double>() + g.o0, (size_t)g.K * 8, cudaMemcpyDeviceToHost));
+    }
     return IEXA_OK;
   }
 
@@ -697,6 +761,12 @@ class CudaEngine : public Engine {
   // Page-locking is EXPLICIT (iexa_host_register): the caller knows the lifetime of its vectors.  (Pinning
   // behind the caller's back is unsafe: freed-and-remapped host memory would keep a stale registration.)
  public:
+  int get_column(int32_t col, double *out_host, std::string &err) override {
+    CK(cudaSetDevice(device_));
+    if (col < 0 || col >= (int32_t)col_dev_ptr_.size() || !col_dev_ptr_[col] || plan_.columns[col].is_int) { err = "column is not resident on the device"; return IEXA_ERR_INVALID; }
+    CK(cudaMemcpy(out_host, col_dev_ptr_[col], (size_t)plan_.columns[col].K * 8, cudaMemcpyDeviceToHost));
+    return IEXA_OK;
+  }
   int host_register(void *p, size_t bytes, std::string &err) override {
     CK(cudaSetDevice(device_));
     if (!p || bytes == 0) { err = "null buffer"; return IEXA_ERR_INVALID; }

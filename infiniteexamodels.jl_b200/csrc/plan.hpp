@@ -34,6 +34,35 @@ struct HostColumn {
   std::vector<int32_t> ivals;   // int column (narrowed; x/theta indices fit in int32)
   int32_t vmin = 0, vmax = 0;   // min / max of a stored int column (index-range queries over the whole column)
   std::vector<double> fvals;
+  // GENERATED fp column (iexa_itr_generated): described by a closed form and produced ON the device by a kernel — no
+  // K-long host array, no upload.  The formulas restate numpy / InfiniteOpt arithmetic operation by operation (each
+  // product and sum rounded once, no FMA), so the device values are bit-identical to the host path's:
+  //   LINSPACE      v(j) = a + j*step, step = (b-a)/(n-1), v(n-1) = b          (supports of an independent parameter, transform.jl:22-24)
+  //   LINSPACE_MID  the same public grid interleaved with the interval midpoints: v(2i) = pub(i), v(2i+1) = 0.5*(pub(i)+pub(i+1)), K = 2n-1
+  //                 (one internal Lobatto node per interval: OrthogonalCollocation(3), transform.jl:22)
+  //   TRAPEZOID     c(j) = (s(j+1)-s(j))/2 [j < K-1] + (s(j)-s(j-1))/2 [j > 0] of column gen_src   (InfiniteOpt's default integral, transform.jl:625-626)
+  //   CONST         v(j) = a
+  int32_t gen_kind = 0;         // 0: stored column
+  int32_t gen_src = -1;         // TRAPEZOID: index into Plan::columns
+  int64_t gen_n = 0;
+  double gen_a = 0, gen_b = 0;
+  double gen_value(int64_t j, const std::vector<HostColumn> &cols) const {
+    auto pub = [&](int64_t i) { return i == gen_n - 1 ? gen_b : gen_a + (double)i * ((gen_b - gen_a) / (double)(gen_n - 1)); };
+    switch (gen_kind) {
+      case 1: return gen_n == 1 ? gen_a : pub(j);
+      case 2: return (j & 1) ? 0.5 * (pub(j >> 1) + pub((j >> 1) + 1)) : pub(j >> 1);
+      case 3: {
+        const HostColumn &s = cols[gen_src];
+        double c = 0.0;
+        if (j < K - 1) c = (s.fp(j + 1, cols) - s.fp(j, cols)) / 2;
+        if (j > 0) c = c + (s.fp(j, cols) - s.fp(j - 1, cols)) / 2;
+        return c;
+      }
+      case 4: return gen_a;
+      default: return 0.0;
+    }
+  }
+  double fp(int64_t j, const std::vector<HostColumn> &cols) const { return gen_kind ? gen_value(j, cols) : fvals[j]; }
   int64_t ival(int64_t j) const { return affine ? aa + ab * (j / ac) + ad * (j % ac) : (int64_t)ivals[j]; }
   // v(j) = a + b*(j/c) + d*(j%c) for some period c <= 8?
   bool detect_affine(const int64_t *v, int64_t n) {
@@ -193,6 +222,80 @@ struct Plan {
     return (int32_t)itrs.size() - 1;
   }
 
+  // iterator whose columns are (partly) GENERATED: int_cols[j] == nullptr is 1..K; gens[j].kind != 0 describes fp column j
+  // by a closed form (HostColumn::gen_*), kind == 0 takes fp_cols[j] as data
+  int32_t itr_generated(int64_t K, int32_t n_int, const int64_t *const *ic, int32_t n_fp, const iexa_colgen *gens,
+                        const double *const *fc) {
+    if (K < 0) throw std::invalid_argument("iterator: negative length");
+    // integer columns: data (through the stored path: affine detection etc.) or iota
+    std::vector<std::vector<int64_t>> iota_store;
+    std::vector<const int64_t *> icp(n_int, nullptr);
+    const size_t col0 = columns.size();
+    Iterator it;
+    it.K = K;
+    for (int32_t j = 0; j < n_int; ++j) {
+      HostColumn c;
+      c.K = K; c.is_int = true;
+      if (!ic || !ic[j]) { c.iota = true; c.affine = true; c.aa = 1; c.ab = 1; c.ac = 1; c.ad = 0; }
+      else {
+        c.iota = true;
+        for (int64_t k = 0; k < K; ++k) if (ic[j][k] != k + 1) { c.iota = false; break; }
+        if (c.iota) { c.affine = true; c.aa = 1; c.ab = 1; c.ac = 1; c.ad = 0; }
+        else c.detect_affine(ic[j], K);
+        if (!c.affine) {
+          c.ivals.resize(K);
+          for (int64_t k = 0; k < K; ++k) {
+            if (ic[j][k] < INT32_MIN || ic[j][k] > INT32_MAX) throw std::invalid_argument("iterator: integer field exceeds int32");
+            c.ivals[k] = (int32_t)ic[j][k];
+          }
+          if (K > 0) { c.vmin = *std::min_element(c.ivals.begin(), c.ivals.end()); c.vmax = *std::max_element(c.ivals.begin(), c.ivals.end()); }
+        }
+      }
+      it.int_cols.push_back(ColRef{(int32_t)columns.size(), 1, K > 0 ? K : 1});
+      columns.push_back(std::move(c));
+    }
+    const size_t fcol0 = columns.size();
+    for (int32_t j = 0; j < n_fp; ++j) {
+      HostColumn c;
+      c.K = K; c.is_int = false;
+      const iexa_colgen &gs = gens[j];
+      if (gs.kind == 0) {
+        if (!fc || !fc[j]) throw std::invalid_argument("iterator: fp column without data or generator");
+        c.fvals.assign(fc[j], fc[j] + K);
+      } else {
+        c.gen_kind = gs.kind; c.gen_n = gs.n; c.gen_a = gs.a; c.gen_b = gs.b;
+        if (gs.kind == 1 && (gs.n != K || K < 1)) throw std::invalid_argument("generated column: LINSPACE needs n == K >= 1");
+        if (gs.kind == 2 && (gs.n < 2 || 2 * gs.n - 1 != K)) throw std::invalid_argument("generated column: LINSPACE_MID needs K == 2n-1, n >= 2");
+        if (gs.kind == 3) {
+          if (gs.src < 0 || gs.src >= j) throw std::invalid_argument("generated column: TRAPEZOID needs an earlier fp column of the same iterator");
+          c.gen_src = (int32_t)(fcol0 + gs.src);
+        }
+        if (gs.kind < 0 || gs.kind > 4) throw std::invalid_argument("generated column: unknown kind");
+      }
+      it.fp_cols.push_back(ColRef{(int32_t)columns.size(), 1, K > 0 ? K : 1});
+      columns.push_back(std::move(c));
+    }
+    (void)col0;
+    itrs.push_back(std::move(it));
+    return (int32_t)itrs.size() - 1;
+  }
+
+  // Parameter functions (transform.jl:161-183: a block of theta holding f(supports) at every support combination) as
+  // TAPES: the engine evaluates them on the device at finalize with the same register programs / interpreter kernel as
+  // a constraint's value — no O(K) closure calls on the host, no upload of the block.  Leaves: literals, fp fields of the
+  // iterator, theta (finite parameters added earlier).
+  std::vector<Generator> pfuncs;
+  int64_t add_par_function(const iexa_node *nodes, int32_t n, const iexa_index *idx, int32_t n_idx, int32_t itr) {
+    for (int32_t i = 0; i < n; ++i) if (nodes[i].op == IEXA_OP_VAR) throw std::invalid_argument("parameter function: variables are not allowed");
+    Generator g = make_gen(nodes, n, idx, n_idx, itr, false);
+    const int64_t off = npar;
+    g.o0 = g.l0 = off; g.k0 = 0; g.k1 = g.K;
+    theta.resize(theta.size() + g.K, 0.0);
+    npar += g.K;
+    pfuncs.push_back(std::move(g));
+    return off;
+  }
+
   int32_t itr_product(int32_t n, const int32_t *ids) {
     Iterator it;
     it.K = 1;
@@ -248,7 +351,7 @@ struct Plan {
   }
   double fp_col_value(const Generator &g, int32_t slot, int64_t k) const {
     const ColRef &r = itrs[g.itr].fp_cols[g.c.fp_cols[slot]];
-    return columns[r.col].fvals[(k / r.div) % r.mod];
+    return columns[r.col].fp((k / r.div) % r.mod, columns);
   }
   int64_t index_value(const Generator &g, int32_t islot, int64_t k) const {
     const IndexExpr &e = g.c.uidx[islot];

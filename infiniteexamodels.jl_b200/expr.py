@@ -305,3 +305,46 @@ def lower(expr, int_cols: List[str], fp_cols: List[str]) -> Tape:
             ix[i]["col"][t] = c
             ix[i]["coef"][t] = coef
     return Tape(arr, ix[: len(idx_rows)] if idx_rows else ix[:0], nvar)
+
+
+def eval_numpy(tape: Tape, fp_cols, theta, K: int) -> np.ndarray:
+    """value of a tape without Var leaves at every support, with numpy (the HOST statement of a parameter function —
+    transform.jl:161-183 calls the Julia closure per support; the engine evaluates the same tape on the device).
+    PAR leaves with constant indices read ``theta``."""
+    D2R = np.pi / 180.0
+    un = {OP["NEG"]: np.negative, OP["POS"]: lambda u: u, OP["INV"]: lambda u: 1.0 / u, OP["SQRT"]: np.sqrt, OP["CBRT"]: np.cbrt,
+          OP["ABS"]: np.abs, OP["ABS2"]: lambda u: u * u, OP["EXP"]: np.exp, OP["EXP2"]: np.exp2, OP["LOG"]: np.log,
+          OP["LOG2"]: np.log2, OP["LOG10"]: np.log10, OP["LOG1P"]: np.log1p, OP["SIN"]: np.sin, OP["COS"]: np.cos,
+          OP["TAN"]: np.tan, OP["ASIN"]: np.arcsin, OP["ACOS"]: np.arccos, OP["ATAN"]: np.arctan,
+          OP["SINH"]: np.sinh, OP["COSH"]: np.cosh, OP["TANH"]: np.tanh, OP["ATANH"]: np.arctanh,
+          OP["SIND"]: lambda u: np.sin(u * D2R), OP["COSD"]: lambda u: np.cos(u * D2R), OP["TAND"]: lambda u: np.tan(u * D2R)}
+    vals = []
+    for nd in tape.nodes:
+        op, a, b, c = int(nd["op"]), int(nd["a"]), int(nd["b"]), float(nd["c"])
+        if op == OP["CONST"]:
+            v = np.full(K, c)
+        elif op == OP["FIELD"]:
+            v = np.asarray(fp_cols[a], dtype=np.float64)
+        elif op == OP["PAR"]:
+            ix = tape.index[a]
+            if int(ix["nterms"]) != 0:
+                raise ValueError("parameter functions may reference finite parameters only")
+            v = np.full(K, float(theta[int(ix["base"]) - 1]))
+        elif op == OP["VAR"]:
+            raise ValueError("parameter functions cannot reference variables")
+        elif op == OP["ADD"]:
+            v = vals[a] + vals[b]
+        elif op == OP["SUB"]:
+            v = vals[a] - vals[b]
+        elif op == OP["MUL"]:
+            v = vals[a] * vals[b]
+        elif op == OP["DIV"]:
+            v = vals[a] / vals[b]
+        elif op == OP["POW"]:
+            v = vals[a] * vals[a] if np.all(vals[b] == 2.0) else np.power(vals[a], vals[b])
+        elif op in un:
+            v = un[op](vals[a])
+        else:
+            raise ValueError(f"eval_numpy: operator {op} not supported in parameter functions")
+        vals.append(v)
+    return np.ascontiguousarray(vals[-1], dtype=np.float64)

@@ -25,6 +25,10 @@ class Meta(C.Structure):
                [(n, C.c_int32) for n in ("minimize", "rank", "world", "device", "n_kernels_specialised", "pad")]
 
 
+class ColGen(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("src", C.c_int32), ("n", C.c_int64), ("a", C.c_double), ("b", C.c_double)]
+
+
 class Segment(C.Structure):
     _fields_ = [("global_start", C.c_int64), ("local_start", C.c_int64), ("length", C.c_int64)]
 
@@ -32,12 +36,12 @@ class Segment(C.Structure):
 # every symbol include/iexa.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "iexa_last_error", "iexa_version", "iexa_plan_create", "iexa_plan_destroy", "iexa_set_option", "iexa_add_var",
-    "iexa_add_par", "iexa_patch_var", "iexa_itr_base", "iexa_itr_product", "iexa_add_con",
+    "iexa_add_par", "iexa_patch_var", "iexa_itr_base", "iexa_itr_generated", "iexa_add_par_function", "iexa_debug_get_column", "iexa_itr_product", "iexa_add_con",
     "iexa_add_obj", "iexa_finalize", "iexa_get_meta", "iexa_get_vector", "iexa_set_vector",
     "iexa_set_par", "iexa_set_par_stream", "iexa_get_par", "iexa_jac_structure", "iexa_hess_structure", "iexa_obj",
     "iexa_grad", "iexa_cons", "iexa_jac_coord", "iexa_hess_coord", "iexa_jprod", "iexa_jtprod",
     "iexa_hprod", "iexa_obj_device", "iexa_host_register", "iexa_host_unregister", "iexa_segments", "iexa_shared_vars", "iexa_shared_ranges", "iexa_host_x_bytes", "iexa_x_ranges", "iexa_algorithmic_bytes",
-    "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_set_class_mode", "iexa_debug_codegen_compile",
+    "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_set_class_mode", "iexa_debug_codegen_compile", "iexa_debug_cache_stats",
     "iexa_halo_create", "iexa_halo_export", "iexa_halo_connect", "iexa_halo_set_sends", "iexa_halo_set_recvs", "iexa_halo_exchange",
     "iexa_halo_allreduce_small", "iexa_halo_status", "iexa_halo_destroy",
     "iexa_csr_create", "iexa_csr_create_keyed", "iexa_coo_locality", "iexa_csr_destroy", "iexa_csr_nnz", "iexa_csr_pattern", "iexa_csr_apply",
@@ -61,6 +65,9 @@ def _declare(L):
     sig("iexa_add_par", _i32, _vp, _i64, _vp, C.POINTER(_i64))
     sig("iexa_patch_var", _i32, _vp, _i32, _i64, _dbl)
     sig("iexa_itr_base", _i32, _vp, _i64, _i32, _vp, _i32, _vp, C.POINTER(_i32))
+    sig("iexa_itr_generated", _i32, _vp, _i64, _i32, _vp, _i32, _vp, _vp, C.POINTER(_i32))
+    sig("iexa_add_par_function", _i32, _vp, _vp, _i32, _vp, _i32, _i32, C.POINTER(_i64))
+    sig("iexa_debug_get_column", _i32, _vp, _i32, _i32, _vp)
     sig("iexa_itr_product", _i32, _vp, _i32, _vp, C.POINTER(_i32))
     sig("iexa_add_con", _i32, _vp, _vp, _i32, _vp, _i32, _i32, _dbl, _dbl, C.POINTER(_i64))
     sig("iexa_add_obj", _i32, _vp, _vp, _i32, _vp, _i32, _i32)
@@ -95,6 +102,7 @@ def _declare(L):
     sig("iexa_debug_codegen_source", _i64, _vp, _vp, _i64)
     sig("iexa_debug_codegen_compile", _i32, _vp, C.POINTER(_i64))
     sig("iexa_debug_set_class_mode", _i32, _vp, _i32)
+    sig("iexa_debug_cache_stats", _i32, C.POINTER(_i32), C.POINTER(_i32))
     sig("iexa_csr_create", _i32, C.POINTER(_vp), _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32)
     sig("iexa_csr_create_keyed", _i32, C.POINTER(_vp), _i64, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _i32)
     sig("iexa_coo_locality", _i32, _vp, _i32, _vp, _i32, _vp)

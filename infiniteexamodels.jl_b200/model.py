@@ -67,8 +67,6 @@ class ExaModel:
         if core.nvar:
             _lib.check(L, L.iexa_add_var(h, core.nvar, x0.ctypes.data, lv.ctypes.data, uv.ctypes.data, C.byref(off)))
         th = np.ascontiguousarray(core.theta_vec, dtype=np.float64)
-        if core.npar:
-            _lib.check(L, L.iexa_add_par(h, core.npar, th.ctypes.data, C.byref(off)))
         itr_ids = {}
 
         def itr_id(it: Itr) -> int:
@@ -81,6 +79,20 @@ class ExaModel:
                     return 0
                 ic = [it.ints[n] for n in it.ints]
                 fc = [it.fps[n] for n in it.fps]
+                if getattr(it, "gens", None) or getattr(it, "iota", None):
+                    # device-side transcription: generated fp columns / iota int columns are DESCRIBED, not passed as data
+                    icp = (C.c_void_p * max(len(ic), 1))(*[None if n in it.iota else it.ints[n].ctypes.data for n in it.ints])
+                    fcp = (C.c_void_p * max(len(fc), 1))(*[None if n in it.gens else it.fps[n].ctypes.data for n in it.fps])
+                    gens = (_lib.ColGen * max(len(fc), 1))()
+                    names = list(it.fps)
+                    for j, n in enumerate(names):
+                        g = it.gens.get(n)
+                        if g is not None:
+                            gens[j].kind, gens[j].n, gens[j].a, gens[j].b = g.kind, g.n, g.a, g.b
+                            gens[j].src = names.index(g.src) if g.src is not None else -1
+                    _lib.check(L, L.iexa_itr_generated(h, it.K, len(ic), icp, len(fc), gens, fcp, C.byref(out)))
+                    itr_ids[id(it)] = out.value
+                    return out.value
                 icp = (C.c_void_p * max(len(ic), 1))(*[c.ctypes.data for c in ic])
                 fcp = (C.c_void_p * max(len(fc), 1))(*[c.ctypes.data for c in fc])
                 _lib.check(L, L.iexa_itr_base(h, it.K, len(ic), icp, len(fc), fcp, C.byref(out)))
@@ -90,6 +102,18 @@ class ExaModel:
             itr_ids[id(it)] = out.value
             return out.value
 
+        # theta: data blocks through iexa_add_par, parameter FUNCTIONS as tapes the engine evaluates on the device
+        pos = 0
+        for par, tape, pit in sorted(getattr(core, "par_functions", []), key=lambda t: t[0].offset):
+            if par.offset > pos:
+                _lib.check(L, L.iexa_add_par(h, par.offset - pos, th[pos:].ctypes.data, C.byref(off)))
+            nodes = np.ascontiguousarray(tape.nodes); index = np.ascontiguousarray(tape.index)
+            _lib.check(L, L.iexa_add_par_function(h, nodes.ctypes.data, len(nodes), index.ctypes.data if len(index) else None,
+                                                  len(index), itr_id(pit), C.byref(off)))
+            assert off.value == par.offset
+            pos = par.offset + par.length
+        if core.npar > pos:
+            _lib.check(L, L.iexa_add_par(h, core.npar - pos, th[pos:].ctypes.data, C.byref(off)))
         for g in core.gens:
             nodes = np.ascontiguousarray(g.tape.nodes)
             index = np.ascontiguousarray(g.tape.index)

@@ -29,10 +29,12 @@ def trapezoid_coeffs(s: np.ndarray) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------------------------
-def quadrotor(num_supports: int = 100, method: str = "oc", T_end: float = 60.0) -> ExaCore:
+def quadrotor(num_supports: int = 100, method: str = "oc", T_end: float = 60.0, device_side: bool = False) -> ExaCore:
     """ESCAPE34/quadrotor.jl:4-76 (``method='oc'``: OrthogonalCollocation(3) + piecewise-constant
     controls, config 3) and examples/quadrotor.jl:7-77 (``method='fd'``: default backward finite
-    difference, config 1)."""
+    difference, config 1).  ``device_side=True`` (OC only): the time supports, the trapezoid weights and the parameter
+    functions d1, d3, d5 are DESCRIBED (generated columns, tapes) and produced on the device by the engine instead of
+    being computed here and uploaded (transform.jl:2-38,161-183,618-633 on the device)."""
     N = int(num_supports)
     pub = np.linspace(0.0, T_end, N)
     if method == "oc":  # one internal Lobatto node (midpoint) per interval: transform.jl:22
@@ -46,16 +48,26 @@ def quadrotor(num_supports: int = 100, method: str = "oc", T_end: float = 60.0) 
     core = ExaCore(minimize=True)
     ds = DataSource()
     iota = np.arange(1, T + 1)
-    base = Itr(T, {"group_idx1": iota}, {"ip1": ts})                       # transform.jl:31
+    if device_side and method == "oc":
+        from .core import linspace_mid_col, trapezoid_col
+        base = Itr(T, {"group_idx1": None}, {"ip1": linspace_mid_col(0.0, T_end, N)})
+        ts = base.fps["ip1"]              # numpy statement of the generated column (bit-identical by construction)
+    else:
+        base = Itr(T, {"group_idx1": iota}, {"ip1": ts})                       # transform.jl:31
 
     # x layout (transform.jl:134-158): x[1:9], u[1:4] then the derivative variables ∂x[1:9]
     x = [core.add_var(T) for _ in range(9)]
     u = [core.add_var(T, start=0.0) for _ in range(4)]
     dx = [core.add_var(T) for _ in range(9)]
     # θ layout (transform.jl:161-183): parameter functions d1, d3, d5 evaluated at every support
-    d1 = core.add_par(np.sin(2 * np.pi * ts / T_end))
-    d3 = core.add_par(2 * np.sin(4 * np.pi * ts / T_end))
-    d5 = core.add_par(2 * (ts / T_end))
+    if device_side and method == "oc":
+        d1 = core.add_par_function(sin((2 * np.pi) * ds.ip1 / T_end), base)
+        d3 = core.add_par_function(2.0 * sin((4 * np.pi) * ds.ip1 / T_end), base)
+        d5 = core.add_par_function(2.0 * (ds.ip1 / T_end), base)
+    else:
+        d1 = core.add_par(np.sin(2 * np.pi * ts / T_end))
+        d3 = core.add_par(2 * np.sin(4 * np.pi * ts / T_end))
+        d5 = core.add_par(2 * (ts / T_end))
 
     i = ds.group_idx1
     X = [None] + [v[i] for v in x]      # 1-based like the Julia source
@@ -108,7 +120,10 @@ def quadrotor(num_supports: int = 100, method: str = "oc", T_end: float = 60.0) 
             core.add_con(u[j][ds.i1] - u[j][ds.i2], col)
 
     # objective: one measure -> one generator c·(quadratic integrand) (transform.jl:693-702)
-    mitr = Itr(T, {"group_idx1": iota}, {"c": trapezoid_coeffs(ts), "ip1": ts})
+    if device_side and method == "oc":
+        mitr = Itr(T, {"group_idx1": None}, {"ip1": linspace_mid_col(0.0, T_end, N), "c": trapezoid_col("ip1")})
+    else:
+        mitr = Itr(T, {"group_idx1": iota}, {"c": trapezoid_coeffs(ts), "ip1": ts})
     P1, P3, P5 = d1[i], d3[i], d5[i]
     quad = (abs2(X[1]) + (-2.0) * X[1] * P1 + abs2(P1)
             + abs2(X[3]) + (-2.0) * X[3] * P3 + abs2(P3)

@@ -226,6 +226,29 @@ function NLPModels.hprod!(m::B200ExaModel, x::AbstractVector, y::AbstractVector,
     return Hv
 end
 
+# ---- device-side transcription: columns described by a closed form, parameter functions as tapes ------------------------
+struct IexaColGen
+    kind::Int32
+    src::Int32
+    n::Int64
+    a::Float64
+    b::Float64
+end
+"iterator whose fp columns are generated ON the device (kind 1 linspace, 2 linspace + interval midpoints, 3 trapezoid weights of column `src`, 4 constant); `int_cols[j] == C_NULL` is 1:K"
+function itr_generated(h::Ptr{Cvoid}, K::Integer, int_cols::Vector{Ptr{Int64}}, gens::Vector{IexaColGen}, fp_cols::Vector{Ptr{Float64}})
+    out = Ref{Int32}(0)
+    check(ccall((:iexa_itr_generated, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Ptr{Ptr{Int64}}, Int32, Ptr{IexaColGen}, Ptr{Ptr{Float64}}, Ref{Int32}),
+                h, K, length(int_cols), int_cols, length(gens), gens, fp_cols, out))
+    return out[]
+end
+"a parameter function (transform.jl:161-183) as a tape over iterator `itr`: its block of θ is evaluated on the device at finalize"
+function add_par_function(h::Ptr{Cvoid}, nodes::Vector{IexaNode}, idx::Vector{IexaIndex}, itr::Integer)
+    off = Ref{Int64}(0)
+    check(ccall((:iexa_add_par_function, LIB), Int32, (Ptr{Cvoid}, Ptr{IexaNode}, Int32, Ptr{IexaIndex}, Int32, Int32, Ref{Int64}),
+                h, nodes, length(nodes), idx, length(idx), itr, off))
+    return off[]
+end
+
 "plan options (before the first generator): key 1 = slot-order policy (0 left to right, 1 right to left), key 2 = strict IEEE"
 set_option!(h::Ptr{Cvoid}, key::Integer, value::Integer) =
     check(ccall((:iexa_set_option, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), h, key, value))

@@ -165,3 +165,33 @@ def test_shape_classes_match_oracle(hostcheck_lib):
         assert_close(_hc(L, m, "hostcheck_eval_groups", which, len(ref), x, y, 0.7 if which == 4 else 1.0), np.asarray(ref), str(which))
     nb = C.c_int64()
     assert L.iexa_debug_codegen_compile(m.h, C.byref(nb)) == 0, L.iexa_last_error().decode()
+
+
+def test_cubin_disk_cache_roundtrip_and_corruption(tmp_path):
+    """compiled images are kept on disk keyed by the generated source: a second PROCESS loads instead of compiling; a
+    truncated / foreign file under the same name is ignored (and replaced)"""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys, ctypes as C; sys.path.insert(0, %r); import iexa_b200 as ex; from iexa_b200 import models\n"
+            "m = ex.ExaModel(models.quadrotor(20, 'oc'), flags=ex.lib.IEXA_F_NO_DEVICE)\n"
+            "nb = C.c_int64(0); assert m.L.iexa_debug_codegen_compile(m.h, C.byref(nb)) == 0, m.L.iexa_last_error()\n"
+            "a, b = C.c_int32(), C.c_int32(); m.L.iexa_debug_cache_stats(C.byref(a), C.byref(b)); print(a.value, b.value, nb.value)\n"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, IEXA_CACHE_DIR=str(tmp_path))
+    env.pop("IEXA_DUMP_DIR", None)
+    run = lambda: subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.split()
+    first = run()
+    assert first[:2] == ["1", "0"]
+    files = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert len(files) == 1
+    second = run()
+    assert second[:2] == ["0", "1"] and second[2] == first[2]
+    path = os.path.join(tmp_path, files[0])
+    with open(path, "r+b") as f:   # corrupt the header: the entry must be ignored, recompiled and rewritten
+        f.seek(8); f.write(b"\xff" * 8)
+    third = run()
+    assert third[:2] == ["1", "0"]
+    assert run()[:2] == ["0", "1"]
+    off = subprocess.run([sys.executable, "-c", code], env=dict(env, IEXA_CACHE_DIR="off"), capture_output=True, text=True, check=True).stdout.split()
+    assert off[:2] == ["1", "0"]
