@@ -161,12 +161,16 @@ class GenCompiler {
   // exists ("parity unpinned") — so it is DATA: 0 = children left to right (inner1 then inner2), 1 = right
   // to left (inner2 then inner1; cross pairs (inner2-leaf, inner1-leaf)).  Oracle and product honour the same value.
   int order_ = 0;
-  void set_options(int slot_order, bool strict) { order_ = slot_order; dag_.strict = strict || dag_.strict; }
+  void set_options(int slot_order, bool strict) {
+    order_ = slot_order;
+    dag_.strict = strict;
+    if (const char *e = getenv("IEXA_STRICT_IEEE")) dag_.strict = e[0] != '0'; // experiments: override the plan's choice
+  }
 
  private:
   void init(const iexa_node *nodes, const iexa_index *idx, int32_t n_idx) {
     if (n_ <= 0) throw std::invalid_argument("empty tape");
-    if (const char *e = getenv("IEXA_STRICT_IEEE")) dag_.strict = e[0] == '1';
+
     g.tape.assign(nodes, nodes + n_);
     if (n_idx > 0) g.raw_idx.assign(idx, idx + n_idx);
     canon_indices(idx, n_idx);

@@ -51,7 +51,7 @@ class ExaModel:
     """``ExaModels.ExaModel(core)`` (infiniteopt_backend.jl:156) backed by the CUDA engine."""
 
     def __init__(self, core: ExaCore, device: int = 0, rank: int = 0, world: int = 1,
-                 flags: int = _lib.IEXA_F_DEFAULT, library=None, slot_order: int = 0, strict_ieee: bool = False):
+                 flags: int = _lib.IEXA_F_DEFAULT, library=None, slot_order: int = 0, strict_ieee: Optional[bool] = None):
         self.L = L = library or _lib.load()
         self.core = core
         h = C.c_void_p()
@@ -59,8 +59,8 @@ class ExaModel:
         self.h = h
         if slot_order:
             _lib.check(L, L.iexa_set_option(h, _lib.IEXA_OPT_SLOT_ORDER, int(slot_order)))
-        if strict_ieee:
-            _lib.check(L, L.iexa_set_option(h, _lib.IEXA_OPT_STRICT_IEEE, 1))
+        if strict_ieee is not None:   # None: the engine's default (strict)
+            _lib.check(L, L.iexa_set_option(h, _lib.IEXA_OPT_STRICT_IEEE, int(bool(strict_ieee))))
         self._keep = []
         off = C.c_int64()
         x0, lv, uv = (np.ascontiguousarray(v, dtype=np.float64) for v in (core.x0_vec, core.lvar_vec, core.uvar_vec))

@@ -346,7 +346,7 @@ def test_strict_ieee_mode_reproduces_the_oracles_nan_pattern_on_the_gpu(name, po
     from oracle.oracle import OracleModel
     core = CASES[name]()
     om = OracleModel(core)
-    m = ex.ExaModel(core, device=0, strict_ieee=True)
+    m = ex.ExaModel(core, device=0)   # IEEE-strict is the default
     x, y = eval_point(core, seed=2)
     rng = np.random.default_rng(1)
     x[rng.choice(core.nvar, size=max(1, core.nvar // 10), replace=False)] = poison
@@ -357,5 +357,7 @@ def test_strict_ieee_mode_reproduces_the_oracles_nan_pattern_on_the_gpu(name, po
                      (ex.jac_coord_(m, xd, z(om.nnzj)).cpu().numpy()[: om.nnzj], om.jac_coord(x)),
                      (ex.hess_coord_(m, xd, yd, z(om.nnzh), 0.7).cpu().numpy()[: om.nnzh], om.hess_coord(x, y, 0.7))):
         assert np.array_equal(np.isnan(got), np.isnan(ref)), "NaN pattern differs from the oracle's"
-        fin = ~np.isnan(ref)
+        inf = np.isinf(ref)
+        assert np.array_equal(got[inf], ref[inf]), "infinite entries differ"
+        fin = np.isfinite(ref)
         assert_close(got[fin], ref[fin], "finite entries")

@@ -1,7 +1,8 @@
 """NaN / Inf semantics.  The reference's evaluator is a run-time AD: it multiplies numbers, so a structural zero times an
-infinite or NaN partial is NaN.  The engine differentiates symbolically and, by default, folds 0*x -> 0 (identical results
-for finite inputs, a SUBSET of the NaNs otherwise).  With IEXA_OPT_STRICT_IEEE the structural zeros are multiplied at run
-time and the NaN PATTERN of every callback equals the oracle's on poisoned inputs — for every BASELINE configuration.
+infinite or NaN partial is NaN.  The engine differentiates symbolically; by DEFAULT (IEXA_OPT_STRICT_IEEE = 1) it keeps
+structural zeros as run-time multiplications, and the NaN PATTERN of every callback equals the oracle's on poisoned inputs —
+for every BASELINE configuration.  IEXA_OPT_STRICT_IEEE = 0 folds 0*x -> 0: identical results for finite inputs, a SUBSET
+of the NaNs otherwise (1.5-2.5 % faster on B200).
 abs'(0) = +1 (sign(+0) taken as +1) in oracle and engine alike (src/operators.jl:14)."""
 import ctypes as C
 
@@ -50,8 +51,8 @@ def test_strict_mode_reproduces_the_oracles_nan_pattern(name, poison, hostcheck_
     L = hostcheck_lib
     core = CASES[name]()
     om = OracleModel(core)
-    strict = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L, strict_ieee=True)
-    folded = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L)
+    strict = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L)   # the default IS strict
+    folded = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L, strict_ieee=False)
     x, y = eval_point(core)
     x = np.where(np.isfinite(x), x, 0.0)
     rng = np.random.default_rng(1)
