@@ -233,6 +233,13 @@ int32_t iexa_jac_coord(iexa_plan *p, const double *x, double *vals, int32_t mems
 /* y may be NULL (objective-only Hessian)                                               */
 int32_t iexa_hess_coord(iexa_plan *p, const double *x, const double *y, double obj_weight,
                         double *vals, int32_t memspace, void *stream);
+/* cons! + jac_coord! + hess_coord! at the SAME (x, y) in one call — what an interior-point iteration asks for (MadNLP's
+ * eval_f / eval_cons / eval_jac / eval_lag_hess wrappers all run at the current iterate).  Device buffers: ONE fused kernel —
+ * every constraint group evaluates value, first and second order from one program (x / theta / columns loaded once, sin /
+ * cos of a state once) — instead of three launches with three fill / drain phases; results are identical to the three
+ * callbacks.  Host buffers, or when the fused kernel is unavailable: the three callbacks in sequence (x uploaded once). */
+int32_t iexa_eval3(iexa_plan *p, const double *x, const double *y, double obj_weight, double *c, double *jac_vals,
+                   double *hess_vals, int32_t memspace, void *stream);
 /* Matrix-free products (NLPModels jprod! / jtprod! / hprod!: the model handed to the solver at
  * ext/InfiniteExaModelsMadNLP.jl:49-50 / ext/InfiniteExaModelsIpopt.jl:48-49 carries the full API).  Fused kernels:
  * the first / second order programs with a product epilogue — no COO values are written or read.
@@ -305,6 +312,9 @@ int64_t iexa_debug_codegen_source(const iexa_plan *p, char *buf, int64_t cap);
 /* regroup a host-only plan with (1) / without (0) shape canonicalisation before inspecting its source */
 int32_t iexa_debug_set_class_mode(iexa_plan *p, int32_t on);
 int32_t iexa_debug_codegen_compile(const iexa_plan *p, int64_t *cubin_bytes);
+/* the same for a named kernel set: 0 = the five callbacks, 1 = jprod! / jtprod! / hprod!, 2 = the fused iexa_eval3 kernel */
+int64_t iexa_debug_codegen_source_of(const iexa_plan *p, int32_t set, char *buf, int64_t cap);
+int32_t iexa_debug_codegen_compile_of(const iexa_plan *p, int32_t set, int64_t *cubin_bytes);
 /* compiled images are cached per process AND on disk ($IEXA_CACHE_DIR | $XDG_CACHE_HOME/iexa_b200 | ~/.cache/iexa_b200;
  * IEXA_CACHE_DIR=off disables), keyed by the generated source: counts of NVRTC compilations / disk hits of this process */
 int32_t iexa_debug_cache_stats(int32_t *nvrtc_compiles, int32_t *disk_hits);

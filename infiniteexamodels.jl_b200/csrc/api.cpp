@@ -303,6 +303,10 @@ int32_t iexa_hess_coord(iexa_plan *p, const double *x, const double *y, double o
                         int32_t memspace, void *stream) {
   ENGINE_CALL(hess(x, y, obj_weight, vals, memspace, stream, err))
 }
+int32_t iexa_eval3(iexa_plan *p, const double *x, const double *y, double obj_weight, double *c, double *jac_vals, double *hess_vals,
+                   int32_t memspace, void *stream) {
+  ENGINE_CALL(eval3(x, y, obj_weight, c, jac_vals, hess_vals, memspace, stream, err))
+}
 int32_t iexa_jprod(iexa_plan *p, const double *x, const double *v, double *Jv, int32_t memspace, void *stream) {
   ENGINE_CALL(jprod(x, v, Jv, memspace, stream, err))
 }
@@ -502,6 +506,27 @@ int64_t iexa_debug_codegen_source(const iexa_plan *p, char *buf, int64_t cap) {
     buf[n] = 0;
   }
   return (int64_t)src.size();
+}
+int64_t iexa_debug_codegen_source_of(const iexa_plan *p, int32_t set, char *buf, int64_t cap) {
+  if (!p || !p->plan.finalized || set < 0 || set > 2) return -1;
+  std::string src = iexa::Specialiser::generate_source(p->plan, set);
+  if (buf && cap > 0) {
+    size_t n = std::min<size_t>((size_t)cap - 1, src.size());
+    std::memcpy(buf, src.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)src.size();
+}
+int32_t iexa_debug_codegen_compile_of(const iexa_plan *p, int32_t set, int64_t *cubin_bytes) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (!p->plan.finalized || set < 0 || set > 2) return fail(IEXA_ERR_STATE, "plan not finalized / bad kernel set");
+  std::string src = iexa::Specialiser::generate_source(p->plan, set), err;
+  std::vector<char> cubin;
+  if (!iexa::compile_cubin(src, cubin, err)) return fail(IEXA_ERR_NVRTC, err);
+  if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+  return IEXA_OK;
+  GUARD_END
 }
 int32_t iexa_debug_set_class_mode(iexa_plan *p, int32_t on) {
   GUARD_BEGIN

@@ -147,7 +147,7 @@ enum { SINK_DENSE = 0, SINK_SUM = 1, SINK_SCATTER = 2 };
 constexpr int kMaxStagedStep = 64; // members with more slots than this store directly
 // measured on B200 (config 3): capping registers at 64 (8 blocks of 128 threads per SM) lifts hess from 64% to 82% of the
 // HBM roofline and cons/jac by 3 points; the occasional spill stays in L1
-static const int kDefaultMinBlocks[KS__N] = {8, 8, 8, 8, 8, 8, 8, 8, 8, 8};
+static const int kDefaultMinBlocks[KS__N] = {8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 6};
 int spec_block() {
   // threads per block of the specialised kernels (a multiple of 32).  Measured on B200, config 3:
   // 128 -> 0.585 ms/eval, 64 -> 0.597, 32 -> 0.627; on a 1/8 shard 64 and 128 tie (0.092 ms).
@@ -180,7 +180,7 @@ static bool use_pdl() { static bool v = [] { const char *e = getenv("IEXA_PDL");
 //   the final kernels 0.134 (4) / 0.129 (8) / 0.132 (12) at 48 registers and 0.126 (all) at 64 registers (8 blocks/SM).
 // slots 5..9 (jprod, jtprod phases 0/1, hprod phases 0/1): IEXA_HOIST_PROD="<jprod>,<jtprod>,<hprod>"
 static int hoist_loads(int cb) {
-  static int v[KS__N] = {-1, -1, -1, -1, 16, 24, 24, 24, 16, 16};
+  static int v[KS__N] = {-1, -1, -1, -1, 16, 24, 24, 24, 16, 16, 16};
   static bool init = [] {
     if (const char *e = getenv("IEXA_HOIST")) {
       int w[5] = {v[0], v[1], v[2], v[3], v[4]};
@@ -202,7 +202,7 @@ static int hoist_loads(int cb) {
 // Measured on B200, config 3: cons 0.138 -> 0.130 ms (its collocation rows are 38 loads of pure index arithmetic),
 // jac 0.226 -> 0.234 ms, hess unchanged: on for the value kernels only.
 static bool idx32_for(int cb) {
-  static int v[KS__N] = {1, 0, 1, 0, 0, 1, 0, 0, 0, 0};
+  static int v[KS__N] = {1, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0};
   static bool init = [] {
     if (const char *e = getenv("IEXA_IDX32")) sscanf(e, "%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4]);
     return true;
@@ -279,6 +279,12 @@ struct BodyGen {
   std::vector<std::string> ixname;
   bool use32, idx32;
   size_t smem_doubles = 0;
+  std::string outname = "out";  // objective groups inside the fused eval3 kernel write their Hessian slots to out3
+  // fused eval3 body: outputs of member m and program p (0 value, 1 first, 2 second order) form the "virtual member" 3m+p
+  bool fused3() const { return prog == GPROG_ALL; }
+  int mem_of(int vm) const { return fused3() ? vm / 3 : vm; }
+  int prog_of(int vm) const { return fused3() ? vm % 3 : prog; }
+  std::string out_of(int vm) const { return fused3() ? (vm % 3 == 0 ? "out" : vm % 3 == 1 ? "out2" : "out3") : outname; }
 
   BodyGen(const Plan &P_, const Group &G_, int gid_, int prog_, int sink_, std::vector<CiEntry> &ci_)
       : P(P_), G(G_), gid(gid_), prog(prog_), sink(sink_), ci(ci_) {
@@ -383,12 +389,13 @@ struct BodyGen {
     //   barrier, 32*maxstep*8 bytes per warp => shared memory never limits occupancy);
     //   block mode (IEXA_STAGE=block): all members' 128 x step tiles, one __syncthreads, copy at the end.
     const bool warp_mode = !block_stage();
-    std::vector<long long> soff(G.members.size(), -1);
-    std::vector<int> stride(G.members.size(), 0), step(G.members.size(), 1), outs_left(G.members.size(), 0);
+    const size_t nvm = fused3() ? 3 * G.members.size() : G.members.size();
+    std::vector<long long> soff(nvm, -1);
+    std::vector<int> stride(nvm, 0), step(nvm, 1), outs_left(nvm, 0);
     int maxstep = 0;
-    for (size_t m = 0; m < G.members.size(); ++m) {
-      const Generator &g = P.member(G, (int)m);
-      step[m] = prog == PROG_D1 ? g.c.o1step : prog == PROG_D2 ? g.c.o2step : 1;
+    for (size_t m = 0; m < nvm; ++m) {
+      const Generator &g = P.member(G, mem_of((int)m));
+      step[m] = prog_of((int)m) == PROG_D1 ? g.c.o1step : prog_of((int)m) == PROG_D2 ? g.c.o2step : 1;
       if (sink == SINK_DENSE && step[m] > 1 && step[m] <= kMaxStagedStep) {
         if (warp_mode) {
           stride[m] = (pad_warp_tiles() && !tma_stage() && !vec2_stage()) ? (step[m] | 1) : step[m];
@@ -408,7 +415,7 @@ struct BodyGen {
     if (warp_mode) smem_doubles = tma ? (size_t)2 * bufsz * (spec_block() / 32) : vec2 ? (size_t)bufsz * (spec_block() / 32) : (size_t)maxstep * 32 * (spec_block() / 32);
     int nflush = 0;
     for (auto &om : outmap) outs_left[om.first]++;
-    std::vector<std::vector<std::pair<int, std::string>>> pending(G.members.size());
+    std::vector<std::vector<std::pair<int, std::string>>> pending(nvm);
     if (G.is_class) {
       o << "      const int nblk_ = (int)" << C(CI_CLS_NBLK) << ";\n"
         << "      const int chunk_ = blk_ / nblk_, wb_ = blk_ - chunk_ * nblk_;\n";
@@ -559,8 +566,8 @@ struct BodyGen {
           if (sink == SINK_DENSE) {
             if (soff[m] >= 0 && warp_mode) pending[m].push_back({c, v}); // flushed when the member is complete
             else if (soff[m] >= 0) o << "      sm[" << soff[m] << " + tid * " << stride[m] << " + " << c << "] = " << v << ";\n";
-            else if (step[m] == 1) o << "      if (active) __stcs(" << atw("out", off(C(CI_MEM_OUT, m, prog), "kl")) << ", " << v << ");\n";
-            else o << "      if (active) __stcs(" << atw("out", off(C(CI_MEM_OUT, m, prog), "kl * " + std::to_string(step[m]) + " + " + std::to_string(c))) << ", " << v << ");\n";
+            else if (step[m] == 1) o << "      if (active) __stcs(" << atw(out_of(m), off(C(CI_MEM_OUT, mem_of(m), prog_of(m)), "kl")) << ", " << v << ");\n";
+            else o << "      if (active) __stcs(" << atw(out_of(m), off(C(CI_MEM_OUT, mem_of(m), prog_of(m)), "kl * " + std::to_string(step[m]) + " + " + std::to_string(c))) << ", " << v << ");\n";
             if (--outs_left[m] == 0 && soff[m] >= 0 && tma) {
               // TMA write-out: the tile sits in buffer (flush & 1), shifted by `par` so that the 16-byte aligned
               // part of the global range is 16-byte aligned in shared memory too; lane 0 issues ONE bulk copy,
@@ -602,7 +609,7 @@ struct BodyGen {
               // the member's tile is complete in this warp: 32*step contiguous doubles of the COO array
               for (auto &pv : pending[m]) o << "      wsm[lane * " << stride[m] << " + " << pv.first << "] = " << pv.second << ";\n";
               o << "      __syncwarp();\n"
-                << "      { double* __restrict__ dst = out + (" << C(CI_MEM_OUT, m, prog) << " + (kb - k0 + w0) * " << step[m] << ");\n"
+                << "      { double* __restrict__ dst = " << out_of(m) << " + (" << C(CI_MEM_OUT, mem_of(m), prog_of(m)) << " + (kb - k0 + w0) * " << step[m] << ");\n"
                 << "        const int n = wact * " << step[m] << ";\n"
                 << "        _Pragma(\"unroll\")\n"
                 << "        for (int i_ = 0; i_ < " << step[m] << "; ++i_) { const int j = lane + 32 * i_; if (j < n) dst[j] = wsm["
@@ -633,7 +640,22 @@ struct BodyGen {
                 << C(CI_IDX_BASE, islot) << " - 1), s_); }\n";
             } else {
               std::string i = ix(islot);
-              o << "      if (active) atomicAdd(out + (" << i << " - 1), " << v << ");\n";
+              // supports 2e and 2e+1 address the SAME entry when every integer column of the index repeats each value
+              // twice (the lower-bound index of the two rows of a collocation element, transform.jl:485-505): the two
+              // lanes are summed with one shuffle and the even lane issues ONE atomic — jtprod! of config 3 is bound by
+              // the L2's RED sector rate (ncu: 37.5 M RED sectors, issue slots 10 % busy), 27 of its 36 atomics per row pair up
+              bool pairs = (prog == PROG_JTV || prog == PROG_HV) && !getenv("IEXA_NO_PAIR_REDUCE");
+              for (auto &t : G.ctx.uidx[islot].terms) {
+                const ColRef &r = P.itrs[G.itr].int_cols[G.ctx.int_cols[t.first]];
+                const HostColumn &hc = P.columns[r.col];
+                pairs = pairs && hc.affine && hc.ac == 2 && hc.ad == 0 && r.div == 1 && r.mod == G.K;
+              }
+              if (pairs)
+                o << "      { const double s_ = active ? " << v << " : 0.0; const double o_ = __shfl_xor_sync(0xffffffffu, s_, 1);\n"
+                  << "        if (!(kb & 1)) { if (!(tid & 1) && active) atomicAdd(out + (" << i << " - 1), s_ + o_); }\n"
+                  << "        else if (active) atomicAdd(out + (" << i << " - 1), s_); }\n";
+              else
+                o << "      if (active) atomicAdd(out + (" << i << " - 1), " << v << ");\n";
             }
           }
           break;
@@ -676,7 +698,8 @@ struct BodyGen {
 };
 
 static const char *kCbName[KS__N] = {"iexa_cb_obj", "iexa_cb_grad", "iexa_cb_cons", "iexa_cb_jac", "iexa_cb_hess",
-                                      "iexa_cb_jprod", "iexa_cb_jtprod_p0", "iexa_cb_jtprod_p1", "iexa_cb_hprod_p0", "iexa_cb_hprod_p1"};
+                                      "iexa_cb_jprod", "iexa_cb_jtprod_p0", "iexa_cb_jtprod_p1", "iexa_cb_hprod_p0", "iexa_cb_hprod_p1",
+                                      "iexa_cb_eval3"};
 
 GeneratedSource generate_source(const Plan &plan, int set) {
   GeneratedSource out;
@@ -687,18 +710,25 @@ GeneratedSource generate_source(const Plan &plan, int set) {
                              {CB_HESS, PROG_D2, SINK_DENSE, true, true, -1},
                              {KS_JPROD, PROG_JV, SINK_DENSE, false, true, -1},
                              {KS_JTPROD0, PROG_JTV, SINK_SCATTER, false, true, 0}, {KS_JTPROD1, PROG_JTV, SINK_SCATTER, false, true, 1},
-                             {KS_HPROD0, PROG_HV, SINK_SCATTER, true, true, 0}, {KS_HPROD1, PROG_HV, SINK_SCATTER, true, true, 1}};
+                             {KS_HPROD0, PROG_HV, SINK_SCATTER, true, true, 0}, {KS_HPROD1, PROG_HV, SINK_SCATTER, true, true, 1},
+                             // cons! + jac_coord! + hess_coord! in one launch: constraint groups run their fused program
+                             // (GPROG_ALL) into out / out2 / out3, objective groups their second-order program into out3
+                             {KS_EVAL3, GPROG_ALL, SINK_DENSE, true, true, -1}};
   for (const CbDef &d : defs) {
-    if ((d.ks < KS_JPROD) != (set == 0)) continue;
+    if (ks_set(d.ks) != set) continue;
+    if (d.ks == KS_EVAL3 && (block_stage() || tma_stage() || vec2_stage())) continue; // default warp staging only
     std::ostringstream cases;
     size_t smem = 0;
     bool any = false;
     for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
       const Group &G = plan.groups[gi];
       if (G.is_obj ? !d.obj : !d.con) continue;
-      if (d.prog != PROG_VAL && G.prog[d.prog].nout == 0) continue;
+      int gprog = d.prog;
+      if (d.ks == KS_EVAL3 && G.is_obj) gprog = PROG_D2;
+      if (gprog != PROG_VAL && G.prog[gprog].nout == 0) continue;
       if (d.phase >= 0 && G.scat_phase[d.prog == PROG_JTV ? 0 : 1] != d.phase) continue;
-      BodyGen bg(plan, G, (int)gi, d.prog, d.sink, out.ci);
+      BodyGen bg(plan, G, (int)gi, gprog, d.sink, out.ci);
+      if (d.ks == KS_EVAL3 && G.is_obj) bg.outname = "out3";
       bg.cb = d.ks;
       bg.idx32 = bg.idx32 && idx32_for(d.ks);
       std::string body = bg.run();
@@ -725,7 +755,7 @@ GeneratedSource generate_source(const Plan &plan, int set) {
     kernels << "extern \"C\" __global__ void __launch_bounds__(IEXA_BLOCK" << (minb > 0 ? ", " + std::to_string(minb) : std::string()) << ") " << kCbName[d.ks]
             << "(const WorkItem* __restrict__ work, const double* __restrict__ x,\n"
                "    const double* __restrict__ theta, const double* __restrict__ y, const double* __restrict__ v, double sigma,\n"
-               "    double* __restrict__ out, double* __restrict__ partials) {\n"
+               "    double* __restrict__ out, double* __restrict__ partials, double* __restrict__ out2, double* __restrict__ out3) {\n"
                "  extern __shared__ __align__(16) double sm[];\n"
                "  const int tid = threadIdx.x;\n"
                "  double acc = 0.0;\n"
@@ -740,7 +770,7 @@ GeneratedSource generate_source(const Plan &plan, int set) {
                "           if (t_ < (unsigned)CI[" << sbase + 1 << "]) { const WorkItem w = work[t_]; gen_ = w.gen; blk_ = w.blk; } } }\n"
             << (use_pdl() ? "  asm volatile(\"griddepcontrol.wait;\" ::: \"memory\");\n" : "")
             <<
-               "  (void)theta; (void)x; (void)y; (void)v; (void)sigma; (void)sm;\n"
+               "  (void)theta; (void)x; (void)y; (void)v; (void)sigma; (void)sm; (void)out2; (void)out3;\n"
                "  switch (gen_) {\n"
             << cases.str() << "    default: break;\n  }\n";
     if (d.sink == SINK_SUM) {
@@ -906,6 +936,10 @@ bool Specialiser::build_products(Plan &plan, const std::vector<const void *> &co
   if (module_[1]) return true;
   return load_set(plan, col_dev_ptr, 1, false, err);
 }
+bool Specialiser::build_eval3(Plan &plan, const std::vector<const void *> &col_dev_ptr, std::string &err) {
+  if (module_[2]) return true;
+  return load_set(plan, col_dev_ptr, 2, false, err);
+}
 
 bool Specialiser::load_set(Plan &plan, const std::vector<const void *> &col_dev_ptr, int set, bool allow_regroup, std::string &err) {
   DynApi &a = api();
@@ -999,7 +1033,7 @@ bool Specialiser::load_set(Plan &plan, const std::vector<const void *> &col_dev_
   r = a.cuMemcpyHtoD_v2(dptr, vals.data(), vals.size() * 8);
   if (r != 0) { err = "cuMemcpyHtoD(CI): " + cu_err(r); return false; }
   for (int ks = 0; ks < KS__N; ++ks) {
-    if ((ks < KS_JPROD) != (set == 0)) continue;
+    if (ks_set(ks) != set) continue;
     if (gs.groups_of[ks].empty()) continue;
     CUfunction f = nullptr;
     if (a.cuModuleGetFunction(&f, mod, kCbName[ks]) != 0 || !f) { err = std::string("missing kernel ") + kCbName[ks]; return false; }
@@ -1018,8 +1052,9 @@ bool Specialiser::load_set(Plan &plan, const std::vector<const void *> &col_dev_
 
 bool Specialiser::launch(int ks, const WorkItem *work, const double *x, const double *theta,
                          const double *y, const double *v, double sigma, double *out, double *partials, cudaStream_t st,
-                         std::string &err) {
-  void *args[] = {(void *)&work, (void *)&x, (void *)&theta, (void *)&y, (void *)&v, (void *)&sigma, (void *)&out, (void *)&partials};
+                         std::string &err, double *out2, double *out3) {
+  void *args[] = {(void *)&work, (void *)&x, (void *)&theta, (void *)&y, (void *)&v, (void *)&sigma, (void *)&out, (void *)&partials,
+                  (void *)&out2, (void *)&out3};
   if (use_pdl() && api().cuLaunchKernelEx) {
     // CUlaunchConfig / CUlaunchAttribute of cuda.h (CUDA 12): the library does not link libcuda, so the two PODs are restated
     struct Attr { int id; char pad[4]; union { char pad[64]; int allowed; void *align_; } value; };

@@ -71,18 +71,20 @@ class Specialiser {
   // second module: jprod! / jtprod! / hprod! kernels of the SAME groups (never regroups the plan)
   bool build_products(Plan &plan, const std::vector<const void *> &col_dev_ptr, std::string &err);
   bool products_built() const { return module_[1] != nullptr; }
+  // third module: the fused cons! + jac_coord! + hess_coord! kernel (iexa_eval3), compiled on its first use
+  bool build_eval3(Plan &plan, const std::vector<const void *> &col_dev_ptr, std::string &err);
   bool has(int ks) const { return ks >= 0 && ks < KS__N && fn_[ks] != nullptr; }
   const std::vector<int> &groups_of(int ks) const { return groups_of_[ks]; }
   const CbSchedule &schedule(int ks) const { return sched_[ks]; }
   bool launch(int ks, const WorkItem *work, const double *x, const double *theta,
               const double *y, const double *v, double sigma, double *out, double *partials, cudaStream_t st,
-              std::string &err);
+              std::string &err, double *out2 = nullptr, double *out3 = nullptr);
   int n_kernels() const { return n_kernels_; }
   static std::string generate_source(const Plan &plan, int set = 0);
 
  private:
   bool load_set(Plan &plan, const std::vector<const void *> &col_dev_ptr, int set, bool allow_regroup, std::string &err);
-  void *module_[2] = {nullptr, nullptr}; // CUmodule
+  void *module_[3] = {nullptr, nullptr, nullptr}; // CUmodule per kernel set (engine.hpp: ks_set)
   std::vector<unsigned long long> dev_allocs_; // instance tables of class groups
   void *fn_[KS__N] = {nullptr};
   size_t smem_[KS__N] = {0};

@@ -435,6 +435,33 @@ class CudaEngine : public Engine {
     return dense_cb(CB_HESS, PROG_D2, x, y, sigma, vals, plan_.loc_nnzh, memspace, stream, err);
   }
 
+  // cons! + jac_coord! + hess_coord! at one (x, y) in ONE launch (iexa_eval3): a constraint group evaluates value, first and
+  // second order from one fused program — x / theta / columns are loaded once and the sin / cos of a state computed once
+  // for all three — and the objective groups add their Hessian slots.  Three launches have three fill / drain phases:
+  // on the reference's own study sizes (16 000 supports) and on 1/8 shards they are most of the time.  Compiled on first use;
+  // falls back to the three separate callbacks when the fused kernel is not available.
+  int eval3(const double *x, const double *y, double sigma, double *c, double *jvals, double *hvals, int memspace,
+            void *stream, std::string &err) override {
+    CK(cudaSetDevice(device_));
+    if (spec_ && !eval3_tried_) {
+      eval3_tried_ = true;
+      std::string serr;
+      if (!spec_->build_eval3(plan_, col_dev_ptr_, serr) || build_group_tables(serr, 2) != IEXA_OK) eval3_note_ = serr.empty() ? "unavailable" : serr;
+    }
+    const bool fused = spec_ && spec_->has(KS_EVAL3) && eval3_note_.empty() && gtable_[KS_EVAL3].nblocks > 0;
+    if (!fused || memspace != IEXA_MEM_DEVICE) {
+      int rc = cons(x, c, memspace, stream, err);
+      if (rc) return rc;
+      const int ms2 = memspace == IEXA_MEM_HOST ? (int)IEXA_MEM_HOST_SAME_X : memspace;
+      if ((rc = jac(x, jvals, ms2, stream, err))) return rc;
+      return hess(x, y, sigma, hvals, ms2, stream, err);
+    }
+    if (!spec_->launch(KS_EVAL3, gtable_[KS_EVAL3].work, x, theta_.as<double>(), y, nullptr, sigma, c, partials_.as<double>(),
+                       (cudaStream_t)stream, err, jvals, hvals))
+      return IEXA_ERR_CUDA;
+    return IEXA_OK;
+  }
+
   int jprod(const double *x, const double *v, double *Jv, int memspace, void *stream, std::string &err) override {
     return prod(CB_JPROD, x, nullptr, v, 1.0, Jv, memspace, stream, err);
   }
@@ -507,13 +534,14 @@ class CudaEngine : public Engine {
   bool gen_failed_ = false;
   DevBuf scat_zero_[2];        // zero ranges of jtprod! / hprod! (Plan::scat_zero_ranges)
   int prod_max_nreg_[3] = {0, 0, 0}; // interpreter register file of the jv / jtv / hv programs
-  bool prod_spec_tried_ = false;
+  bool prod_spec_tried_ = false, eval3_tried_ = false;
+  std::string eval3_note_;
   double *par_stage_ = nullptr; size_t par_stage_bytes_ = 0; cudaEvent_t par_stage_event_ = nullptr;
   GenD *gens_dev_ = nullptr;
   std::vector<GenD> gens_host_; // device pointers inside; objs first then cons
   Table table_[CB__N];
   Table gtable_[KS__N]; // specialised path, per kernel slot: block -> (group, block of supports)
-  DevBuf gwork_[2];
+  DevBuf gwork_[3];
   std::vector<const void *> col_dev_ptr_;
   double *pinned_f_ = nullptr;
   std::map<void *, size_t> registered_;
@@ -708,7 +736,7 @@ class CudaEngine : public Engine {
 
   // work tables of the specialised kernels of one module (set 0: the five callbacks; set 1: the products)
   int build_group_tables(std::string &err, int set = 0) {
-    const int ks0 = set == 0 ? 0 : KS_JPROD, ks1 = set == 0 ? KS_JPROD : KS__N;
+    const int ks0 = set == 0 ? 0 : set == 1 ? KS_JPROD : KS_EVAL3, ks1 = set == 0 ? KS_JPROD : set == 1 ? KS_EVAL3 : KS__N;
     std::vector<WorkItem> items;
     size_t starts[KS__N + 1];
     for (int cb = ks0; cb < ks1; ++cb) {
@@ -734,7 +762,7 @@ class CudaEngine : public Engine {
       bool lpt = oe ? oe[0] == 'l' : false;
       if (lpt) { // heaviest groups first (longest processing time first): the kernel drains on short blocks
         const int prog = (cb == CB_OBJ || cb == CB_CONS) ? PROG_VAL : (cb == CB_GRAD || cb == CB_JAC) ? PROG_D1 : cb == CB_HESS ? PROG_D2
-                         : cb == KS_JPROD ? PROG_JV : (cb == KS_JTPROD0 || cb == KS_JTPROD1) ? PROG_JTV : PROG_HV;
+                         : cb == KS_JPROD ? PROG_JV : (cb == KS_JTPROD0 || cb == KS_JTPROD1) ? PROG_JTV : cb == KS_EVAL3 ? (int)GPROG_ALL : PROG_HV;
         std::stable_sort(ord.begin(), ord.end(), [&](const Ord &a, const Ord &b) {
           return plan_.groups[a.gi].prog[prog].code.size() > plan_.groups[b.gi].prog[prog].code.size();
         });

@@ -9,7 +9,10 @@ namespace iexa {
 enum Callback { CB_OBJ = 0, CB_GRAD = 1, CB_CONS = 2, CB_JAC = 3, CB_HESS = 4, CB_JPROD = 5, CB_JTPROD = 6, CB_HPROD = 7, CB__N = 8 };
 // kernel slots of the specialised path: the five callbacks, jprod!, and the two phases of each scatter product
 // (phase 0: groups whose single-writer outputs are plain stores; phase 1: everything else, atomics — plan.hpp)
-enum KernelSlot { KS_JPROD = 5, KS_JTPROD0 = 6, KS_JTPROD1 = 7, KS_HPROD0 = 8, KS_HPROD1 = 9, KS__N = 10 };
+enum KernelSlot { KS_JPROD = 5, KS_JTPROD0 = 6, KS_JTPROD1 = 7, KS_HPROD0 = 8, KS_HPROD1 = 9, KS_EVAL3 = 10, KS__N = 11 };
+// NVRTC module of a kernel slot: 0 = the five callbacks (compiled at finalize), 1 = products, 2 = eval3 (compiled on first use)
+inline int ks_set(int ks) { return ks < KS_JPROD ? 0 : ks < KS_EVAL3 ? 1 : 2; }
+enum { GPROG_ALL = 6 };
 
 struct Engine {
   virtual ~Engine() {}
@@ -23,6 +26,9 @@ struct Engine {
   virtual int jac(const double *x, double *vals, int memspace, void *stream, std::string &err) = 0;
   virtual int hess(const double *x, const double *y, double sigma, double *vals, int memspace,
                    void *stream, std::string &err) = 0;
+  // cons! + jac_coord! + hess_coord! at one (x, y) in ONE launch
+  virtual int eval3(const double *x, const double *y, double sigma, double *c, double *jvals, double *hvals, int memspace,
+                    void *stream, std::string &err) = 0;
   virtual int jprod(const double *x, const double *v, double *Jv, int memspace, void *stream,
                     std::string &err) = 0;
   virtual int jtprod(const double *x, const double *v, double *Jtv, int memspace, void *stream,

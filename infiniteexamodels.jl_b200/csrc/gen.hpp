@@ -74,6 +74,7 @@ struct MemberSlots {
   std::vector<int32_t> jac_slot;                        // index slot per first-order slot
   std::vector<std::pair<int32_t, int32_t>> hess_slot;   // index-slot pair per second-order slot
   int wid = 0;                                          // member id of the root weight W (D_W)
+  int val = -1;                                         // DAG id of the member's value
 };
 struct ProductOuts {
   std::vector<int> jv;                    // one node per member

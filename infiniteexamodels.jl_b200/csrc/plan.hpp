@@ -117,10 +117,12 @@ struct Group {
   SlotCtx ctx;
   // val, d1, d2 over all members, then the matrix-free products jv (one output per member), jtv and hv (one output per
   // touched index slot of the group: contributions of all members are summed in the program)
-  Program prog[6];
-  std::vector<std::pair<int32_t, int32_t>> outmap[6]; // program output j -> (member position, slot); jtv / hv: (0, index slot)
+  // [6] (GPROG_ALL, constraint groups): value + first + second order of every member in ONE program — the fused
+  // cons! + jac_coord! + hess_coord! evaluation (iexa_eval3): x / theta / columns loaded once, sin / cos of a state once
+  Program prog[7];
+  std::vector<std::pair<int32_t, int32_t>> outmap[7]; // program output j -> (member position, slot); jtv / hv: (0, index slot); [6]: (3*member + {0 val, 1 d1, 2 d2}, slot)
   std::vector<std::vector<int32_t>> jac_slot;         // per member: group index slot of each first-order slot
-  std::vector<uint8_t> x_slots[6];
+  std::vector<uint8_t> x_slots[7];
   // scatter products (jtprod! / hprod!): phase of the group (0: launched first, may store single-writer outputs directly;
   // 1: launched after phase 0, atomics only) and, per output, 1 = plain store — Plan::analyse_scatter
   int scat_phase[2] = {1, 1};
@@ -505,7 +507,7 @@ struct Plan {
             for (size_t c = 0; c < gc.slot1().size(); ++c) { o12[0].push_back(gc.slot1()[c]); G.outmap[1].push_back({(int32_t)j, (int32_t)c}); }
             for (size_t c = 0; c < gc.slot2().size(); ++c) { o12[1].push_back(gc.slot2()[c]); G.outmap[2].push_back({(int32_t)j, (int32_t)c}); }
             MemberSlots ms;
-            ms.s1 = gc.slot1(); ms.s2 = gc.slot2(); ms.jac_slot = gc.g.jac_slot; ms.hess_slot = gc.g.hess_slot; ms.wid = (int)j;
+            ms.s1 = gc.slot1(); ms.s2 = gc.slot2(); ms.jac_slot = gc.g.jac_slot; ms.hess_slot = gc.g.hess_slot; ms.wid = (int)j; ms.val = gc.val_root();
             mslots.push_back(std::move(ms));
           }
           const size_t nis = G.ctx.uidx.size();
@@ -569,7 +571,7 @@ struct Plan {
         slots1[li] += g.c.o1step > 1 ? (g.c.o1step | 1) : 0;
         slots2[li] += g.c.o2step > 1 ? (g.c.o2step | 1) : 0;
         MemberSlots ms;
-        ms.s1 = gc.slot1(); ms.s2 = gc.slot2(); ms.jac_slot = gc.g.jac_slot; ms.hess_slot = gc.g.hess_slot; ms.wid = mpos;
+        ms.s1 = gc.slot1(); ms.s2 = gc.slot2(); ms.jac_slot = gc.g.jac_slot; ms.hess_slot = gc.g.hess_slot; ms.wid = mpos; ms.val = gc.val_root();
         mslots[li].push_back(std::move(ms));
       }
       for (size_t li = 0; li < dags.size(); ++li) {
@@ -595,6 +597,17 @@ struct Plan {
     }
     G.prog[5] = schedule(dag, po.hv, nis, G.x_slots[5]);
     for (int32_t u : po.hv_slot) G.outmap[5].push_back({0, u});
+    // fused value + first + second order (iexa_eval3)
+    G.outmap[6].clear(); G.prog[6] = Program();
+    if (!G.is_obj) {
+      std::vector<int> all;
+      for (size_t m = 0; m < M.size(); ++m) {
+        all.push_back(M[m].val); G.outmap[6].push_back({(int32_t)(3 * m), 0});
+        for (size_t c = 0; c < M[m].s1.size(); ++c) { all.push_back(M[m].s1[c]); G.outmap[6].push_back({(int32_t)(3 * m + 1), (int32_t)c}); }
+        for (size_t c = 0; c < M[m].s2.size(); ++c) { all.push_back(M[m].s2[c]); G.outmap[6].push_back({(int32_t)(3 * m + 2), (int32_t)c}); }
+      }
+      G.prog[6] = schedule(dag, all, nis, G.x_slots[6]);
+    }
   }
   bool class_mode_ = false;
 

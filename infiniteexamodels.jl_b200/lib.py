@@ -39,9 +39,9 @@ SYMBOLS = [
     "iexa_add_par", "iexa_patch_var", "iexa_itr_base", "iexa_itr_generated", "iexa_add_par_function", "iexa_debug_get_column", "iexa_itr_product", "iexa_add_con",
     "iexa_add_obj", "iexa_finalize", "iexa_get_meta", "iexa_get_vector", "iexa_set_vector",
     "iexa_set_par", "iexa_set_par_stream", "iexa_get_par", "iexa_jac_structure", "iexa_hess_structure", "iexa_obj",
-    "iexa_grad", "iexa_cons", "iexa_jac_coord", "iexa_hess_coord", "iexa_jprod", "iexa_jtprod",
+    "iexa_grad", "iexa_cons", "iexa_jac_coord", "iexa_hess_coord", "iexa_eval3", "iexa_jprod", "iexa_jtprod",
     "iexa_hprod", "iexa_obj_device", "iexa_host_register", "iexa_host_unregister", "iexa_segments", "iexa_shared_vars", "iexa_shared_ranges", "iexa_host_x_bytes", "iexa_x_ranges", "iexa_algorithmic_bytes",
-    "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_set_class_mode", "iexa_debug_codegen_compile", "iexa_debug_cache_stats",
+    "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_set_class_mode", "iexa_debug_codegen_compile", "iexa_debug_codegen_source_of", "iexa_debug_codegen_compile_of", "iexa_debug_cache_stats",
     "iexa_halo_create", "iexa_halo_export", "iexa_halo_connect", "iexa_halo_set_sends", "iexa_halo_set_recvs", "iexa_halo_exchange",
     "iexa_halo_allreduce_small", "iexa_halo_status", "iexa_halo_destroy",
     "iexa_csr_create", "iexa_csr_create_keyed", "iexa_coo_locality", "iexa_csr_destroy", "iexa_csr_nnz", "iexa_csr_pattern", "iexa_csr_apply",
@@ -86,6 +86,7 @@ def _declare(L):
     sig("iexa_cons", _i32, _vp, _vp, _vp, _i32, _vp)
     sig("iexa_jac_coord", _i32, _vp, _vp, _vp, _i32, _vp)
     sig("iexa_hess_coord", _i32, _vp, _vp, _vp, _dbl, _vp, _i32, _vp)
+    sig("iexa_eval3", _i32, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _i32, _vp)
     sig("iexa_jprod", _i32, _vp, _vp, _vp, _vp, _i32, _vp)
     sig("iexa_jtprod", _i32, _vp, _vp, _vp, _vp, _i32, _vp)
     sig("iexa_hprod", _i32, _vp, _vp, _vp, _vp, _dbl, _vp, _i32, _vp)
@@ -102,6 +103,8 @@ def _declare(L):
     sig("iexa_debug_codegen_source", _i64, _vp, _vp, _i64)
     sig("iexa_debug_codegen_compile", _i32, _vp, C.POINTER(_i64))
     sig("iexa_debug_set_class_mode", _i32, _vp, _i32)
+    sig("iexa_debug_codegen_source_of", _i64, _vp, _i32, _vp, _i64)
+    sig("iexa_debug_codegen_compile_of", _i32, _vp, _i32, C.POINTER(_i64))
     sig("iexa_debug_cache_stats", _i32, C.POINTER(_i32), C.POINTER(_i32))
     sig("iexa_csr_create", _i32, C.POINTER(_vp), _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32)
     sig("iexa_csr_create_keyed", _i32, C.POINTER(_vp), _i64, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _i32)

@@ -250,6 +250,15 @@ def hess_coord_(m: ExaModel, x, y, vals, obj_weight: float = 1.0):
     return vals
 
 
+def eval3_(m: ExaModel, x, y, c, jvals, hvals, obj_weight: float = 1.0):
+    """cons! + jac_coord! + hess_coord! at the same (x, y) in one call (one fused kernel for device buffers)"""
+    bx, by = m._buf(x, m.meta.nvar), m._buf(y, m.loc_ncon)
+    bc, bj, bh = m._buf(c, m.loc_ncon), m._buf(jvals, m.loc_nnzj), m._buf(hvals, m.loc_nnzh)
+    ms, st = m._pair(bx, by, bc, bj, bh)
+    _lib.check(m.L, m.L.iexa_eval3(m.h, bx[0], by[0], float(obj_weight), bc[0], bj[0], bh[0], ms, st))
+    return c, jvals, hvals
+
+
 def jprod_(m: ExaModel, x, v, Jv):
     bx, bv, bo = m._buf(x, m.meta.nvar), m._buf(v, m.meta.nvar), m._buf(Jv, m.loc_ncon)
     ms, st = m._pair(bx, bv, bo)
@@ -301,7 +310,8 @@ def bind(m: ExaModel, name: str, x, out, y=None, obj_weight: float = 1.0, new_x:
     ``bind(m, "grad", x, g)``, ``bind(m, "jprod", x, Jv, v=v)``, ``bind(m, "jtprod", x, Jtv, v=w)``,
     ``bind(m, "hprod", x, Hv, y, σ, v=v)``.  ``new_x=False`` (host buffers only) is Ipopt's ``new_x`` flag: x is the x
     of the previous host call on this model, so the engine reuses its device copy (IEXA_MEM_HOST_SAME_X)."""
-    bx, bo, by, bv = m._buf(x, m.meta.nvar), m._buf(out), m._buf(y), m._buf(v)
+    bx, by, bv = m._buf(x, m.meta.nvar), m._buf(y), m._buf(v)
+    bo = m._buf(out[0] if isinstance(out, tuple) else out)
     ms, st = m._pair(*[b for b in (bx, bo, by, bv) if b[0] is not None])
     if not new_x and ms == _lib.IEXA_MEM_HOST:
         ms = _lib.IEXA_MEM_HOST_SAME_X
@@ -316,6 +326,9 @@ def bind(m: ExaModel, name: str, x, out, y=None, obj_weight: float = 1.0, new_x:
         return BoundCall(m, L.iexa_grad, (h, vp(bx[0]), vp(bo[0]), ms, vp(st)), (x, out))
     if name == "hess_coord":
         return BoundCall(m, L.iexa_hess_coord, (h, vp(bx[0]), vp(by[0]), C.c_double(obj_weight), vp(bo[0]), ms, vp(st)), (x, out, y))
+    if name == "eval3":   # out = (c, jac_vals, hess_vals)
+        bc, bj, bh = (m._buf(o) for o in out)
+        return BoundCall(m, L.iexa_eval3, (h, vp(bx[0]), vp(by[0]), C.c_double(obj_weight), vp(bc[0]), vp(bj[0]), vp(bh[0]), ms, vp(st)), (x, out, y))
     if name == "jprod":
         return BoundCall(m, L.iexa_jprod, (h, vp(bx[0]), vp(bv[0]), vp(bo[0]), ms, vp(st)), (x, out, v))
     if name == "jtprod":

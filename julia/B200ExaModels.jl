@@ -218,6 +218,14 @@ function NLPModels.jtprod_nln!(m::B200ExaModel, x::AbstractVector, v::AbstractVe
                                      m.plan.h, _ptr(x), _ptr(v), _ptr(Jtv), _ms(x), _st(x)))
     return Jtv
 end
+"cons! + jac_coord! + hess_coord! at the same (x, y) in ONE call (one fused kernel for CuArrays)"
+function eval3!(m::B200ExaModel, x::AbstractVector, y::AbstractVector, c::AbstractVector, jvals::AbstractVector, hvals::AbstractVector;
+                obj_weight = 1.0)
+    GC.@preserve x y c jvals hvals check(ccall((:iexa_eval3, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}),
+        m.plan.h, _ptr(x), _ptr(y), obj_weight, _ptr(c), _ptr(jvals), _ptr(hvals), _ms(x), _st(x)))
+    return c, jvals, hvals
+end
 function NLPModels.hprod!(m::B200ExaModel, x::AbstractVector, y::AbstractVector, v::AbstractVector, Hv::AbstractVector;
                           obj_weight = 1.0)
     GC.@preserve x y v Hv check(ccall((:iexa_hprod, LIB), Int32,

@@ -70,6 +70,11 @@ for nm, fn, w in (("cons", bind(m, "cons", x, c), 2), ("jac", bind(m, "jac_coord
     if w >= 2:
         tot += ms
     print(f"{nm}: {ms:.4f} ms  {B[w]/ms/1e6:.1f} GB/s  frac_of_6552={B[w]/ms/1e6/6552:.3f}")
+if os.environ.get("IEXA_EVAL3", "1") != "0":   # the fused cons + jac + hess kernel (compiled on first use)
+    f3 = bind(m, "eval3", x, (c, jv, hv), y, 1.0)
+    tp = time.time(); f3(); torch.cuda.synchronize(); tb3 = time.time() - tp
+    ms = timeit(f3)
+    print(f"eval3 (one fused launch): {ms:.4f} ms -> {1e3/ms:.0f} evals/s, {sum(B[2:])/ms/1e6:.0f} GB/s ({sum(B[2:])/ms/1e6/6552:.3f} of 6552)  [three launches: {tot:.4f} ms; module build {tb3:.2f}s]")
 if os.environ.get("IEXA_PROD", "1") != "0":  # matrix-free products (fused kernels, second NVRTC module compiled on first use)
     v = torch.from_numpy(rng.uniform(-1, 1, core.nvar)).cuda()
     w = torch.from_numpy(rng.uniform(-1, 1, max(core.ncon, 1))).cuda()

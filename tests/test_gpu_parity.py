@@ -361,3 +361,30 @@ def test_strict_ieee_mode_reproduces_the_oracles_nan_pattern_on_the_gpu(name, po
         assert np.array_equal(got[inf], ref[inf]), "infinite entries differ"
         fin = np.isfinite(ref)
         assert_close(got[fin], ref[fin], "finite entries")
+
+
+@pytest.mark.parametrize("name", ["quadrotor_oc_40", "quadrotor_oc_ragged", "pandemic_50x4", "farmer_1000", "ode_5x5"])
+def test_eval3_fused_kernel_matches_the_oracle_and_the_three_callbacks(name, oracle_cache):
+    """iexa_eval3: cons! + jac_coord! + hess_coord! at one (x, y) in ONE launch (one fused program per constraint group)"""
+    import torch
+    core, om = _oracle(oracle_cache, name)
+    m = ex.ExaModel(core, device=0)
+    x, y = eval_point(core, seed=6)
+    dev = torch.device("cuda:0")
+    xd, yd = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)
+    z = lambda n: torch.full((max(n, 1),), 7.0, dtype=torch.float64, device=dev)
+    c, jv, hv = z(om.ncon), z(om.nnzj), z(om.nnzh)
+    ex.eval3_(m, xd, yd, c, jv, hv, 0.7)
+    assert_close(c.cpu().numpy()[: om.ncon], om.cons(x), "cons")
+    assert_close(jv.cpu().numpy()[: om.nnzj], om.jac_coord(x), "jac_coord")
+    assert_close(hv.cpu().numpy()[: om.nnzh], om.hess_coord(x, y, 0.7), "hess_coord")
+    c2, j2, h2 = z(om.ncon), z(om.nnzj), z(om.nnzh)
+    ex.cons_(m, xd, c2); ex.jac_coord_(m, xd, j2); ex.hess_coord_(m, xd, yd, h2, 0.7)
+    assert_close(c.cpu().numpy(), c2.cpu().numpy(), "eval3 vs cons!")
+    assert_close(jv.cpu().numpy(), j2.cpu().numpy(), "eval3 vs jac_coord!")
+    assert_close(hv.cpu().numpy(), h2.cpu().numpy(), "eval3 vs hess_coord!")
+    # host buffers: the three callbacks in sequence behind the same entry point
+    ch, jh, hh = np.zeros(max(om.ncon, 1)), np.zeros(max(om.nnzj, 1)), np.zeros(max(om.nnzh, 1))
+    ex.eval3_(m, x, y, ch, jh, hh, 0.7)
+    assert_close(ch[: om.ncon], om.cons(x), "cons (host)")
+    assert_close(hh[: om.nnzh], om.hess_coord(x, y, 0.7), "hess_coord (host)")
