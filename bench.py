@@ -549,6 +549,27 @@ def main():
         products["engine_note"] = m.L.iexa_engine_note(m.h).decode()[:120]
         del v, w, Jv, Jtw, Hv, pcalls
 
+    # ---- the fused entry point: cons! + jac_coord! + hess_coord! at one (x, y) in ONE launch (iexa_eval3).  NOT the headline
+    #      (the metric counts the three NLPModels calls); reported next to it
+    eval3 = None
+    if not args.no_products:
+        f3 = bind(m, "eval3", x, (c, jv, hv), y, 1.0)
+        for _ in range(3):
+            f3()
+        barrier()
+        n3 = max(5, min(args.steps, 50))
+        a, b = ctx.ev(), ctx.ev()
+        a.record()
+        for _ in range(n3):
+            f3()
+        b.record(); barrier()
+        ms3 = float(ctx.max_over_ranks(a.elapsed_time(b) / n3)[0])
+        b3 = float(ctx.sum_over_ranks(float(ex.algorithmic_bytes(m, ex.lib.CB_EVAL3)))[0])
+        eval3 = {"ms": ms3, "evals/s": 1e3 / ms3, "bytes": int(b3), "GB/s": b3 / (ms3 * 1e-3) / 1e9, "frac": b3 / (ms3 * 1e-3) / 1e9 / (peak * world),
+                 "launches": 1, "note": "iexa_eval3: one fused kernel — every constraint group evaluates value, first and second order from ONE program (x / theta / "
+                                        "columns loaded once, sin / cos of a state once); algorithmic bytes = distinct inputs once + c + Jacobian + Hessian values; "
+                                        "results identical to the three callbacks (tests/test_gpu_parity.py)"}
+
     # ---- solver iteration: obj + grad! + cons! + jac_coord! + hess_coord! + COO->CSR of both matrices, device-resident,
     #      with (N > 1) the x halo exchange and the all-reduces INSIDE the timed step (ESCAPE34/utils.jl:7,23 `ad_time`)
     iteration = None
@@ -647,7 +668,7 @@ def main():
                                "nvrtc_compiles": int(cstat[0].value), "disk_cache_hits": int(cstat[1].value),
                                "note": "compiled images are cached in memory and on disk keyed by the generated source (IEXA_CACHE_DIR)"},
                    "warmup_steps_run": int(nwarm)},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "products": products, "iteration": iteration,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval3": eval3, "products": products, "iteration": iteration,
         "x_distribution": xdist, "workloads": workloads,
         "gpu_launches": int(args.steps * launches_step),
         "clocks": clocks, "wall_s_timed_region": t_wall,

@@ -292,7 +292,7 @@ int64_t iexa_host_x_bytes(const iexa_plan *p);
 
 /* ---- byte accounting used by bench.py's roofline: ALGORITHMIC bytes of
  *      one call of each callback, computed from the finalised plan.
- * which: 0 obj, 1 grad, 2 cons, 3 jac_coord, 4 hess_coord, 5 jprod, 6 jtprod, 7 hprod
+ * which: 0 obj, 1 grad, 2 cons, 3 jac_coord, 4 hess_coord, 5 jprod, 6 jtprod, 7 hprod, 8 eval3 (inputs once + c + both value arrays)
  * (products: the inputs their first / second order programs load, the touched part of v — or y and v — and every
  * entry of the dense result once; no COO values are materialised)                          */
 int64_t iexa_algorithmic_bytes(const iexa_plan *p, int32_t which);

@@ -427,22 +427,31 @@ int64_t iexa_host_x_bytes(const iexa_plan *p) {
 
 // ---- algorithmic bytes --------------------------------------------------------
 int64_t iexa_algorithmic_bytes(const iexa_plan *pc, int32_t which) {
-  if (!pc || !pc->plan.finalized || which < 0 || which > 7) return -1;
+  if (!pc || !pc->plan.finalized || which < 0 || which > 8) return -1;
   iexa_plan *p = const_cast<iexa_plan *>(pc);
   if (p->bytes_cache[which] >= 0) return p->bytes_cache[which];
   const iexa::Plan &P = p->plan;
-  std::vector<const iexa::Generator *> gens;
-  const bool use_obj = which == 0 || which == 1 || which == 4 || which == 7;
-  const bool use_con = which >= 2;
-  if (use_obj) for (auto &g : P.objs) gens.push_back(&g);
-  if (use_con) for (auto &g : P.cons) gens.push_back(&g);
-  std::vector<bool> xs((size_t)P.nvar, false), ts((size_t)P.npar, false), vs(which >= 5 ? (size_t)P.nvar : 0, false);
+  // (generator, program) pairs of the call; distinct inputs are counted once over ALL of them
+  std::vector<std::pair<const iexa::Generator *, const iexa::Program *>> work;
+  auto prog_of = [&](const iexa::Generator &g, int w) -> const iexa::Program & {
+    return (w == 0 || w == 2) ? g.c.val : (w == 1 || w == 3) ? g.c.d1 : w == 4 ? g.c.d2 : w == 5 ? g.c.jv : w == 6 ? g.c.jtv : g.c.hv;
+  };
+  if (which == 8) { // iexa_eval3: value + first + second order of the constraints and second order of the objectives, inputs ONCE
+    for (auto &g : P.objs) work.push_back({&g, &g.c.d2});
+    for (auto &g : P.cons) { work.push_back({&g, &g.c.val}); work.push_back({&g, &g.c.d1}); work.push_back({&g, &g.c.d2}); }
+  } else {
+    const bool use_obj = which == 0 || which == 1 || which == 4 || which == 7;
+    const bool use_con = which >= 2;
+    if (use_obj) for (auto &g : P.objs) work.push_back({&g, &prog_of(g, which)});
+    if (use_con) for (auto &g : P.cons) work.push_back({&g, &prog_of(g, which)});
+  }
+  std::vector<bool> xs((size_t)P.nvar, false), ts((size_t)P.npar, false), vs(which >= 5 && which <= 7 ? (size_t)P.nvar : 0, false);
   std::vector<std::vector<bool>> colseen(P.columns.size());
+  std::vector<bool> yrow(which == 8 ? (size_t)P.ncon : 0, false);
   int64_t bytes = 0;
-  for (const iexa::Generator *gp : gens) {
-    const iexa::Generator &g = *gp;
-    const iexa::Program &pr = (which == 0 || which == 2) ? g.c.val : (which == 1 || which == 3) ? g.c.d1 : which == 4 ? g.c.d2
-                              : which == 5 ? g.c.jv : which == 6 ? g.c.jtv : g.c.hv;
+  for (auto &wk : work) {
+    const iexa::Generator &g = *wk.first;
+    const iexa::Program &pr = *wk.second;
     if (pr.nout == 0) continue;
     const iexa::Iterator &it = P.itrs[g.itr];
     std::vector<int32_t> lx, lp, lv;
@@ -481,6 +490,8 @@ int64_t iexa_algorithmic_bytes(const iexa_plan *pc, int32_t which) {
     for (size_t s = 0; s < iused.size(); ++s) if (iused[s]) touch_col(it.int_cols[g.c.int_cols[s]], 4);
     if ((which == 4 || which == 7) && !g.is_obj && pr.uses_w) bytes += 8 * (g.k1 - g.k0); // multipliers y
     if (which == 6 && pr.uses_w) bytes += 8 * (g.k1 - g.k0);                                // v[row]
+    if (which == 8 && !g.is_obj && pr.uses_w)
+      for (int64_t k = g.k0; k < g.k1; ++k) if (!yrow[g.o0 + k]) { yrow[g.o0 + k] = true; bytes += 8; }
   }
   switch (which) {
     case 0: bytes += 8; break;
@@ -490,6 +501,7 @@ int64_t iexa_algorithmic_bytes(const iexa_plan *pc, int32_t which) {
     case 4: bytes += 8 * P.loc_nnzh; break;
     case 5: bytes += 8 * P.loc_ncon; break;
     case 6: case 7: bytes += 8 * P.nvar; break; // every entry of the dense result is written once
+    case 8: bytes += 8 * (P.loc_ncon + P.loc_nnzj + P.loc_nnzh); break;
   }
   p->bytes_cache[which] = bytes;
   return bytes;

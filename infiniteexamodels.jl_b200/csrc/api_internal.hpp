@@ -9,5 +9,5 @@ struct iexa_plan {
   iexa::Plan plan;
   std::unique_ptr<iexa::Engine> engine;
   uint32_t flags = 0;
-  int64_t bytes_cache[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  int64_t bytes_cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
 };

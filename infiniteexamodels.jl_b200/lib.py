@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 IEXA_MEM_HOST, IEXA_MEM_DEVICE, IEXA_MEM_HOST_SAME_X = 0, 1, 2
 IEXA_F_DEFAULT, IEXA_F_NO_SPECIALISE, IEXA_F_NO_DEVICE = 0, 1, 2
 IEXA_OPT_SLOT_ORDER, IEXA_OPT_STRICT_IEEE = 1, 2
-CB_OBJ, CB_GRAD, CB_CONS, CB_JAC, CB_HESS, CB_JPROD, CB_JTPROD, CB_HPROD = range(8)
+CB_OBJ, CB_GRAD, CB_CONS, CB_JAC, CB_HESS, CB_JPROD, CB_JTPROD, CB_HPROD, CB_EVAL3 = range(9)
 
 
 class IexaError(RuntimeError):
