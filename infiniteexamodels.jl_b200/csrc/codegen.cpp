@@ -180,7 +180,9 @@ static bool use_pdl() { static bool v = [] { const char *e = getenv("IEXA_PDL");
 //   the final kernels 0.134 (4) / 0.129 (8) / 0.132 (12) at 48 registers and 0.126 (all) at 64 registers (8 blocks/SM).
 // slots 5..9 (jprod, jtprod phases 0/1, hprod phases 0/1): IEXA_HOIST_PROD="<jprod>,<jtprod>,<hprod>"
 static int hoist_loads(int cb) {
-  static int v[KS__N] = {-1, -1, -1, -1, 16, 24, 24, 24, 16, 16, 16};
+  // products (B200, config 3, round 2): jprod 0.139 ms at 12 (0.148 at 24, 0.156 at 0); jtprod 0.310 at 24 (0.316 at 12, 0.344 at 0);
+  // hprod 0.2765 at 4 (0.283 at 0 / 8, 0.293 at 16, 0.298 at 32)
+  static int v[KS__N] = {-1, -1, -1, -1, 16, 12, 24, 24, 4, 4, 16};
   static bool init = [] {
     if (const char *e = getenv("IEXA_HOIST")) {
       int w[5] = {v[0], v[1], v[2], v[3], v[4]};
