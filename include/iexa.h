@@ -227,6 +227,8 @@ int32_t iexa_jac_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_byt
 int32_t iexa_hess_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_bytes,
                             int32_t memspace, void *stream);
 int32_t iexa_obj(iexa_plan *p, const double *x, double *f_host, int32_t memspace, void *stream);
+/* world > 1: g is written only inside this rank's iexa_x_ranges (its own supports, shared variables, halos); the rank contributes
+ * nothing elsewhere and leaves those entries UNTOUCHED (zero g first if the whole vector is to be all-reduced)              */
 int32_t iexa_grad(iexa_plan *p, const double *x, double *g, int32_t memspace, void *stream);
 int32_t iexa_cons(iexa_plan *p, const double *x, double *c, int32_t memspace, void *stream);
 int32_t iexa_jac_coord(iexa_plan *p, const double *x, double *vals, int32_t memspace, void *stream);

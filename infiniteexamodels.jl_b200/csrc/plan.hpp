@@ -669,6 +669,22 @@ struct Plan {
       pos = std::max(pos, d.second);
     }
     if (pos < nvar) grad_zero_ranges.push_back({pos, nvar - pos});
+    if (world > 1) {
+      // sharded: a rank contributes nothing outside the parts of x it reads (its own supports, shared variables, halos) —
+      // zero-filling the other ranks' 1 - 1/world of g on every call made grad! the one callback that did not scale
+      // (8 GPUs, config 3: 0.068 ms of which 0.05 ms were the memset).  Entries outside iexa_x_ranges are left UNTOUCHED.
+      std::vector<std::pair<int64_t, int64_t>> rr = x_read_ranges(), cut; // 1-based inclusive, sorted, disjoint
+      size_t j = 0;
+      for (auto &z : grad_zero_ranges) {
+        const int64_t zlo = z.first, zhi = z.first + z.second; // 0-based [zlo, zhi)
+        while (j < rr.size() && rr[j].second <= zlo) ++j;      // rr[j] as 0-based [first-1, second)
+        for (size_t q = j; q < rr.size() && rr[q].first - 1 < zhi; ++q) {
+          const int64_t lo = std::max(zlo, rr[q].first - 1), hi = std::min(zhi, rr[q].second);
+          if (lo < hi) cut.push_back({lo, hi - lo});
+        }
+      }
+      grad_zero_ranges.swap(cut);
+    }
   }
 
 

@@ -332,6 +332,8 @@ class ShardedExaModel:
         if self._ev:
             self._ev.grad_(x, g)
         else:
+            if self.world > 1:   # the engine writes only inside this rank's read ranges (iexa_grad): zero the rest here
+                g.zero_() if isinstance(g, self.torch.Tensor) else g.fill(0.0)
             _m.grad_(self.model, x, g)
         if self.world > 1 and self.shared_all:
             gt = g if isinstance(g, self.torch.Tensor) else self.torch.from_numpy(g)
@@ -351,6 +353,8 @@ class ShardedExaModel:
         if self._ev:
             self._ev.grad_(x, g)
         else:
+            if self.world > 1:
+                g.zero_() if isinstance(g, self.torch.Tensor) else g.fill(0.0)
             _m.grad_(self.model, x, g)
         if self.world > 1:
             gt = g if isinstance(g, self.torch.Tensor) else self.torch.from_numpy(g)

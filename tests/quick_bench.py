@@ -29,7 +29,8 @@ core = {"quad": lambda: models.quadrotor(N, "oc"), "quadfd": lambda: models.quad
         "opf118": lambda: exa_core(opf.opf(opf.synthetic_grid(118), num_supports=N))[0],
         "farmer": lambda: models.farmer(N)}[name]()
 t1 = time.time()
-m = ex.ExaModel(core, device=0, flags=flags)
+WORLD = int(os.environ.get("IEXA_QB_WORLD", "1"))   # time ONE shard of a world-W sharding on this GPU (rank W/2)
+m = ex.ExaModel(core, device=0, flags=flags, rank=WORLD // 2, world=WORLD)
 t2 = time.time()
 print(f"{name} N={N} build core {t1-t0:.2f}s plan+finalize {t2-t1:.2f}s nvar={m.meta.nvar} ncon={m.meta.ncon} "
       f"nnzj={m.meta.nnzj} nnzh={m.meta.nnzh} gens={m.cmeta.nobj_gen + m.cmeta.ncon_gen} spec={m.cmeta.n_kernels_specialised} "
@@ -37,10 +38,10 @@ print(f"{name} N={N} build core {t1-t0:.2f}s plan+finalize {t2-t1:.2f}s nvar={m.
 rng = np.random.default_rng(0)
 x0 = np.where(np.isfinite(core.x0_vec), core.x0_vec, 0.0)
 x = torch.from_numpy(x0 + 0.1 * rng.uniform(-1, 1, core.nvar)).cuda()
-y = torch.from_numpy(rng.uniform(-1, 1, core.ncon)).cuda()
-c = torch.zeros(max(m.meta.ncon, 1), dtype=torch.float64, device="cuda")
-jv = torch.zeros(max(m.meta.nnzj, 1), dtype=torch.float64, device="cuda")
-hv = torch.zeros(max(m.meta.nnzh, 1), dtype=torch.float64, device="cuda")
+y = torch.from_numpy(rng.uniform(-1, 1, max(m.loc_ncon, 1))).cuda()
+c = torch.zeros(max(m.loc_ncon, 1), dtype=torch.float64, device="cuda")
+jv = torch.zeros(max(m.loc_nnzj, 1), dtype=torch.float64, device="cuda")
+hv = torch.zeros(max(m.loc_nnzh, 1), dtype=torch.float64, device="cuda")
 g = torch.zeros(m.meta.nvar, dtype=torch.float64, device="cuda")
 
 
@@ -77,8 +78,8 @@ if os.environ.get("IEXA_EVAL3", "1") != "0":   # the fused cons + jac + hess ker
     print(f"eval3 (one fused launch): {ms:.4f} ms -> {1e3/ms:.0f} evals/s, {sum(B[2:])/ms/1e6:.0f} GB/s ({sum(B[2:])/ms/1e6/6552:.3f} of 6552)  [three launches: {tot:.4f} ms; module build {tb3:.2f}s]")
 if os.environ.get("IEXA_PROD", "1") != "0":  # matrix-free products (fused kernels, second NVRTC module compiled on first use)
     v = torch.from_numpy(rng.uniform(-1, 1, core.nvar)).cuda()
-    w = torch.from_numpy(rng.uniform(-1, 1, max(core.ncon, 1))).cuda()
-    Jv = torch.zeros(max(m.meta.ncon, 1), dtype=torch.float64, device="cuda")
+    w = torch.from_numpy(rng.uniform(-1, 1, max(m.loc_ncon, 1))).cuda()
+    Jv = torch.zeros(max(m.loc_ncon, 1), dtype=torch.float64, device="cuda")
     Jtw = torch.zeros(m.meta.nvar, dtype=torch.float64, device="cuda"); Hv = torch.zeros_like(Jtw)
     tp = time.time(); ex.jprod_(m, x, v, Jv); torch.cuda.synchronize(); print(f"product module build {time.time()-tp:.2f}s note={m.L.iexa_engine_note(m.h).decode()[:80]!r}")
     Bp = [ex.algorithmic_bytes(m, w_) for w_ in (5, 6, 7)]
