@@ -217,6 +217,31 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 # helpers of the GPU arm
 # ---------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(gpu_index: int):
+    """one process per GPU: run this rank — and therefore allocate its pinned host buffers — on the NUMA node its GPU hangs off
+    (what `numactl --cpunodebind --membind` does in a deployment): the host-buffer path (`e2e`) otherwise pulls half of the
+    ranks' PCIe traffic across the socket interconnect.  Best effort; returns the node or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]            # sysfs uses a 4-digit domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 class Ctx:
     """torch / distributed plumbing of one rank"""
 
@@ -231,6 +256,7 @@ class Ctx:
             raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.numa = bind_to_gpu_numa_node(self.local_rank) if self.world > 1 else None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self._flush = None
@@ -667,7 +693,7 @@ def main():
                    "build_s": {"lowering": t_core, "plan+upload+nvrtc": t_plan, "plan+upload (image cached)": t_rebuild,
                                "nvrtc_compiles": int(cstat[0].value), "disk_cache_hits": int(cstat[1].value),
                                "note": "compiled images are cached in memory and on disk keyed by the generated source (IEXA_CACHE_DIR)"},
-                   "warmup_steps_run": int(nwarm)},
+                   "warmup_steps_run": int(nwarm), "numa_node_of_rank0": ctx.numa},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval3": eval3, "products": products, "iteration": iteration,
         "x_distribution": xdist, "workloads": workloads,
         "gpu_launches": int(args.steps * launches_step),

@@ -219,6 +219,7 @@ class ExaCore:
         self.ncon = 0
         self.gens: List[GenSpec] = []
         self.par_functions = []           # (Parameter, Tape, Itr): blocks the engine evaluates on the device
+        self.var_defaults = []            # per add_var block: (n, start is 0, lvar is -inf, uvar is +inf)
         self._x0 = self._lvar = self._uvar = self._theta = None
 
     # -- add_var / add_par ------------------------------------------------------------------------
@@ -235,6 +236,9 @@ class ExaCore:
 
         v = Variable(self.nvar, dims)
         self.x0.append(col(start)); self.lvar.append(col(lvar)); self.uvar.append(col(uvar))
+        # blocks whose start / bounds are the engine's defaults (0, -inf, +inf) need no host array at all (model.py)
+        sc = lambda a, d: np.ndim(a) == 0 and float(a) == d
+        self.var_defaults.append((n, sc(start, 0.0), sc(lvar, -np.inf), sc(uvar, np.inf)))
         self.nvar += n
         self._x0 = None
         return v
@@ -261,12 +265,12 @@ class ExaCore:
         return p
 
     # flat vectors (mutable until the model is built: transform.jl:216-231 patches them)
-    def _flat(self):
-        if self._x0 is None:
+    def _flat(self, what="x"):
+        if what == "x" and self._x0 is None:
             cat = lambda l: np.concatenate(l) if l else np.zeros(0)
             self._x0, self._lvar, self._uvar = cat(self.x0), cat(self.lvar), cat(self.uvar)
             self.x0, self.lvar, self.uvar = [self._x0], [self._lvar], [self._uvar]
-        if self._theta is None:
+        if what == "theta" and self._theta is None:
             self._theta = np.concatenate(self.theta) if self.theta else np.zeros(0)
             self.theta = [self._theta]
 
@@ -277,7 +281,7 @@ class ExaCore:
     @property
     def uvar_vec(self): self._flat(); return self._uvar
     @property
-    def theta_vec(self): self._flat(); return self._theta
+    def theta_vec(self): self._flat("theta"); return self._theta
 
     # -- add_con / add_obj ------------------------------------------------------------------------
     def _lower(self, expr, itr: Itr) -> Tape:

@@ -94,6 +94,7 @@ int32_t iexa_patch_var(iexa_plan *p, int32_t which, int64_t i, double value) {
   NEED_PLAN(p);
   if (p->plan.finalized && which != 0) return fail(IEXA_ERR_STATE, "bounds are frozen after finalize");
   if (i < 1 || i > p->plan.nvar) return fail(IEXA_ERR_INVALID, "variable index out of range");
+  if (which >= 0 && which <= 2) p->plan.materialise_vars();
   std::vector<double> *v = which == 0 ? &p->plan.x0 : which == 1 ? &p->plan.lvar : which == 2 ? &p->plan.uvar : nullptr;
   if (!v) return fail(IEXA_ERR_INVALID, "which must be 0,1,2");
   (*v)[i - 1] = value;
@@ -223,6 +224,7 @@ int32_t iexa_get_vector(const iexa_plan *p, int32_t which, double *out) {
     else std::memcpy(out, P.y0.data(), P.y0.size() * 8);
     return IEXA_OK;
   }
+  const_cast<iexa::Plan &>(P).materialise_vars();
   const std::vector<double> *v = which == 0 ? &P.x0 : which == 1 ? &P.lvar : &P.uvar;
   if (!v->empty()) std::memcpy(out, v->data(), v->size() * 8);
   return IEXA_OK;
@@ -234,6 +236,7 @@ int32_t iexa_set_vector(iexa_plan *p, int32_t which, const double *in) {
   iexa::Plan &P = p->plan;
   if (!in || (which != 0 && which != 5)) return fail(IEXA_ERR_INVALID, "only x0 (0) and y0 (5) can be set");
   if (which == 5) { P.y0.assign(in, in + P.ncon); return IEXA_OK; }
+  P.materialise_vars();
   if (!P.x0.empty()) std::memcpy(P.x0.data(), in, P.x0.size() * 8);
   return IEXA_OK;
   GUARD_END

@@ -63,8 +63,14 @@ class ExaModel:
             _lib.check(L, L.iexa_set_option(h, _lib.IEXA_OPT_STRICT_IEEE, int(bool(strict_ieee))))
         self._keep = []
         off = C.c_int64()
-        x0, lv, uv = (np.ascontiguousarray(v, dtype=np.float64) for v in (core.x0_vec, core.lvar_vec, core.uvar_vec))
-        if core.nvar:
+        if core._x0 is None and len(core.var_defaults) == len(core.x0) and core.nvar:
+            # block by block, as the reference calls add_var (transform.jl:113,154): no concatenated 8*nvar-byte host vectors, and a
+            # block whose start / bounds are the defaults (0, -inf, +inf) passes NULL — the engine fills them itself
+            for (n, d0, dl, du), a0, al, au in zip(core.var_defaults, core.x0, core.lvar, core.uvar):
+                _lib.check(L, L.iexa_add_var(h, n, None if d0 else a0.ctypes.data, None if dl else al.ctypes.data,
+                                             None if du else au.ctypes.data, C.byref(off)))
+        elif core.nvar:
+            x0, lv, uv = (np.ascontiguousarray(v, dtype=np.float64) for v in (core.x0_vec, core.lvar_vec, core.uvar_vec))
             _lib.check(L, L.iexa_add_var(h, core.nvar, x0.ctypes.data, lv.ctypes.data, uv.ctypes.data, C.byref(off)))
         th = np.ascontiguousarray(core.theta_vec, dtype=np.float64)
         itr_ids = {}
