@@ -281,6 +281,7 @@ struct BodyGen {
   std::vector<std::string> ixname;
   bool use32, idx32;
   size_t smem_doubles = 0;
+  bool rider = false;           // body appended to another group's case: k, kl, active, tid, ... are already in scope
   std::string outname = "out";  // objective groups inside the fused eval3 kernel write their Hessian slots to out3
   // fused eval3 body: outputs of member m and program p (0 value, 1 first, 2 second order) form the "virtual member" 3m+p
   bool fused3() const { return prog == GPROG_ALL; }
@@ -418,6 +419,7 @@ struct BodyGen {
     int nflush = 0;
     for (auto &om : outmap) outs_left[om.first]++;
     std::vector<std::vector<std::pair<int, std::string>>> pending(nvm);
+    if (!rider) {
     if (G.is_class) {
       o << "      const int nblk_ = (int)" << C(CI_CLS_NBLK) << ";\n"
         << "      const int chunk_ = blk_ / nblk_, wb_ = blk_ - chunk_ * nblk_;\n";
@@ -432,6 +434,7 @@ struct BodyGen {
       << "      const bool active = tid < nact;\n"
       << "      const long long k = kb + (active ? tid : nact - 1);\n"
       << "      const long long kl = k - k0; (void)kl;\n";
+    }
     if (tma && maxstep > 0)
       o << "      double* __restrict__ wsm = sm + (tid >> 5) * " << 2 * bufsz << ";\n"
         << "      const int out_par = (int)(((unsigned long long)out >> 3) & 1ull);\n"
@@ -446,8 +449,10 @@ struct BodyGen {
       o << "      double* __restrict__ wsm = sm + (tid >> 5) * " << 32 * maxstep << ";\n"
         << "      const int lane = tid & 31, w0 = tid & ~31;\n"
         << "      const int wact = nact - w0 < 0 ? 0 : (nact - w0 > 32 ? 32 : nact - w0);\n";
-    if (use32) o << "      const unsigned kk = (unsigned)k; (void)kk;\n";
-    else o << "      const long long kk = k; (void)kk;\n";
+    if (!rider) {
+      if (use32) o << "      const unsigned kk = (unsigned)k; (void)kk;\n";
+      else o << "      const long long kk = k; (void)kk;\n";
+    }
     if (G.is_class) { // the instances of this block's chunk, one after the other (same supports, same program)
       const int ninst = (int)G.n_inst(), ch = class_chunk();
       const char *ue = getenv("IEXA_CLASS_UNROLL");
@@ -627,6 +632,11 @@ struct BodyGen {
               islot = c;
               const int w = prog == PROG_JTV ? 0 : 1;
               direct = G.scat_phase[w] == 0 && (size_t)I.dst < G.scat_direct[w].size() && G.scat_direct[w][I.dst];
+              if (direct && G.scat_direct[w][I.dst] == 2) { // rider: the same thread stored this entry a moment ago
+                std::string i = ix(islot);
+                o << "      if (active) out[" << i << " - 1] += " << v << ";\n";
+                break;
+              }
             } else {
               islot = G.jac_slot[m][c];
               const std::vector<Generator> &gens = G.is_obj ? P.objs : P.cons;
@@ -729,11 +739,24 @@ GeneratedSource generate_source(const Plan &plan, int set) {
       if (d.ks == KS_EVAL3 && G.is_obj) gprog = PROG_D2;
       if (gprog != PROG_VAL && G.prog[gprog].nout == 0) continue;
       if (d.phase >= 0 && G.scat_phase[d.prog == PROG_JTV ? 0 : 1] != d.phase) continue;
+      const int sw = d.prog == PROG_JTV ? 0 : 1;
+      if (d.phase == 0 && G.scat_rider_of[sw] >= 0) continue; // evaluated inside its primary's case (below)
       BodyGen bg(plan, G, (int)gi, gprog, d.sink, out.ci);
       if (d.ks == KS_EVAL3 && G.is_obj) bg.outname = "out3";
       bg.cb = d.ks;
       bg.idx32 = bg.idx32 && idx32_for(d.ks);
       std::string body = bg.run();
+      if (d.phase == 0)
+        for (size_t ri = 0; ri < plan.groups.size(); ++ri) {
+          const Group &R = plan.groups[ri];
+          if (R.scat_rider_of[sw] != (int)gi || R.scat_phase[sw] != 0 || R.prog[d.prog].nout == 0) continue;
+          BodyGen rb(plan, R, (int)ri, d.prog, d.sink, out.ci);
+          rb.cb = d.ks;
+          rb.rider = true;
+          rb.use32 = bg.use32;           // the primary declared kk with its own width
+          rb.idx32 = bg.idx32;
+          body += "      { // rider: group " + std::to_string(ri) + " on the same supports, same thread\n" + rb.run() + "      }\n";
+        }
       cases << "    case " << gi << ":\n    {\n" << body << "    } break;\n";
       smem = std::max(smem, bg.smem_doubles * 8);
       out.groups_of[d.ks].push_back((int)gi);

@@ -766,6 +766,10 @@ class CudaEngine : public Engine {
         std::stable_sort(ord.begin(), ord.end(), [&](const Ord &a, const Ord &b) {
           return plan_.groups[a.gi].prog[prog].code.size() > plan_.groups[b.gi].prog[prog].code.size();
         });
+      } else if (oe ? oe[0] == 'g' : false) {
+        // group-major: all blocks of one body back to back (fewer distinct case bodies resident at a time: the instruction
+        // cache of a kernel with dozens of shape-class bodies — ncu: no_instruction is the 2nd stall of the 118-bus OPF cons)
+        std::stable_sort(ord.begin(), ord.end(), [](const Ord &a, const Ord &b) { return a.gi < b.gi; });
       } else
       std::stable_sort(ord.begin(), ord.end(), [](const Ord &a, const Ord &b) { return a.frac < b.frac; });
       for (const Ord &o : ord) items.push_back(WorkItem{o.gi, o.b});

@@ -126,7 +126,12 @@ struct Group {
   // scatter products (jtprod! / hprod!): phase of the group (0: launched first, may store single-writer outputs directly;
   // 1: launched after phase 0, atomics only) and, per output, 1 = plain store — Plan::analyse_scatter
   int scat_phase[2] = {1, 1};
-  std::vector<uint8_t> scat_direct[2];
+  std::vector<uint8_t> scat_direct[2];   // per output: 0 atomic, 1 plain store, 2 accumulate onto the store of the same thread (rider)
+  // RIDER: a group with the SAME number of supports as an accepted phase-0 group whose single-writer outputs address the same entries
+  // through the same thread (index c0 + s*k with equal c0, s) is evaluated by that group's threads right after its body —
+  // `out[i] += v` by the thread that just stored out[i]: no atomic, no zero-fill, x / v loads hit the L1 the primary
+  // filled.  hprod! of config 3: the fused ODE rows ride on the objective group (both walk the time supports).
+  int scat_rider_of[2] = {-1, -1};
   size_t dag_nodes = 0;
   // Shape class (build_groups(class_mode = true)): ONE member program shared by many generators of
   // identical shape — same tape structure, columns and index-term structure; they differ only in
@@ -856,6 +861,7 @@ struct Plan {
       for (size_t gi = 0; gi < groups.size(); ++gi) {
         Group &G = groups[gi];
         G.scat_phase[w] = 1;
+        G.scat_rider_of[w] = -1;
         G.scat_direct[w].assign(G.outmap[prog].size(), 0);
         if (G.prog[prog].nout > 0 && G.k1 > G.k0 && !G.is_class && !no_direct) order.push_back((int)gi);
       }
@@ -891,6 +897,71 @@ struct Plan {
         G.scat_direct[w] = isd;
         direct.insert(direct.end(), D.begin(), D.end());
         atomic.insert(atomic.end(), A.begin(), A.end());
+      }
+      // riders (see Group::scat_rider_of)
+      if (!getenv("IEXA_NO_RIDERS")) {
+        struct St { int64_t c0, s; Iv iv; };
+        std::map<int, std::vector<St>> stored; // primary -> what its unit stores, thread k <-> entry c0 + s*k
+        auto stores_of = [&](int gi) -> std::vector<St> & {
+          auto it = stored.find(gi);
+          if (it != stored.end()) return it->second;
+          std::vector<St> v;
+          const Group &G = groups[gi];
+          const Iterator &itr = itrs[G.itr];
+          for (size_t j = 0; j < G.outmap[prog].size(); ++j) {
+            if (!G.scat_direct[w][j]) continue;
+            int64_t c0, sg;
+            if (!linear_in_k(itr, G.ctx.int_cols, G.K, G.ctx.uidx[G.outmap[prog][j].second], c0, sg)) continue;
+            const int64_t a = c0 + sg * G.k0, b = c0 + sg * (G.k1 - 1);
+            v.push_back(St{c0, sg, {std::min(a, b), std::max(a, b)}});
+          }
+          return stored.emplace(gi, std::move(v)).first->second;
+        };
+        for (size_t hi = 0; hi < groups.size(); ++hi) {
+          Group &H = groups[hi];
+          if (H.is_class || H.scat_phase[w] == 0 || H.prog[prog].nout == 0 || H.k1 <= H.k0) continue;
+          for (int gi : order) {
+            const Group &G = groups[gi];
+            if (G.scat_phase[w] != 0 || G.scat_rider_of[w] >= 0 || G.K != H.K || G.k0 != H.k0 || G.k1 != H.k1 || (size_t)gi == hi) continue; // same support count: thread k <-> support k of both
+            std::vector<St> &unit = stores_of(gi);
+            const Iterator &itr = itrs[H.itr];
+            std::vector<uint8_t> mode(H.outmap[prog].size(), 0);
+            std::vector<St> fresh;
+            std::vector<Iv> Aat;
+            bool ok = true, any = false;
+            for (size_t j = 0; j < H.outmap[prog].size() && ok; ++j) {
+              const IndexExpr &e = H.ctx.uidx[H.outmap[prog][j].second];
+              int64_t c0, sg, lo, hi2;
+              if (linear_in_k(itr, H.ctx.int_cols, H.K, e, c0, sg)) {
+                const int64_t a = c0 + sg * H.k0, b = c0 + sg * (H.k1 - 1);
+                const Iv iv{std::min(a, b), std::max(a, b)};
+                bool same = false;
+                for (const St &u : unit) same = same || (u.c0 == c0 && u.s == sg);
+                for (const St &u : fresh) same = same || (u.c0 == c0 && u.s == sg);
+                if (same) { mode[j] = 2; any = true; }
+                else if (iv.first >= 1 && iv.second <= nvar && !overlaps(direct, iv) && !overlaps(atomic, iv)) {
+                  bool clash = false;
+                  for (const St &u : fresh) clash = clash || (iv.first <= u.iv.second && u.iv.first <= iv.second);
+                  for (const Iv &a2 : Aat) clash = clash || (iv.first <= a2.second && a2.first <= iv.second);
+                  if (clash) ok = false; else { mode[j] = 1; fresh.push_back(St{c0, sg, iv}); any = true; }
+                } else ok = false;
+              } else {
+                index_range(itr, H.ctx.int_cols, e, H.k0, H.k1, lo, hi2);
+                const Iv iv{lo, hi2};
+                bool clash = overlaps(direct, iv);
+                for (const St &u : fresh) clash = clash || (iv.first <= u.iv.second && u.iv.first <= iv.second);
+                if (clash) ok = false; else Aat.push_back(iv);
+              }
+            }
+            if (!ok || !any) continue;
+            H.scat_phase[w] = 0;
+            H.scat_rider_of[w] = gi;
+            H.scat_direct[w] = mode;
+            for (const St &u : fresh) { unit.push_back(u); direct.push_back(u.iv); }
+            atomic.insert(atomic.end(), Aat.begin(), Aat.end());
+            break;
+          }
+        }
       }
       std::sort(direct.begin(), direct.end());
       scat_zero_ranges[w].clear();

@@ -217,12 +217,18 @@ int32_t hostcheck_prod(iexa_plan *p, int32_t which, int32_t use_groups, const do
   const int prog = which - 2, w = which - 6;
   int64_t st[4] = {0, 0, 0, 0};
   if (which != 5) for (auto &z : P.scat_zero_ranges[w]) { for (int64_t i = 0; i < z.second; ++i) out[z.first + i] = 0.0; st[2] += z.second; }
-  for (int phase = 0; phase < 2; ++phase)
+  // device protocol: phase-0 primaries, then their riders (same thread, right after the primary's body), then phase 1
+  for (int phase = 0; phase < 3; ++phase)
   for (const Group &G : P.groups) {
     if (G.is_obj && which != 7) continue;
     const Program &pr = G.prog[prog];
-    if (which != 5 && (pr.nout == 0 || G.scat_phase[w] != phase)) continue;
-    if (which == 5 && phase == 1) continue;
+    if (which != 5) {
+      if (pr.nout == 0) continue;
+      const bool is_rider = G.scat_phase[w] == 0 && G.scat_rider_of[w] >= 0;
+      const int gp = G.scat_phase[w] == 1 ? 2 : (is_rider ? 1 : 0);
+      if (gp != phase) continue;
+    }
+    if (which == 5 && phase != 0) continue;
     if (which != 5) { st[3]++; if (phase == 0) st[0]++; }
     tmp.assign(pr.nout > 0 ? pr.nout : 1, 0.0);
     const std::vector<Generator> &gens = G.is_obj ? P.objs : P.cons;
@@ -236,8 +242,8 @@ int32_t hostcheck_prod(iexa_plan *p, int32_t which, int32_t use_groups, const do
       for (size_t j = 0; j < G.outmap[prog].size(); ++j) {
         if (which == 5) { const Generator &g = inst >= 0 ? gens[G.inst_gen(ii, G.outmap[prog][j].first)] : P.member(G, G.outmap[prog][j].first); out[g.o0 + k] = tmp[j]; continue; }
         const int64_t i = g_index(P, G, G.outmap[prog][j].second, k, inst) - 1;
-        const bool direct = phase == 0 && G.scat_direct[w][j];
-        if (direct) { out[i] = tmp[j]; if (ii == 0 && k == 0) st[1]++; } else out[i] += tmp[j];
+        const int mode = phase < 2 ? G.scat_direct[w][j] : 0;
+        if (mode == 1) { out[i] = tmp[j]; if (ii == 0 && k == 0) st[1]++; } else out[i] += tmp[j]; // mode 2 (rider): += onto the primary's store
       }
     }
   }

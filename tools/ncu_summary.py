@@ -37,13 +37,13 @@ def main(path):
                 print(f"   {key:<75} {r[col[key]]} {units[col[key]]}")
         st = []
         for n, i in col.items():
-            if n.startswith(STALL) and n.endswith("_per_warp_active.pct") and r[i] not in ("", "n/a"):
+            if n.startswith(STALL) and n.endswith("_per_issue_active.ratio") and r[i] not in ("", "n/a"):
                 try:
-                    st.append((float(r[i].replace(",", "")), n[len(STALL):-len("_per_warp_active.pct")]))
+                    st.append((float(r[i].replace(",", "")), n[len(STALL):-len("_per_issue_active.ratio")]))
                 except ValueError:
                     pass
         st.sort(reverse=True)
-        print("   stalls (% of warp-active cycles): " + ", ".join(f"{n}={v:.1f}" for v, n in st[:7]))
+        print("   stalls (warps stalled per issue-active cycle): " + ", ".join(f"{n}={v:.2f}" for v, n in st[:7]))
         if len(rs) > 1 and "gpu__time_duration.sum" in col:
             print("   durations of all captured launches: " + ", ".join(x[col["gpu__time_duration.sum"]] for x in rs) + " " + units[col["gpu__time_duration.sum"]])
 
