@@ -147,7 +147,9 @@ enum { SINK_DENSE = 0, SINK_SUM = 1, SINK_SCATTER = 2 };
 constexpr int kMaxStagedStep = 64; // members with more slots than this store directly
 // measured on B200 (config 3): capping registers at 64 (8 blocks of 128 threads per SM) lifts hess from 64% to 82% of the
 // HBM roofline and cons/jac by 3 points; the occasional spill stays in L1
-static const int kDefaultMinBlocks[KS__N] = {8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 6};
+// products (round 2, config 3): hprod! with its rider body needs registers — 8 blocks/SM (64 registers, 400 B of spills) 0.291 ms,
+// 6 blocks (80 registers) 0.215 ms; jtprod! 0.310 -> 0.300 ms at 6; jprod 0.139 at 8 (0.144 at 10)
+static const int kDefaultMinBlocks[KS__N] = {8, 8, 8, 8, 8, 8, 6, 6, 6, 6, 6};
 int spec_block() {
   // threads per block of the specialised kernels (a multiple of 32).  Measured on B200, config 3:
   // 128 -> 0.585 ms/eval, 64 -> 0.597, 32 -> 0.627; on a 1/8 shard 64 and 128 tie (0.092 ms).
@@ -181,8 +183,8 @@ static bool use_pdl() { static bool v = [] { const char *e = getenv("IEXA_PDL");
 // slots 5..9 (jprod, jtprod phases 0/1, hprod phases 0/1): IEXA_HOIST_PROD="<jprod>,<jtprod>,<hprod>"
 static int hoist_loads(int cb) {
   // products (B200, config 3, round 2): jprod 0.139 ms at 12 (0.148 at 24, 0.156 at 0); jtprod 0.310 at 24 (0.316 at 12, 0.344 at 0);
-  // hprod 0.2765 at 4 (0.283 at 0 / 8, 0.293 at 16, 0.298 at 32)
-  static int v[KS__N] = {-1, -1, -1, -1, 16, 12, 24, 24, 4, 4, 16};
+  // hprod (80 registers, rider body fused): 0.215 at 16
+  static int v[KS__N] = {-1, -1, -1, -1, 16, 12, 24, 24, 16, 16, 16};
   static bool init = [] {
     if (const char *e = getenv("IEXA_HOIST")) {
       int w[5] = {v[0], v[1], v[2], v[3], v[4]};
@@ -776,6 +778,13 @@ GeneratedSource generate_source(const Plan &plan, int set) {
       minb = v[d.ks];
     } else {
       minb = kDefaultMinBlocks[d.ks] * 128 / spec_block();
+      if (const char *pe = getenv("IEXA_MINBLOCKS_PROD")) { // "<jprod>,<jtprod>,<hprod>" (tuning)
+        int v[3] = {8, 8, 8};
+        sscanf(pe, "%d,%d,%d", &v[0], &v[1], &v[2]);
+        if (d.ks == KS_JPROD) minb = v[0];
+        else if (d.ks == KS_JTPROD0 || d.ks == KS_JTPROD1) minb = v[1];
+        else if (d.ks == KS_HPROD0 || d.ks == KS_HPROD1) minb = v[2];
+      }
     }
     kernels << "extern \"C\" __global__ void __launch_bounds__(IEXA_BLOCK" << (minb > 0 ? ", " + std::to_string(minb) : std::string()) << ") " << kCbName[d.ks]
             << "(const WorkItem* __restrict__ work, const double* __restrict__ x,\n"
