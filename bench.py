@@ -115,17 +115,36 @@ def workload_config(name, supports, nvar, ncon, nnzj, nnzh):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region.  A 20-step timed region lasts 10 ms — shorter than nvidia-smi's fastest
+    sampling period (and a longer warm-up to wait for it runs the GPU into its power cap) — so the clocks are polled in-process
+    through NVML every millisecond by a thread (the launching thread sits in cudaStreamSynchronize without the GIL);
+    `nvidia-smi -lms` (B200_PROFILING.md recipe) is the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
-        self.rows = []
-        self.proc = None
+        self.rows, self.samples = [], []
+        self.proc, self.nvml, self.h = None, None, None
         self.gpu = gpu_index
+        self._stop = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices: honour CUDA_VISIBLE_DEVICES
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -135,11 +154,41 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                util = int(n.nvmlDeviceGetUtilizationRates(self.h).gpu)
+                self.samples.append((time.perf_counter(), mhz, rs, util))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t0=None, t1=None):
+        if self.nvml is not None:
+            self._stop = True
+            self.t.join(timeout=1)
+            sel = [s for s in self.samples if (t0 is None or s[0] >= t0) and (t1 is None or s[0] <= t1)] or self.samples
+            reasons = set()
+            for s in sel:
+                for bit, name in self.REASONS.items():
+                    if s[2] & bit:
+                        reasons.add(name)
+            return {"sm_mhz": float(np.median([s[1] for s in sel])) if sel else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(reasons), "samples": len(sel), "samples_total": len(self.samples),
+                    "how": "NVML polled in-process every ms; samples between the start of the timed region and the end of the per-kernel pass"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -161,7 +210,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "how": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -470,18 +519,14 @@ def main():
     def step():
         f_cons(); f_jac(); f_hess()
 
-    # clocks / throttle reasons are sampled from the warm-up through the timed region and the per-kernel pass (a 20-step
-    # timed region lasts 10 ms — shorter than nvidia-smi's fastest sampling period)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_w = time.perf_counter()
-    nwarm = 0
-    while nwarm < max(args.warmup, 3) or time.perf_counter() - t_w < 0.35:
-        step(); nwarm += 1
-        if nwarm % 16 == 0:
-            torch.cuda.synchronize()
+    nwarm = max(args.warmup, 3)
+    for _ in range(nwarm):
+        step()
     barrier()
+    t_mark0 = sampler.mark()
     # (1) the timed region: EXACTLY K steps between two events on the launching (current torch) stream —
     #     nothing else is enqueued between the callbacks, as in a solver iteration
     e0, e1 = ctx.ev(), ctx.ev()
@@ -505,7 +550,7 @@ def main():
         ev[i][2].record(); f_hess()
         ev[i][3].record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_mark0, sampler.mark()) if rank == 0 else None
     per = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in ev]).mean(axis=0)  # ms
     per = ctx.max_over_ranks(per)
     ms_per_step = float(ctx.max_over_ranks(total_ms)[0]) / args.steps

@@ -128,6 +128,7 @@ def _declare(L):
     sig("hostcheck_eval_groups", _i32, _vp, _i32, _vp, _vp, _dbl, _vp, C.POINTER(_i32))
     sig("hostcheck_set_class_mode", _i32, _vp, _i32)
     sig("hostcheck_structure", _i32, _vp, _i32, _vp, _vp)
+    sig("hostcheck_scatter_info", _i32, _vp, _i32, _vp)
     sig("hostcheck_prod", _i32, _vp, _i32, _i32, _vp, _vp, _vp, _dbl, _vp, _vp)
     sig("hostcheck_gen_stats", _i32, _vp, _i32, _i32, _vp)
     sig("hostcheck_grad_stats", _i32, _vp, _vp)

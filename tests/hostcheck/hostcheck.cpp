@@ -251,6 +251,19 @@ int32_t hostcheck_prod(iexa_plan *p, int32_t which, int32_t use_groups, const do
   return IEXA_OK;
 }
 
+// two-phase scatter analysis of jtprod! (w = 0) / hprod! (w = 1): out = {phase-0 primaries, riders, phase-1 groups}
+int32_t hostcheck_scatter_info(iexa_plan *p, int32_t w, int64_t *out) {
+  if (!p || !p->plan.finalized || w < 0 || w > 1) return IEXA_ERR_STATE;
+  out[0] = out[1] = out[2] = 0;
+  for (const Group &G : p->plan.groups) {
+    if (G.prog[4 + w].nout == 0) continue;
+    if (G.scat_phase[w] == 1) out[2]++;
+    else if (G.scat_rider_of[w] >= 0) out[1]++;
+    else out[0]++;
+  }
+  return IEXA_OK;
+}
+
 // which: 0 jac, 1 hess; 1-based int64 rows/cols, GLOBAL layout
 int32_t hostcheck_structure(iexa_plan *p, int32_t which, int64_t *rows, int64_t *cols) {
   if (!p || !p->plan.finalized) return IEXA_ERR_STATE;

@@ -85,6 +85,19 @@ def test_scatter_phases_quadrotor(hostcheck_lib):
     assert st[0] >= 1 and st[1] >= 7, st
 
 
+def test_hprod_rider_quadrotor(hostcheck_lib):
+    """hprod! of the quadrotor: the objective group (K = T) stores its 10 diagonal blocks directly; the fused ODE rows walk the
+    same supports and ride on it — `out[i] += v` by the thread that just stored out[i] — so the whole product is ONE launch
+    without atomics or a second phase; jtprod! keeps its second phase (the collocation rows walk other supports)"""
+    L = hostcheck_lib
+    m = ex.ExaModel(models.quadrotor(9, "oc"), flags=ex.lib.IEXA_F_NO_DEVICE, library=L)
+    info = np.zeros(3, dtype=np.int64)
+    assert L.hostcheck_scatter_info(m.h, 1, info.ctypes.data) == 0
+    assert list(info) == [1, 1, 0], info
+    assert L.hostcheck_scatter_info(m.h, 0, info.ctypes.data) == 0
+    assert info[0] == 1 and info[2] == 3, info
+
+
 def test_scatter_phases_product_iterator(hostcheck_lib):
     """pandemic: the column-major index of a variable over the (t, xi) product iterator is linear in k (mixed-radix digits
     recombine), so the scenario blocks are single-writer; u(t) is shared by the scenarios -> atomics on a zeroed range"""
