@@ -308,6 +308,21 @@ def test_opf_shape_classes_and_budget_fallback(oracle_cache, monkeypatch):
         ex.hess_structure_(m, r, cc)
         ro, co = om.hess_structure()
         assert (r.cpu().numpy() == ro).all() and (cc.cpu().numpy() == co).all()
+        # fused products and the fused eval3 kernel through the same (fused-class / class / interpreter) paths
+        rng = np.random.default_rng(2)
+        v, w = rng.uniform(-1, 1, om.nvar), rng.uniform(-1, 1, om.ncon)
+        vd, wd = torch.from_numpy(v).cuda(), torch.from_numpy(w).cuda()
+        z = lambda n: torch.full((max(n, 1),), 7.0, dtype=torch.float64, device="cuda")
+        assert_close(ex.jprod_(m, xd, vd, z(om.ncon)).cpu().numpy()[: om.ncon], om.jprod(x, v), "jprod")
+        assert_close(ex.jtprod_(m, xd, wd, z(om.nvar)).cpu().numpy(), om.jtprod(x, w), "jtprod")
+        assert_close(ex.hprod_(m, xd, yd, vd, z(om.nvar), 0.9).cpu().numpy(), om.hprod(x, y, v, 0.9), "hprod")
+        c3, j3, h3 = z(om.ncon), z(om.nnzj), z(om.nnzh)
+        ex.eval3_(m, xd, yd, c3, j3, h3, 0.9)
+        assert_close(c3.cpu().numpy()[: om.ncon], om.cons(x), "eval3 cons")
+        assert_close(j3.cpu().numpy()[: om.nnzj], om.jac_coord(x), "eval3 jac")
+        assert_close(h3.cpu().numpy()[: om.nnzh], om.hess_coord(x, y, 0.9), "eval3 hess")
+        if expect_spec:
+            assert m.L.iexa_engine_note(m.h) == b"", m.L.iexa_engine_note(m.h)
 
 
 @pytest.mark.parametrize("mode", list(MODES))
