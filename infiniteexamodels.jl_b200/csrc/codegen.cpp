@@ -63,6 +63,7 @@ struct DynApi {
   int (*nvrtcGetProgramLogSize)(nvrtcProgram, size_t *) = nullptr;
   int (*nvrtcGetProgramLog)(nvrtcProgram, char *) = nullptr;
   int (*nvrtcDestroyProgram)(nvrtcProgram *) = nullptr;
+  int (*nvrtcVersion)(int *, int *) = nullptr; // optional: part of the on-disk cache key
 
   std::mutex mu; // lazily initialised from any thread that finalizes a plan
   bool load_nvrtc(std::string &err) {
@@ -75,6 +76,7 @@ struct DynApi {
     L(nvrtcCreateProgram) L(nvrtcCompileProgram) L(nvrtcGetCUBINSize) L(nvrtcGetCUBIN)
     L(nvrtcGetProgramLogSize) L(nvrtcGetProgramLog) L(nvrtcDestroyProgram)
 #undef L
+    *(void **)(&nvrtcVersion) = dlsym(nvrtc, "nvrtcVersion");
     nvrtc_ok = true;
     return true;
   }
@@ -906,6 +908,12 @@ bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string
   const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
   std::string key_text = src;
   for (const char *o : opts) { key_text += '\n'; key_text += o; }
+  { // the compiler that produced an image is part of its identity
+    std::string verr;
+    int maj = 0, min = 0;
+    if (a.load_nvrtc(verr) && a.nvrtcVersion) a.nvrtcVersion(&maj, &min);
+    key_text += "\nnvrtc " + std::to_string(maj) + "." + std::to_string(min);
+  }
   if (!getenv("IEXA_DUMP_DIR") && disk_cache_load(key_text, cubin)) {
     std::lock_guard<std::mutex> g(cubin_cache_mutex());
     ++g_disk_hits;

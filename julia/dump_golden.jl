@@ -9,7 +9,10 @@
 #   int64 jrows[nnzj], jcols[nnzj] ; float64 jvals[nnzj] ;
 #   int64 hrows[nnzh], hcols[nnzh] ; float64 hvals[nnzh]
 # tests/test_golden_dumps.py loads every *.golden it finds, rebuilds the same model through the Python
-# front end, and compares structure bit-exactly and values to 1e-12 relative / 1e-14 absolute.
+# front end, IDENTIFIES the slot-order policy (iexa_set_option IEXA_OPT_SLOT_ORDER: the order in which ExaModels' symbolic
+# passes meet the leaves is data in the engine and in the oracle, not code) under which the plan compiler reproduces the dump's COO
+# structure bit for bit, and then compares values to 1e-12 relative / 1e-14 absolute.  If no known policy matches, the assertion
+# message names the two places (gen.hpp: GenCompiler::kids / jr / hr, oracle.c: kids) where a further order is added.
 using InfiniteExaModels, InfiniteOpt, ExaModels, NLPModels, Random
 
 function dump(name, im::InfiniteModel, dir)

@@ -43,14 +43,16 @@ def test_against_exa_models_dump(path, hostcheck_lib):
     compare_with_dump(path, hostcheck_lib)
 
 
-def test_dump_harness_on_a_dump_written_by_the_oracle(tmp_path, hostcheck_lib):
+@pytest.mark.parametrize("policy", [0, 1])
+def test_dump_harness_on_a_dump_written_by_the_oracle(tmp_path, hostcheck_lib, policy):
     """The comparison above has never seen a real dump (no Julia here).  This runs the SAME loader and comparison on a
-    file in julia/dump_golden.jl's binary format whose contents come from the oracle, so that the day a real dump is
-    dropped into tests/golden/ the harness itself is known to work — it pins nothing about ExaModels."""
+    file in julia/dump_golden.jl's binary format whose contents come from the oracle — under either slot-order policy: the
+    harness must IDENTIFY the policy from the structure and then hold the values — so that the day a real dump is
+    dropped into tests/golden/ the harness itself is known to work.  It pins nothing about ExaModels."""
     from oracle.oracle import OracleModel
     from conftest import eval_point
     core = BUILDERS["quadrotor_oc_40"]()
-    om = OracleModel(core)
+    om = OracleModel(core, slot_order=policy)
     x, y = eval_point(core, seed=0)
     jr, jc = om.jac_structure(); hr, hc = om.hess_structure()
     path = tmp_path / "quadrotor_oc_40.golden"
@@ -62,18 +64,38 @@ def test_dump_harness_on_a_dump_written_by_the_oracle(tmp_path, hostcheck_lib):
     compare_with_dump(str(path), hostcheck_lib)
 
 
-def compare_with_dump(path, hostcheck_lib):
+POLICIES = {0: "IEXA_SLOT_ORDER_LEFT_TO_RIGHT", 1: "IEXA_SLOT_ORDER_RIGHT_TO_LEFT"}
+
+
+def identify_policy(name, d, L):
+    """the slot-order policy (iexa_set_option IEXA_OPT_SLOT_ORDER) under which the plan compiler reproduces the dump's COO
+    structure bit for bit — the slot ORDER of ExaModels is data here, so a real dump only has to select a value"""
+    tried = []
+    for policy in POLICIES:
+        m = ex.ExaModel(BUILDERS[name](), flags=ex.lib.IEXA_F_NO_DEVICE, library=L, slot_order=policy)
+        if (m.meta.nvar, m.meta.ncon, m.meta.nnzj, m.meta.nnzh) != (len(d["x"]), len(d["y"]), len(d["jv"]), len(d["hv"])):
+            tried.append(f"{POLICIES[policy]}: dimensions differ")
+            continue
+        ok = True
+        for which, rk, ck in ((0, "jr", "jc"), (1, "hr", "hc")):
+            r = np.zeros(max(len(d[rk]), 1), dtype=np.int64); c = np.zeros_like(r)
+            L.hostcheck_structure(m.h, which, r.ctypes.data, c.ctypes.data)
+            ok = ok and (r[: len(d[rk])] == d[rk]).all() and (c[: len(d[ck])] == d[ck]).all()
+        if ok:
+            return policy, m
+        tried.append(f"{POLICIES[policy]}: structure differs")
+    raise AssertionError("no slot-order policy reproduces the dump's structure: " + "; ".join(tried) +
+                         " — add the order as a policy in gen.hpp (GenCompiler::kids / jr / hr) and oracle.c (kids)")
+
+
+def compare_with_dump(path, hostcheck_lib, expect_policy=None):
     name = os.path.splitext(os.path.basename(path))[0]
     d = load(path)
     L = hostcheck_lib
-    m = ex.ExaModel(BUILDERS[name](), flags=ex.lib.IEXA_F_NO_DEVICE, library=L)
-    assert (m.meta.nvar, m.meta.ncon, m.meta.nnzj, m.meta.nnzh) == (len(d["x"]), len(d["y"]), len(d["jv"]), len(d["hv"]))
-    r = np.zeros(len(d["jv"]), dtype=np.int64); c = np.zeros_like(r)
-    L.hostcheck_structure(m.h, 0, r.ctypes.data, c.ctypes.data)
-    assert (r == d["jr"]).all() and (c == d["jc"]).all(), "Jacobian structure must be bit-exact"
-    r = np.zeros(len(d["hv"]), dtype=np.int64); c = np.zeros_like(r)
-    L.hostcheck_structure(m.h, 1, r.ctypes.data, c.ctypes.data)
-    assert (r == d["hr"]).all() and (c == d["hc"]).all(), "Hessian structure must be bit-exact"
+    policy, m = identify_policy(name, d, L)
+    print(f"{name}: structure reproduced bit for bit under {POLICIES[policy]}")
+    if expect_policy is not None:
+        assert policy == expect_policy
     x, y = np.ascontiguousarray(d["x"]), np.ascontiguousarray(d["y"])
     for which, key, n in ((2, "cons", len(y)), (3, "jv", len(d["jv"])), (4, "hv", len(d["hv"])), (1, "grad", len(x))):
         out = np.zeros(max(n, 1))
