@@ -143,7 +143,13 @@ int32_t iexa_plan_destroy(iexa_plan *p);
  *     numbers (tests/test_nan_semantics.py: NaN pattern identical to the oracle on poisoned inputs for every BASELINE
  *     config); 0 folds them: identical results for finite inputs, a subset of the NaNs otherwise, 1.5-2.5 % faster.  */
 enum { IEXA_OPT_SLOT_ORDER = 1, IEXA_OPT_STRICT_IEEE = 2 };
-enum { IEXA_SLOT_ORDER_LEFT_TO_RIGHT = 0, IEXA_SLOT_ORDER_RIGHT_TO_LEFT = 1 };
+/*     JAC_ROW_SORTED (an engine-native layout, NOT a hypothesis about ExaModels): LEFT_TO_RIGHT for everything except the
+ *     first-order slots of constraint generators, which are put in increasing column order whenever that order is the
+ *     same at every support.  A generator's rows are contiguous in the COO array (ExaModels' own layout:
+ *     slot = o1 + o1step*(k-1) + c), so the array jac_coord! writes then IS a CSR value array — iexa_jac_csr_rowptr gives the
+ *     row pointers, iexa_jac_structure's cols are the column indices, and the COO->CSR pass (iexa_csr_apply) that a
+ *     KKT assembly otherwise pays per iteration disappears.  Same nnz, same values, a permutation of the default order. */
+enum { IEXA_SLOT_ORDER_LEFT_TO_RIGHT = 0, IEXA_SLOT_ORDER_RIGHT_TO_LEFT = 1, IEXA_SLOT_ORDER_JAC_ROW_SORTED = 2 };
 int32_t iexa_set_option(iexa_plan *p, int32_t key, int64_t value);
 
 /* ExaModels.add_var  — transform.jl:113 (finite), :154 (infinite + derivative vars).
@@ -226,6 +232,11 @@ int32_t iexa_jac_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_byt
                            int32_t memspace, void *stream);
 int32_t iexa_hess_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_bytes,
                             int32_t memspace, void *stream);
+/* is_csr_out = 1 when the jac_coord! array is already in CSR order (rows contiguous, columns strictly increasing inside a
+ * row): policy IEXA_SLOT_ORDER_JAC_ROW_SORTED and every constraint generator had a static column order.
+ * iexa_jac_csr_rowptr then writes the ncon+1 (local counts when world > 1) 0-based row pointers; IEXA_ERR_STATE otherwise. */
+int32_t iexa_jac_is_csr(const iexa_plan *p, int32_t *is_csr_out);
+int32_t iexa_jac_csr_rowptr(iexa_plan *p, void *rowptr, int32_t idx_bytes, int32_t memspace, void *stream);
 int32_t iexa_obj(iexa_plan *p, const double *x, double *f_host, int32_t memspace, void *stream);
 /* world > 1: g is written only inside this rank's iexa_x_ranges (its own supports, shared variables, halos); the rank contributes
  * nothing elsewhere and leaves those entries UNTOUCHED (zero g first if the whole vector is to be all-reduced)              */

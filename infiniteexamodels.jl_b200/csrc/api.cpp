@@ -57,7 +57,7 @@ int32_t iexa_set_option(iexa_plan *p, int32_t key, int64_t value) {
     return fail(IEXA_ERR_STATE, "options must be set before the first generator is added");
   switch (key) {
     case IEXA_OPT_SLOT_ORDER:
-      if (value != IEXA_SLOT_ORDER_LEFT_TO_RIGHT && value != IEXA_SLOT_ORDER_RIGHT_TO_LEFT) return fail(IEXA_ERR_INVALID, "unknown slot-order policy");
+      if (value != IEXA_SLOT_ORDER_LEFT_TO_RIGHT && value != IEXA_SLOT_ORDER_RIGHT_TO_LEFT && value != IEXA_SLOT_ORDER_JAC_ROW_SORTED) return fail(IEXA_ERR_INVALID, "unknown slot-order policy");
       p->plan.opt_slot_order = (int)value;
       return IEXA_OK;
     case IEXA_OPT_STRICT_IEEE:
@@ -282,6 +282,31 @@ int32_t iexa_jac_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_byt
 }
 int32_t iexa_hess_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_bytes, int32_t memspace, void *stream) {
   ENGINE_CALL(structure(1, rows, cols, idx_bytes, memspace, stream, err))
+}
+int32_t iexa_jac_is_csr(const iexa_plan *p, int32_t *is_csr_out) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (!is_csr_out) return fail(IEXA_ERR_INVALID, "null output");
+  if (!p->plan.finalized) return fail(IEXA_ERR_STATE, "plan not finalized");
+  *is_csr_out = p->plan.jac_is_csr() ? 1 : 0;
+  return IEXA_OK;
+  GUARD_END
+}
+int32_t iexa_jac_csr_rowptr(iexa_plan *p, void *rowptr, int32_t idx_bytes, int32_t memspace, void *stream) {
+  if (p && p->plan.finalized && memspace == IEXA_MEM_HOST && rowptr && (idx_bytes == 4 || idx_bytes == 8)) {
+    // pure structure into a host buffer: answered from the plan (also on a build without a device)
+    GUARD_BEGIN
+    if (!p->plan.jac_is_csr()) return fail(IEXA_ERR_STATE, "the Jacobian COO order is not CSR (needs IEXA_SLOT_ORDER_JAC_ROW_SORTED and a static column order in every generator)");
+    const std::vector<int64_t> rp = p->plan.jac_rowptr();
+    if (idx_bytes == 8) std::memcpy(rowptr, rp.data(), rp.size() * 8);
+    else {
+      if (rp.back() > INT32_MAX) return fail(IEXA_ERR_INVALID, "nnzj does not fit Int32 row pointers");
+      for (size_t i = 0; i < rp.size(); ++i) static_cast<int32_t *>(rowptr)[i] = (int32_t)rp[i];
+    }
+    return IEXA_OK;
+    GUARD_END
+  }
+  ENGINE_CALL(jac_rowptr(rowptr, idx_bytes, memspace, stream, err))
 }
 int32_t iexa_coo_locality(iexa_plan *p, int32_t which, int32_t *keys, int32_t memspace, void *stream) {
   if (which != 0 && which != 1) return fail(IEXA_ERR_INVALID, "which must be 0 (Jacobian) or 1 (Hessian)");

@@ -793,6 +793,22 @@ class CudaEngine : public Engine {
   // Page-locking is EXPLICIT (iexa_host_register): the caller knows the lifetime of its vectors.  (Pinning
   // behind the caller's back is unsafe: freed-and-remapped host memory would keep a stale registration.)
  public:
+  int jac_rowptr(void *rowptr, int idx_bytes, int memspace, void *stream, std::string &err) override {
+    CK(cudaSetDevice(device_));
+    if (!rowptr || (idx_bytes != 4 && idx_bytes != 8)) { err = "rowptr: null buffer or idx_bytes not 4/8"; return IEXA_ERR_INVALID; }
+    if (!plan_.jac_is_csr()) { err = "the Jacobian COO order is not CSR (needs IEXA_SLOT_ORDER_JAC_ROW_SORTED and a static column order in every generator)"; return IEXA_ERR_STATE; }
+    if (idx_bytes == 4 && plan_.loc_nnzj > INT32_MAX) { err = "nnzj does not fit Int32 row pointers"; return IEXA_ERR_INVALID; }
+    const std::vector<int64_t> rp = plan_.jac_rowptr();
+    const size_t n = rp.size();
+    std::vector<int32_t> rp32;
+    const void *src = rp.data();
+    if (idx_bytes == 4) { rp32.assign(rp.begin(), rp.end()); src = rp32.data(); }
+    if (memspace == IEXA_MEM_HOST) { std::memcpy(rowptr, src, n * (size_t)idx_bytes); return IEXA_OK; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(rowptr, src, n * (size_t)idx_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // the staging vectors die with this call
+    return IEXA_OK;
+  }
   int get_column(int32_t col, double *out_host, std::string &err) override {
     CK(cudaSetDevice(device_));
     if (col < 0 || col >= (int32_t)col_dev_ptr_.size() || !col_dev_ptr_[col] || plan_.columns[col].is_int) { err = "column is not resident on the device"; return IEXA_ERR_INVALID; }

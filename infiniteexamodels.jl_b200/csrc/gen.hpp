@@ -53,6 +53,8 @@ struct GenCompiled {
   int32_t o1step = 0, o2step = 0;
   int32_t n_occ1 = 0, n_occ2 = 0; // occurrences before compression (reporting)
   bool is_null = false;           // constant-only generator (ExaModels.Null, transform.jl:393)
+  std::vector<int32_t> jac_perm;  // IEXA_SLOT_ORDER_JAC_ROW_SORTED: applied permutation of the first-order slots (empty: policy order kept)
+  bool jac_row_sorted = false;    // the slots of every row are in strictly increasing column order
   // programs
   Program val, d1, d2;
   std::vector<uint8_t> x_slots_val, x_slots_d1, x_slots_d2; // which index slots each program LOADX-es
@@ -133,7 +135,22 @@ class GenCompiler {
   void differentiate() {
     build_values();
     first_order();
+    if (jac_perm) apply_jac_perm(*jac_perm);
     second_order();
+  }
+  // IEXA_SLOT_ORDER_JAC_ROW_SORTED: first-order slot c of the policy order becomes slot position p with perm[p] = c (the
+  // slots of a row sorted by column index — computed by Plan::jac_row_sort, which knows the iterator's columns)
+  const std::vector<int32_t> *jac_perm = nullptr;
+  const SlotCtx &ctx() const { return ctx_; }
+  void apply_jac_perm(const std::vector<int32_t> &perm) {
+    if (perm.size() != g.jac_slot.size()) return;
+    std::vector<int> s1(perm.size());
+    std::vector<int32_t> js(perm.size());
+    for (size_t p = 0; p < perm.size(); ++p) { s1[p] = slot1_[perm[p]]; js[p] = g.jac_slot[perm[p]]; }
+    slot1_.swap(s1);
+    g.jac_slot.swap(js);
+    slot1_of_.clear();
+    for (size_t p = 0; p < g.jac_slot.size(); ++p) slot1_of_[g.jac_slot[p]] = (int32_t)p;
   }
   int val_root() const { return val_[n_ - 1]; }
   const std::vector<int> &slot1() const { return slot1_; }

@@ -352,12 +352,23 @@ struct Plan {
     const Iterator &it = itrs[itr];
     GenCompiler gc(nodes, n, idx, n_idx, (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size());
     gc.is_obj_ = is_obj;
-    gc.set_options(opt_slot_order, opt_strict);
+    gc.set_options(opt_slot_order == 2 ? 0 : opt_slot_order, opt_strict);
+    std::vector<int32_t> perm;
+    bool sorted = false;
+    if (opt_slot_order == 2 && !is_obj) {
+      // a dry symbolic pass gives the policy-order slots; their static column order (if there is one) becomes the slot order
+      GenCompiler probe(nodes, n, idx, n_idx, (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size());
+      probe.set_options(0, opt_strict);
+      probe.differentiate();
+      sorted = jac_row_sort(it, probe.ctx(), probe.g.jac_slot, perm);
+      if (sorted) gc.jac_perm = &perm;
+    }
     gc.compile();
     Generator g;
     g.itr = itr;
     g.K = it.K;
     g.c = std::move(gc.g);
+    if (sorted) { g.c.jac_perm = perm; g.c.jac_row_sorted = true; }
     return g;
   }
 
@@ -441,6 +452,7 @@ struct Plan {
     for (int32_t c : g.c.int_cols) put(c);
     for (int32_t c : g.c.fp_cols) put(c);
     for (int32_t s : g.c.jac_slot) put(s);
+    for (int32_t s : g.c.jac_perm) put(s);
     for (auto &pr : g.c.hess_slot) { put(pr.first); put(pr.second); }
     return k;
   }
@@ -527,7 +539,8 @@ struct Plan {
             GenCompiler gc(gj.c.tape.data(), (int32_t)gj.c.tape.size(), gj.c.raw_idx.data(), (int32_t)gj.c.raw_idx.size(),
                            (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size(), G.ctx, dag, (int)j);
             gc.cpar_of_node = &cpar;
-            gc.set_options(opt_slot_order, opt_strict);
+            gc.set_options(opt_slot_order == 2 ? 0 : opt_slot_order, opt_strict);
+            if (!gj.c.jac_perm.empty()) gc.jac_perm = &gj.c.jac_perm;
             gc.differentiate();
             // a parameter that happens to be 0/1 in instance 0 must not have been folded: slot counts must match
             if ((int)gc.slot1().size() != gj.c.o1step || (int)gc.slot2().size() != gj.c.o2step)
@@ -593,7 +606,8 @@ struct Plan {
         int mpos = (int)G.members.size();
         GenCompiler gc(g.c.tape.data(), (int32_t)g.c.tape.size(), g.c.raw_idx.data(), (int32_t)g.c.raw_idx.size(),
                        (int32_t)it.int_cols.size(), (int32_t)it.fp_cols.size(), G.ctx, *dags[li], mpos);
-        gc.set_options(opt_slot_order, opt_strict);
+        gc.set_options(opt_slot_order == 2 ? 0 : opt_slot_order, opt_strict);
+        if (!g.c.jac_perm.empty()) gc.jac_perm = &g.c.jac_perm;
         gc.differentiate();
         G.members.push_back((int32_t)gi);
         G.jac_slot.push_back(gc.g.jac_slot);
@@ -804,6 +818,53 @@ struct Plan {
       else m.push_back(r);
     }
     return m;
+  }
+
+  // IEXA_SLOT_ORDER_JAC_ROW_SORTED.  perm[p] = policy-order slot that comes p-th when the first-order slots of a row are sorted by
+  // column index — provided that order is STATIC (the same for every support k in [0, K)) and strict (no two slots share a
+  // column at any k).  Pairs of slots with identical term structure differ by a constant; every other pair is checked over
+  // all supports.  Then rows are contiguous and column-sorted in the COO array: it IS the CSR value array, with
+  // rowptr[o0 + k] = o1 + o1step*k — the COO->CSR pass of the Jacobian disappears (iexa_jac_rowptr).
+  bool jac_row_sort(const Iterator &it, const SlotCtx &ctx, const std::vector<int32_t> &jac_slot, std::vector<int32_t> &perm) const {
+    const size_t n = jac_slot.size();
+    perm.resize(n);
+    for (size_t i = 0; i < n; ++i) perm[i] = (int32_t)i;
+    if (n <= 1) return true;
+    if (it.K <= 0) return true;
+    auto col_at = [&](int32_t slot, int64_t k) {
+      const ColRef &r = it.int_cols[ctx.int_cols[slot]];
+      return columns[r.col].ival((k / r.div) % r.mod);
+    };
+    auto idx_at = [&](const IndexExpr &e, int64_t k) {
+      int64_t v = e.base;
+      for (auto &t : e.terms) v += t.second * col_at(t.first, k);
+      return v;
+    };
+    std::vector<int64_t> key0(n);
+    for (size_t i = 0; i < n; ++i) key0[i] = idx_at(ctx.uidx[jac_slot[i]], 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return key0[a] < key0[b]; });
+    for (size_t p = 0; p + 1 < n; ++p) {
+      const IndexExpr &ea = ctx.uidx[jac_slot[perm[p]]], &eb = ctx.uidx[jac_slot[perm[p + 1]]];
+      if (key0[perm[p]] >= key0[perm[p + 1]]) return false;      // duplicate column at k = 0
+      if (ea.terms == eb.terms) continue;                         // constant difference: static
+      for (int64_t k = 1; k < it.K; ++k)                          // neighbours in the sorted order stay strictly ordered
+        if (idx_at(ea, k) >= idx_at(eb, k)) return false;
+    }
+    return true;
+  }
+  // every constraint generator's rows are column-sorted (policy IEXA_SLOT_ORDER_JAC_ROW_SORTED and a static order exists)
+  bool jac_is_csr() const {
+    for (const Generator &g : cons) if (g.c.o1step > 1 && !g.c.jac_row_sorted) return false;
+    return opt_slot_order == 2;
+  }
+
+  // 0-based row pointers of this rank's rows: the rows of a generator are o1step slots apart (structure, built once per model)
+  std::vector<int64_t> jac_rowptr() const {
+    std::vector<int64_t> rp((size_t)loc_ncon + 1);
+    for (const Generator &g : cons)
+      for (int64_t k = g.k0; k < g.k1; ++k) rp[g.l0 + (k - g.k0)] = g.l1 + (int64_t)g.c.o1step * (k - g.k0);
+    rp[(size_t)loc_ncon] = loc_nnzj;
+    return rp;
   }
 
   // every x / theta index a tape can produce must stay inside [1, nvar] / [1, npar]: the kernels address

@@ -235,6 +235,21 @@ def jac_structure_(m: ExaModel, rows, cols):
     return rows, cols
 
 
+def jac_is_csr(m: ExaModel) -> bool:
+    """The jac_coord! array is already a CSR value array (slot_order=2, iexa.h IEXA_SLOT_ORDER_JAC_ROW_SORTED)."""
+    out = C.c_int32(0)
+    _lib.check(m.L, m.L.iexa_jac_is_csr(m.h, C.byref(out)))
+    return bool(out.value)
+
+
+def jac_csr_rowptr_(m: ExaModel, rowptr):
+    """0-based CSR row pointers (loc_ncon + 1 entries) of the row-sorted Jacobian layout; the column indices are jac_structure's cols."""
+    b = m._buf(rowptr, m.loc_ncon + 1)
+    ms, st = m._pair(b)
+    _lib.check(m.L, m.L.iexa_jac_csr_rowptr(m.h, b[0], _idx_bytes(rowptr), ms, st))
+    return rowptr
+
+
 def hess_structure_(m: ExaModel, rows, cols):
     br, bc = m._buf(rows, m.loc_nnzh), m._buf(cols, m.loc_nnzh)
     ms, st = m._pair(br, bc)

@@ -388,6 +388,22 @@ mutable struct CsrMap
     nnz::Int64
 end
 
+"""
+`jac_is_csr(m)`: under `slot_order = 2` (IEXA_SLOT_ORDER_JAC_ROW_SORTED) the array `jac_coord!` writes is already a CSR value
+array; `jac_csr_rowptr!(m, rowptr)` fills the `ncon + 1` zero-based row pointers and `jac_structure!`'s cols are the column
+indices, so a KKT assembly needs no COO->CSR pass for the Jacobian.
+"""
+function jac_is_csr(m::B200ExaModel)
+    out = Ref{Int32}(0)
+    check(ccall((:iexa_jac_is_csr, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}), m.plan.h, out))
+    return out[] == 1
+end
+function jac_csr_rowptr!(m::B200ExaModel, rowptr::AbstractVector{T}) where {T<:Union{Int32,Int64}}
+    GC.@preserve rowptr check(ccall((:iexa_jac_csr_rowptr, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}),
+                                    m.plan.h, _ptr(rowptr), sizeof(T), _ms(rowptr), _st(rowptr)))
+    return rowptr
+end
+
 "locality keys of the Jacobian (0) / Hessian (1) COO slots, for `CsrMap(...; keys)` of patterns with duplicates"
 function coo_locality!(m::B200ExaModel, which::Integer, keys::AbstractVector{Int32})
     GC.@preserve keys check(ccall((:iexa_coo_locality, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32, Ptr{Cvoid}),

@@ -73,6 +73,8 @@ typedef struct {
   int64_t nvar, ncon, nnzj, nnzh, npar;
   double *theta;
   int order;                /* policy given to generators added from now on */
+  int row_sorted;           /* policy 2: constraint generators' first-order slots column-sorted when a static order exists */
+  int all_sorted;           /* every constraint generator added under policy 2 had such an order */
 } omodel;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -111,7 +113,8 @@ int orc_max_threads(void) {
 
 omodel *orc_create(void) { return (omodel *)calloc(1, sizeof(omodel)); }
 /* slot-order policy of the generators added AFTER this call: 0 = inner1 then inner2, 1 = inner2 then inner1 */
-void orc_set_slot_order(omodel *m, int order) { m->order = order ? 1 : 0; }
+void orc_set_slot_order(omodel *m, int order) { m->order = order == 1; m->row_sorted = order == 2; }
+int orc_jac_is_csr(const omodel *m) { return m->row_sorted && m->all_sorted == 0; }
 /* first / second child of a binary node in the policy's visiting order */
 #define KID1(g, t) ((g)->order ? (g)->c2[t] : (g)->c1[t])
 #define KID2(g, t) ((g)->order ? (g)->c1[t] : (g)->c2[t])
@@ -258,6 +261,29 @@ static int add_gen(omodel *m, int is_obj, const onode *nodes, int n_nodes, const
   g->o1step = compress(&l1, &g->comp1, &g->slot1_idx, &dummy); free(dummy);
   g->o2step = compress(&l2, &g->comp2, &g->slot2_i, &g->slot2_j);
   free(l1.a); free(l1.b); free(l2.a); free(l2.b);
+  if (m->row_sorted && !is_obj && g->o1step > 1) {
+    /* policy 2, by brute force: order the slots by their column at k = 0 and keep that order only if it is strictly
+     * increasing at EVERY support (then each Jacobian row is contiguous and column-sorted: COO array == CSR array) */
+    int ns = g->o1step, ok = 1;
+    int *pos = (int *)malloc(sizeof(int) * (size_t)ns);          /* pos[p] = old slot at sorted position p */
+    for (int s = 0; s < ns; ++s) pos[s] = s;
+    for (int a = 1; a < ns; ++a) {                                 /* insertion sort, stable */
+      int v = pos[a], b = a;
+      while (b > 0 && idx_val(g, g->slot1_idx[pos[b - 1]], 0) > idx_val(g, g->slot1_idx[v], 0)) { pos[b] = pos[b - 1]; --b; }
+      pos[b] = v;
+    }
+    for (int64_t k = 0; k < K && ok; ++k)
+      for (int p = 0; p + 1 < ns; ++p)
+        if (idx_val(g, g->slot1_idx[pos[p]], k) >= idx_val(g, g->slot1_idx[pos[p + 1]], k)) { ok = 0; break; }
+    if (ok) {
+      int *inv = (int *)malloc(sizeof(int) * (size_t)ns), *si = (int *)malloc(sizeof(int) * (size_t)(ns + 1));
+      for (int p = 0; p < ns; ++p) { inv[pos[p]] = p; si[p] = g->slot1_idx[pos[p]]; }
+      for (int i = 0; i < g->nocc1; ++i) g->comp1[i] = inv[g->comp1[i]];
+      memcpy(g->slot1_idx, si, sizeof(int) * (size_t)ns);
+      free(inv); free(si);
+    } else m->all_sorted = -1;
+    free(pos);
+  }
   m->ngen++;
   return m->ngen - 1;
 }

@@ -42,6 +42,7 @@ def lib():
         L.orc_add_gen_borrow.argtypes = L.orc_add_gen.argtypes
         L.orc_add_gen_borrow.restype = i32
         L.orc_set_slot_order.argtypes = [vp, i32]
+        L.orc_jac_is_csr.argtypes = [vp]; L.orc_jac_is_csr.restype = i32
         L.orc_finalize.argtypes = [vp]
         for f in ("orc_ncon", "orc_nnzj", "orc_nnzh"):
             getattr(L, f).argtypes = [vp]

@@ -38,7 +38,7 @@ def _hc(L, m, fn, which, n, x, y=None, sig=1.0):
     return out[:n]
 
 
-@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("order", [0, 1, 2])
 @pytest.mark.parametrize("name", list(CASES))
 def test_product_and_oracle_agree_under_each_policy(name, order, hostcheck_lib):
     from oracle.oracle import OracleModel
@@ -68,17 +68,76 @@ def test_policies_permute_slots_but_not_the_matrices(name):
     x = np.where(np.isfinite(x), x, 0.0)
     mats = []
     structs = []
-    for order in (0, 1):
+    for order in (0, 1, 2):
         om = OracleModel(core, slot_order=order)
         jr, jc = om.jac_structure(); hr, hc = om.hess_structure()
         J = sp.coo_matrix((om.jac_coord(x), (jr - 1, jc - 1)), shape=(om.ncon, om.nvar)).tocsr()
         H = sp.coo_matrix((om.hess_coord(x, y, 0.7), (hr - 1, hc - 1)), shape=(om.nvar, om.nvar)).tocsr()
         mats.append((J, H)); structs.append((jr, jc, hr, hc))
-    for a, b in zip(mats[0], mats[1]):
-        d = abs(a - b)
-        assert d.max() <= 1e-12 * max(1.0, abs(a).max()) if d.nnz else True
+    for other in mats[1:]:
+        for a, b in zip(mats[0], other):
+            d = abs(a - b)
+            assert d.max() <= 1e-12 * max(1.0, abs(a).max()) if d.nnz else True
     if name in ("quadrotor_oc", "opf_case3"):  # trees with binary nodes over several variables: the ORDER really differs
         assert any(not np.array_equal(u, v) for u, v in zip(structs[0], structs[1]))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_row_sorted_policy_makes_the_coo_array_a_csr_array(name, hostcheck_lib):
+    """IEXA_SLOT_ORDER_JAC_ROW_SORTED: rows contiguous and columns strictly increasing inside each row — in the oracle (brute
+    force over every support) and in the plan compiler (structural analysis) alike; the row pointers the C ABI hands out
+    plus jac_structure's columns plus the UNTOUCHED jac_coord! values are the CSR matrix scipy builds from the COO triplets."""
+    from oracle.oracle import OracleModel
+    import scipy.sparse as sp
+    L = hostcheck_lib
+    core = CASES[name]()
+    om = OracleModel(core, slot_order=2)
+    assert om.L.orc_jac_is_csr(om.h) == 1
+    m = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L, slot_order=2)
+    assert ex.jac_is_csr(m)
+    jr, jc = om.jac_structure()
+    assert (np.diff(jr) >= 0).all()
+    same_row = np.diff(jr) == 0
+    assert (np.diff(jc)[same_row] > 0).all()
+    rp = np.zeros(om.ncon + 1, dtype=np.int64)
+    ex.jac_csr_rowptr_(m, rp)
+    rp32 = np.zeros(om.ncon + 1, dtype=np.int32)
+    ex.jac_csr_rowptr_(m, rp32)
+    assert (rp32 == rp).all()
+    x, _ = eval_point(core)
+    x = np.where(np.isfinite(x), x, 0.0)
+    vals = om.jac_coord(x)
+    ref = sp.coo_matrix((vals, (jr - 1, jc - 1)), shape=(om.ncon, om.nvar)).tocsr()
+    ref.sort_indices()
+    mine = sp.csr_matrix((vals, (jc - 1).astype(np.int64), rp), shape=(om.ncon, om.nvar))
+    assert mine.has_sorted_indices or True
+    assert (mine.indptr == ref.indptr).all() and (mine.indices == ref.indices).all()
+    assert np.array_equal(mine.data, ref.data)      # nothing summed, nothing moved: bit-identical
+    # the default policy is NOT CSR for the models whose trees meet the variables out of column order
+    m0 = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L)
+    assert not ex.jac_is_csr(m0)
+    with pytest.raises(Exception):
+        ex.jac_csr_rowptr_(m0, rp)
+
+
+def test_row_sorted_policy_falls_back_per_generator_when_no_static_order_exists(hostcheck_lib):
+    """A generator whose two variables swap their column order along the iterator keeps the default slot order; the model then
+    reports 'not CSR' instead of a wrong pattern (oracle and plan compiler agree on that too)."""
+    from oracle.oracle import OracleModel
+    L = hostcheck_lib
+    c = ex.ExaCore()
+    ds = ex.DataSource()
+    v = c.add_var(6)
+    it = ex.Itr(3, {"a": np.array([1, 2, 5]), "b": np.array([4, 3, 2])})    # a < b, a < b, a > b
+    c.add_con(v[ds.a] * 2.0 + v[ds.b] * v[ds.b], it, 0.0, 0.0)
+    c.add_obj(v[1] * v[1], ex.Itr.empty())
+    om = OracleModel(c, slot_order=2)
+    m = ex.ExaModel(c, flags=ex.lib.IEXA_F_NO_DEVICE, library=L, slot_order=2)
+    assert om.L.orc_jac_is_csr(om.h) == 0 and not ex.jac_is_csr(m)
+    jr, jc = om.jac_structure()
+    r = np.zeros(len(jr), dtype=np.int64); cc = np.zeros_like(r)
+    assert L.hostcheck_structure(m.h, 0, r.ctypes.data, cc.ctypes.data) == 0
+    assert (r == jr).all() and (cc == jc).all()
 
 
 def test_options_are_frozen_once_a_generator_exists(hostcheck_lib):
