@@ -71,6 +71,9 @@ for nm, fn, w in (("cons", bind(m, "cons", x, c), 2), ("jac", bind(m, "jac_coord
     if w >= 2:
         tot += ms
     print(f"{nm}: {ms:.4f} ms  {B[w]/ms/1e6:.1f} GB/s  frac_of_6552={B[w]/ms/1e6/6552:.3f}")
+_fc, _fj, _fh = bind(m, "cons", x, c), bind(m, "jac_coord", x, jv), bind(m, "hess_coord", x, hv, y, 1.0)
+ms3 = timeit(lambda: (_fc(), _fj(), _fh()))
+print(f"step (cons, jac, hess back to back): {ms3:.4f} ms -> {1e3/ms3:.0f} evals/s (sum of the three timed alone: {tot:.4f} ms)")
 if os.environ.get("IEXA_EVAL3", "1") != "0":   # the fused cons + jac + hess kernel (compiled on first use)
     f3 = bind(m, "eval3", x, (c, jv, hv), y, 1.0)
     tp = time.time(); f3(); torch.cuda.synchronize(); tb3 = time.time() - tp
