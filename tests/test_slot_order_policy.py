@@ -120,6 +120,41 @@ def test_row_sorted_policy_makes_the_coo_array_a_csr_array(name, hostcheck_lib):
         ex.jac_csr_rowptr_(m0, rp)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", ["quadrotor_oc", "pandemic", "farmer"])
+def test_row_sorted_row_pointers_of_a_shard(name, world, hostcheck_lib):
+    """world > 1: a rank's row pointers index ITS slice of the value array; mapped back through iexa_segments they are the
+    global row pointers of the rows the rank owns, and the ranks' rows tile the model."""
+    L = hostcheck_lib
+    core = CASES[name]()
+    g = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L, slot_order=2)
+    rp_g = ex.jac_csr_rowptr_(g, np.zeros(g.meta.ncon + 1, dtype=np.int64))
+    seen_rows = np.zeros(g.meta.ncon, dtype=np.int64)
+    for r in range(world):
+        m = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L, slot_order=2, rank=r, world=world)
+        assert ex.jac_is_csr(m)
+        rp = ex.jac_csr_rowptr_(m, np.zeros(m.loc_ncon + 1, dtype=np.int64))
+        assert rp[0] == 0 and rp[-1] == m.loc_nnzj and (np.diff(rp) >= 0).all()
+
+        def segs(which):
+            n = L.iexa_segments(m.h, which, None, 0)
+            sg = (ex.lib.Segment * max(n, 1))()
+            L.iexa_segments(m.h, which, sg, n)
+            return [(q.global_start, q.local_start, q.length) for q in sg[:n]]
+        # local slot -> global slot
+        l2g = np.full(max(m.loc_nnzj, 1), -1, dtype=np.int64)
+        for gs, ls, ln in segs(1):
+            l2g[ls:ls + ln] = np.arange(gs, gs + ln)
+        for gs, ls, ln in segs(0):          # rows
+            seen_rows[gs:gs + ln] += 1
+            for i in range(ln):
+                a, b = rp[ls + i], rp[ls + i + 1]
+                assert b - a == rp_g[gs + i + 1] - rp_g[gs + i]
+                if b > a:
+                    assert l2g[a] == rp_g[gs + i] and l2g[b - 1] == rp_g[gs + i + 1] - 1
+    assert (seen_rows == 1).all()
+
+
 def test_row_sorted_policy_falls_back_per_generator_when_no_static_order_exists(hostcheck_lib):
     """A generator whose two variables swap their column order along the iterator keeps the default slot order; the model then
     reports 'not CSR' instead of a wrong pattern (oracle and plan compiler agree on that too)."""
