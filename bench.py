@@ -729,6 +729,25 @@ def main():
                              "sample": "same model, OpenMP over supports, best of 3 full evals"}}
         del om
 
+    # ---- device memory per rank (inputs sharded, not just outputs)
+    db = ex.device_bytes(m)
+    nxr = m.L.iexa_x_ranges(m.h, None, 0)
+    xsegs = (ex.lib.Segment * max(nxr, 1))()
+    m.L.iexa_x_ranges(m.h, xsegs, nxr)
+    xr = 8 * sum(sg.length for sg in xsegs[:nxr]) if world > 1 else 8 * m.meta.nvar
+    caller_local = 8 * (m.loc_ncon * 2 + m.loc_nnzj + m.loc_nnzh)           # y, c, Jacobian values, Hessian values of this rank
+    mine = [db["columns"] + db["theta"] + db["programs_tables"], caller_local, xr, 8 * m.meta.nvar]
+    mx = [float(v) for v in ctx.max_over_ranks([float(v) for v in mine])]
+    whole = 8 * (core.ncon * 2 + bytes_meta["nnzj"] + bytes_meta["nnzh"]) + db["columns_unsharded"] + db["theta_unsharded"]
+    device_memory = {
+        "engine_bytes_per_rank_max": int(mx[0]), "engine_columns": db["columns"], "engine_columns_unsharded": db["columns_unsharded"],
+        "engine_theta": db["theta"], "engine_theta_unsharded": db["theta_unsharded"], "engine_programs_tables": db["programs_tables"],
+        "host_path_staging_rank0": db["host_path_staging"],
+        "caller_y_c_jac_hess_bytes_per_rank_max": int(mx[1]), "x_bytes_touched_per_rank_max": int(mx[2]), "x_bytes_addressed": int(mx[3]),
+        "per_rank_over_unsharded": (mx[0] + mx[1] + mx[2]) / float(whole + 8 * m.meta.nvar),
+        "note": "engine = iterator columns (the slice this rank's supports visit) + theta (full-length virtual range, only this rank's 2 MB granules "
+                "backed) + programs / tables; caller = y, c and the value arrays of the rank's rows; x is addressed full-length by contract "
+                "(global indices) — a rank touches x_bytes_touched of it (iexa_x_ranges); per_rank_over_unsharded counts the touched part"}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -740,7 +759,7 @@ def main():
                                "note": "compiled images are cached in memory and on disk keyed by the generated source (IEXA_CACHE_DIR)"},
                    "warmup_steps_run": int(nwarm), "numa_node_of_rank0": ctx.numa},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval3": eval3, "products": products, "iteration": iteration,
-        "x_distribution": xdist, "workloads": workloads,
+        "x_distribution": xdist, "workloads": workloads, "device_memory": device_memory,
         "gpu_launches": int(args.steps * launches_step),
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }

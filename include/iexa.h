@@ -284,6 +284,15 @@ typedef struct iexa_segment {
 } iexa_segment;
 /* which: 0 rows, 1 jac slots, 2 hess slots.  Returns the count; fills up to cap.       */
 int64_t iexa_segments(const iexa_plan *p, int32_t which, iexa_segment *out, int64_t cap);
+/* Device memory the ENGINE holds for this plan on this rank, in bytes:
+ *   out6[0] iterator columns resident here        out6[1] the same columns of the unsharded model
+ *   out6[2] theta resident here                   out6[3] 8 * npar
+ *   out6[4] programs, descriptors, work tables    out6[5] staging buffers of the host-memory path (grown on first use)
+ * world > 1: a rank keeps the slice of every column that its own supports visit, and theta — addressed by global parameter
+ * indices inside the kernels — is a full-length virtual address range in which only the granules (2 MB) covering the rank's
+ * slices are backed by memory (CUDA virtual-memory API; IEXA_NO_VMM=1 / IEXA_NO_COLUMN_SLICES=1 keep everything whole).
+ * x, y and the outputs belong to the caller: x is full-length by contract (global indices), of which a rank touches iexa_x_ranges. */
+int32_t iexa_device_bytes(const iexa_plan *p, int64_t *out6);
 /* variable indices (1-based) whose gradient entries receive contributions from more than
  * one rank (finite / shared variables and shard-boundary halos): the slice that must be
  * all-reduced after iexa_grad.  Returns the count; fills up to cap.                    */

@@ -283,6 +283,15 @@ int32_t iexa_jac_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_byt
 int32_t iexa_hess_structure(iexa_plan *p, void *rows, void *cols, int32_t idx_bytes, int32_t memspace, void *stream) {
   ENGINE_CALL(structure(1, rows, cols, idx_bytes, memspace, stream, err))
 }
+int32_t iexa_device_bytes(const iexa_plan *p, int64_t *out6) {
+  GUARD_BEGIN
+  NEED_PLAN(p);
+  if (!out6) return fail(IEXA_ERR_INVALID, "null output");
+  if (!p->plan.finalized || !p->engine) return fail(IEXA_ERR_STATE, "no device engine");
+  p->engine->device_bytes(out6);
+  return IEXA_OK;
+  GUARD_END
+}
 int32_t iexa_jac_is_csr(const iexa_plan *p, int32_t *is_csr_out) {
   GUARD_BEGIN
   NEED_PLAN(p);

@@ -7,7 +7,9 @@
 // every thread owns one support point k and runs the generator's register program.
 // Outputs go straight to their precomputed slots  out[l + ostep*(k-k0) + c]  — every slot is
 // rewritten on every call, so no fill!(vals, 0) pass is needed.
+#include <cuda.h>          // types of the virtual-memory API only: the entry points are taken from libcuda.so.1 with dlsym
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -204,9 +206,10 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__r
 __device__ __forceinline__ double gen_pub(long long i, long long n, double a, double b, double step) {
   return i == n - 1 ? b : __dadd_rn(a, __dmul_rn((double)i, step));
 }
-__global__ void __launch_bounds__(256) gen_column_kernel(int kind, long long K, long long n, double a, double b, double step,
+// positions [j0, j1) of a K-long column (world > 1: the slice this rank reads); src / out are addressed by the GLOBAL position
+__global__ void __launch_bounds__(256) gen_column_kernel(int kind, long long K, long long j0, long long j1, long long n, double a, double b, double step,
                                                          const double *__restrict__ src, double *__restrict__ out) {
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < K; j += (long long)gridDim.x * blockDim.x) {
+  for (long long j = j0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < j1; j += (long long)gridDim.x * blockDim.x) {
     double v = 0.0;
     switch (kind) {
       case 1: v = n == 1 ? a : gen_pub(j, n, a, b, step); break;
@@ -297,6 +300,117 @@ struct DevBuf {
     return e;
   }
   template <typename T> T *as() { return (T *)p; }
+};
+
+// A full-length-ADDRESSABLE device vector of which only some ranges are backed by memory (world > 1: theta is addressed by
+// global parameter indices inside the kernels, but a rank reads only the slices of its own supports).  The CUDA virtual-memory
+// API reserves the whole address range and maps physical granules (2 MB) over the ranges this rank reads; the kernels keep
+// their global indices.  Small vectors, dense read sets, or a driver without the API: one ordinary allocation.
+struct SparseDev {
+  struct Vmm {
+    CUresult (*GetGran)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*Reserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*Create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*AddrFree)(CUdeviceptr, size_t) = nullptr;
+    bool ok = false;
+    Vmm() {
+      void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+      if (!h) return;
+      *(void **)&GetGran = dlsym(h, "cuMemGetAllocationGranularity");
+      *(void **)&Reserve = dlsym(h, "cuMemAddressReserve");
+      *(void **)&Create = dlsym(h, "cuMemCreate");
+      *(void **)&Map = dlsym(h, "cuMemMap");
+      *(void **)&SetAccess = dlsym(h, "cuMemSetAccess");
+      *(void **)&Unmap = dlsym(h, "cuMemUnmap");
+      *(void **)&Release = dlsym(h, "cuMemRelease");
+      *(void **)&AddrFree = dlsym(h, "cuMemAddressFree");
+      ok = GetGran && Reserve && Create && Map && SetAccess && Unmap && Release && AddrFree;
+    }
+  };
+  static Vmm &vmm() { static Vmm v; return v; }
+
+  DevBuf dense;
+  CUdeviceptr va = 0;
+  size_t va_size = 0, full = 0, resident = 0;
+  std::vector<std::pair<size_t, size_t>> chunks;   // mapped byte ranges [lo, hi) of the reservation, sorted, disjoint
+  std::vector<CUmemGenericAllocationHandle> handles;
+  bool sparse = false;
+
+  void *base() const { return sparse ? (void *)va : dense.p; }
+  void release() {
+    if (sparse) {
+      for (size_t i = 0; i < chunks.size(); ++i) { vmm().Unmap(va + chunks[i].first, chunks[i].second - chunks[i].first); vmm().Release(handles[i]); }
+      if (va) vmm().AddrFree(va, va_size);
+    }
+    chunks.clear(); handles.clear(); va = 0; va_size = 0; sparse = false; resident = 0;
+  }
+  ~SparseDev() { release(); }
+  // ranges: byte ranges [lo, hi) that must be backed, sorted and disjoint
+  cudaError_t alloc(size_t full_bytes, const std::vector<std::pair<size_t, size_t>> &ranges, int device, bool allow_sparse) {
+    release();
+    full = full_bytes;
+    if (allow_sparse && vmm().ok && !getenv("IEXA_NO_VMM")) {
+      CUmemAllocationProp prop{};
+      prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+      prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      prop.location.id = device;
+      size_t G = 0;
+      if (vmm().GetGran(&G, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) == CUDA_SUCCESS && G > 0) {
+        std::vector<std::pair<size_t, size_t>> ch;
+        size_t tot = 0;
+        for (auto &r : ranges) {
+          if (r.second <= r.first) continue;
+          size_t lo = r.first / G * G, hi = (r.second + G - 1) / G * G;
+          if (!ch.empty() && lo <= ch.back().second) ch.back().second = std::max(ch.back().second, hi);
+          else ch.emplace_back(lo, hi);
+        }
+        for (auto &c : ch) tot += c.second - c.first;
+        const size_t vs = (full_bytes + G - 1) / G * G;
+        // worth it only when the vector is large and the rank reads a minority of it
+        if (full_bytes >= 8 * G && tot * 4 <= vs * 3 && !ch.empty()) {
+          CUdeviceptr a = 0;
+          if (vmm().Reserve(&a, vs, G, 0, 0) == CUDA_SUCCESS) {
+            va = a; va_size = vs; sparse = true;
+            CUmemAccessDesc acc{};
+            acc.location = prop.location;
+            acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+            bool good = true;
+            for (auto &c : ch) {
+              CUmemGenericAllocationHandle h;
+              if (vmm().Create(&h, c.second - c.first, &prop, 0) != CUDA_SUCCESS) { good = false; break; }
+              if (vmm().Map(va + c.first, c.second - c.first, 0, h, 0) != CUDA_SUCCESS) { vmm().Release(h); good = false; break; }
+              chunks.push_back(c); handles.push_back(h);
+              if (vmm().SetAccess(va + c.first, c.second - c.first, &acc, 1) != CUDA_SUCCESS) { good = false; break; }
+            }
+            if (good) { resident = tot; return cudaSuccess; }
+            release();   // fall through to the ordinary allocation
+          }
+        }
+      }
+    }
+    cudaError_t e = dense.ensure(full_bytes ? full_bytes : 8);
+    if (e == cudaSuccess) resident = full_bytes;
+    return e;
+  }
+  // host -> device copy of the bytes [off, off + n) of the FULL vector that are resident here (the rest belongs to other ranks)
+  cudaError_t upload(const char *host_full, size_t off, size_t n, cudaStream_t st, bool async) {
+    auto cp = [&](size_t lo, size_t hi) -> cudaError_t {
+      if (hi <= lo) return cudaSuccess;
+      char *d = (char *)base() + lo;
+      return async ? cudaMemcpyAsync(d, host_full + (lo - off), hi - lo, cudaMemcpyHostToDevice, st)
+                   : cudaMemcpy(d, host_full + (lo - off), hi - lo, cudaMemcpyHostToDevice);
+    };
+    if (!sparse) return cp(off, off + n);
+    for (auto &c : chunks) {
+      cudaError_t e = cp(std::max(off, c.first), std::min({off + n, c.second, full}));
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
 };
 
 struct HostArena {
@@ -456,7 +570,7 @@ class CudaEngine : public Engine {
       if ((rc = jac(x, jvals, ms2, stream, err))) return rc;
       return hess(x, y, sigma, hvals, ms2, stream, err);
     }
-    if (!spec_->launch(KS_EVAL3, gtable_[KS_EVAL3].work, x, theta_.as<double>(), y, nullptr, sigma, c, partials_.as<double>(),
+    if (!spec_->launch(KS_EVAL3, gtable_[KS_EVAL3].work, x, theta_ptr(), y, nullptr, sigma, c, partials_.as<double>(),
                        (cudaStream_t)stream, err, jvals, hvals))
       return IEXA_ERR_CUDA;
     return IEXA_OK;
@@ -481,7 +595,7 @@ class CudaEngine : public Engine {
     if (n <= 0) return IEXA_OK;
     if (device_sync) { // iexa_set_par: no stream given — safe against callbacks in flight on ANY stream
       CK(cudaDeviceSynchronize());
-      CK(cudaMemcpy(theta_.as<double>() + off, vals, (size_t)n * 8, cudaMemcpyHostToDevice));
+      CK(theta_.upload((const char *)vals, (size_t)off * 8, (size_t)n * 8, nullptr, false));
       return IEXA_OK;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -494,7 +608,7 @@ class CudaEngine : public Engine {
       par_stage_bytes_ = (size_t)n * 8;
     }
     std::memcpy(par_stage_, vals, (size_t)n * 8);
-    CK(cudaMemcpyAsync(theta_.as<double>() + off, par_stage_, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(theta_.upload((const char *)par_stage_, (size_t)off * 8, (size_t)n * 8, st, true));
     CK(cudaEventRecord(par_stage_event_, st));
     return IEXA_OK;
   }
@@ -527,7 +641,11 @@ class CudaEngine : public Engine {
   Plan &plan_;
   int device_;
   uint32_t flags_;
-  DevBuf leaf_, desc_, gens_, theta_, work_;
+  DevBuf leaf_, desc_, gens_, work_;
+  SparseDev theta_;                                      // full-length addressable; world > 1: only this rank's slices are backed
+  std::vector<std::pair<int64_t, int64_t>> col_range_;   // resident positions [lo, hi) of every column (world > 1: the rank's slice)
+  size_t col_bytes_ = 0, col_bytes_full_ = 0;
+  double *theta_ptr() const { return (double *)theta_.base(); }
   DevBuf zero_ranges_;
   DevBuf partials_, fdev_, stage_x_, stage_y_, stage_v_, stage_out_, stage_a_, stage_b_, scratch_;
   std::vector<std::unique_ptr<DevBuf>> gen_bufs_; // device-generated iterator columns
@@ -555,17 +673,28 @@ class CudaEngine : public Engine {
     std::vector<size_t> col_off(P.columns.size(), (size_t)-1);
     col_dev_ptr_.assign(P.columns.size(), nullptr);
     std::vector<int32_t> gen_order; // generated columns in dependency order
+    // world > 1: a rank keeps the positions [lo, hi) of a column that its own supports visit (Plan::column_read_ranges); the
+    // device pointer is moved back by lo elements so that the kernels keep indexing with the global position
+    col_range_ = P.column_read_ranges();
+    if (P.world <= 1 || getenv("IEXA_NO_COLUMN_SLICES"))
+      for (size_t c = 0; c < P.columns.size(); ++c) col_range_[c] = {0, P.columns[c].K};
+    col_bytes_ = col_bytes_full_ = 0;
+    std::vector<char> col_seen(P.columns.size(), 0);
     std::function<void(int32_t)> need_col = [&](int32_t c) {
-      if (col_off[c] != (size_t)-1 || col_dev_ptr_[c]) return;
+      if (col_seen[c]) return;
+      col_seen[c] = 1;
       const HostColumn &hc = P.columns[c];
-      if (hc.is_int) { if (!hc.affine) col_off[c] = A.add(hc.ivals.data(), hc.ivals.size() * 4); }
-      else if (hc.gen_kind) { // generated on the device: own buffer, nothing uploaded
+      const int64_t lo = col_range_[c].first, n = std::max<int64_t>(col_range_[c].second - col_range_[c].first, 0);
+      if (hc.is_int) {
+        if (!hc.affine) { col_off[c] = A.add(hc.ivals.data() + lo, (size_t)n * 4); col_bytes_ += (size_t)n * 4; col_bytes_full_ += hc.ivals.size() * 4; }
+      } else if (hc.gen_kind) { // generated on the device: own buffer, nothing uploaded
         if (hc.gen_src >= 0) need_col(hc.gen_src);
         gen_bufs_.emplace_back(new DevBuf());
-        if (gen_bufs_.back()->ensure((size_t)(hc.K > 0 ? hc.K : 1) * 8) != cudaSuccess) { cudaGetLastError(); gen_failed_ = true; return; }
-        col_dev_ptr_[c] = gen_bufs_.back()->p;
+        if (gen_bufs_.back()->ensure((size_t)(n > 0 ? n : 1) * 8) != cudaSuccess) { cudaGetLastError(); gen_failed_ = true; return; }
+        col_dev_ptr_[c] = (char *)gen_bufs_.back()->p - (size_t)lo * 8;
+        col_bytes_ += (size_t)n * 8; col_bytes_full_ += (size_t)hc.K * 8;
         gen_order.push_back(c);
-      } else col_off[c] = A.add(hc.fvals.data(), hc.fvals.size() * 8);
+      } else { col_off[c] = A.add(hc.fvals.data() + lo, (size_t)n * 8); col_bytes_ += (size_t)n * 8; col_bytes_full_ += hc.fvals.size() * 8; }
     };
     std::vector<Generator *> all;
     for (auto &g : P.objs) all.push_back(&g);
@@ -599,12 +728,14 @@ class CudaEngine : public Engine {
     CK(cudaMemcpy(leaf_.p, A.bytes.data(), A.bytes.size(), cudaMemcpyHostToDevice));
     char *lb = (char *)leaf_.p;
     for (size_t c = 0; c < P.columns.size(); ++c)
-      if (col_off[c] != (size_t)-1) col_dev_ptr_[c] = lb + col_off[c];
+      if (col_off[c] != (size_t)-1) col_dev_ptr_[c] = lb + col_off[c] - (size_t)col_range_[c].first * (P.columns[c].is_int ? 4 : 8);
     for (int32_t c : gen_order) { // produce the generated columns on the device (a TRAPEZOID column after its source)
       const HostColumn &hc = P.columns[c];
       const double step = hc.gen_n > 1 ? (hc.gen_b - hc.gen_a) / (double)(hc.gen_n - 1) : 0.0;
-      const int nb = (int)std::max<int64_t>(1, std::min<int64_t>((hc.K + 255) / 256, 148 * 8));
-      gen_column_kernel<<<nb, 256>>>(hc.gen_kind, hc.K, hc.gen_n, hc.gen_a, hc.gen_b, step,
+      const int64_t j0 = col_range_[c].first, j1 = col_range_[c].second;
+      if (j1 <= j0) continue;
+      const int nb = (int)std::max<int64_t>(1, std::min<int64_t>((j1 - j0 + 255) / 256, 148 * 8));
+      gen_column_kernel<<<nb, 256>>>(hc.gen_kind, hc.K, j0, j1, hc.gen_n, hc.gen_a, hc.gen_b, step,
                                      hc.gen_src >= 0 ? (const double *)col_dev_ptr_[hc.gen_src] : nullptr, (double *)col_dev_ptr_[c]);
       CK(cudaGetLastError());
     }
@@ -682,8 +813,12 @@ class CudaEngine : public Engine {
     CK(cudaMemcpy(gens_.p, gens_host_.data(), gens_host_.size() * sizeof(GenD), cudaMemcpyHostToDevice));
     gens_dev_ = gens_.as<GenD>();
 
-    CK(theta_.ensure((size_t)(P.npar > 0 ? P.npar : 1) * 8));
-    if (P.npar > 0) CK(cudaMemcpy(theta_.p, P.theta.data(), (size_t)P.npar * 8, cudaMemcpyHostToDevice));
+    {
+      std::vector<std::pair<size_t, size_t>> tr;
+      for (auto &r : P.theta_read_ranges()) tr.emplace_back((size_t)r.first * 8, (size_t)r.second * 8);
+      CK(theta_.alloc((size_t)(P.npar > 0 ? P.npar : 1) * 8, tr, device_, P.world > 1 && P.pfuncs.empty()));
+      if (P.npar > 0) CK(theta_.upload((const char *)P.theta.data(), 0, (size_t)P.npar * 8, nullptr, false));
+    }
 
     // work tables
     const int nobj = (int)P.objs.size(), ncon = (int)P.cons.size();
@@ -726,10 +861,10 @@ class CudaEngine : public Engine {
       CK(cudaMemcpy(wb.p, pw.data(), pw.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
       Table T;
       T.work = wb.as<WorkItem>(); T.nblocks = (int)pw.size(); T.max_nreg = g.c.val.nreg;
-      int rc = launch_interp(T, g.c.val.nreg, PROG_VAL, SINK_DENSE, nullptr, nullptr, nullptr, 1.0, theta_.as<double>(), nullptr, err);
+      int rc = launch_interp(T, g.c.val.nreg, PROG_VAL, SINK_DENSE, nullptr, nullptr, nullptr, 1.0, theta_ptr(), nullptr, err);
       if (rc) return rc;
       CK(cudaDeviceSynchronize());
-      CK(cudaMemcpy(P.theta.data() + g.o0, theta_.as<double>() + g.o0, (size_t)g.K * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(P.theta.data() + g.o0, theta_ptr() + g.o0, (size_t)g.K * 8, cudaMemcpyDeviceToHost));
     }
     return IEXA_OK;
   }
@@ -809,10 +944,20 @@ class CudaEngine : public Engine {
     CK(cudaStreamSynchronize(st));   // the staging vectors die with this call
     return IEXA_OK;
   }
+  void device_bytes(int64_t *out) const override {
+    size_t gen = 0;
+    for (auto &b : gen_bufs_) gen += b->bytes;
+    out[0] = (int64_t)col_bytes_; out[1] = (int64_t)col_bytes_full_;
+    out[2] = (int64_t)(plan_.npar > 0 ? theta_.resident : 0); out[3] = (int64_t)plan_.npar * 8;
+    out[4] = (int64_t)(leaf_.bytes + gen + desc_.bytes + gens_.bytes + work_.bytes + zero_ranges_.bytes + partials_.bytes + fdev_.bytes +
+                       scat_zero_[0].bytes + scat_zero_[1].bytes + gwork_[0].bytes + gwork_[1].bytes + gwork_[2].bytes + scratch_.bytes) - out[0];
+    out[5] = (int64_t)(stage_x_.bytes + stage_y_.bytes + stage_v_.bytes + stage_out_.bytes + stage_a_.bytes + stage_b_.bytes);
+  }
   int get_column(int32_t col, double *out_host, std::string &err) override {
     CK(cudaSetDevice(device_));
     if (col < 0 || col >= (int32_t)col_dev_ptr_.size() || !col_dev_ptr_[col] || plan_.columns[col].is_int) { err = "column is not resident on the device"; return IEXA_ERR_INVALID; }
-    CK(cudaMemcpy(out_host, col_dev_ptr_[col], (size_t)plan_.columns[col].K * 8, cudaMemcpyDeviceToHost));
+    const int64_t lo = col_range_[col].first, hi = col_range_[col].second;   // world > 1: only this rank's slice is resident
+    if (hi > lo) CK(cudaMemcpy(out_host + lo, (const double *)col_dev_ptr_[col] + lo, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost));
     return IEXA_OK;
   }
   int host_register(void *p, size_t bytes, std::string &err) override {
@@ -885,7 +1030,7 @@ class CudaEngine : public Engine {
     const Table &T = table_[cb];
     if (T.nblocks == 0) return IEXA_OK;
     double *part = partials_.as<double>();
-    const double *th = theta_.as<double>();
+    const double *th = theta_ptr();
     if (spec_ && spec_->has(cb)) {
       const Table &GT = gtable_[cb];
       if (GT.nblocks == 0) return IEXA_OK;
@@ -899,7 +1044,7 @@ class CudaEngine : public Engine {
                     double sigma, double *outd, cudaStream_t st, std::string &err) {
     if (T.nblocks == 0) return IEXA_OK;
     double *part = partials_.as<double>();
-    const double *th = theta_.as<double>();
+    const double *th = theta_ptr();
     if (max_nreg <= 32)
       interp_kernel<32><<<T.nblocks, BLOCK, 0, st>>>(gens_dev_, T.work, prog, sink, xd, th, yd, vd, sigma, outd, part);
     else if (max_nreg <= 96)
@@ -976,7 +1121,7 @@ class CudaEngine : public Engine {
     if (memspace == IEXA_MEM_HOST) { CK(stage_out_.ensure((size_t)no * 8)); od = stage_out_.as<double>(); }
     const bool spec = spec_ && spec_->products_built() && prod_note_.empty();
     double *part = partials_.as<double>();
-    const double *th = theta_.as<double>();
+    const double *th = theta_ptr();
     if (cb == CB_JPROD) {
       if (spec) {
         if (spec_->has(KS_JPROD) && gtable_[KS_JPROD].nblocks > 0 &&

@@ -37,6 +37,7 @@ struct Engine {
                     int memspace, void *stream, std::string &err) = 0;
   virtual int set_par(int64_t off, int64_t n, const double *vals, void *stream, bool device_sync, std::string &err) = 0;
   virtual int jac_rowptr(void *rowptr, int idx_bytes, int memspace, void *stream, std::string &err) = 0; // CSR row pointers (JAC_ROW_SORTED)
+  virtual void device_bytes(int64_t *out) const = 0; // [columns, columns of the unsharded model, theta, theta full, programs + tables, host-path staging]
   virtual int get_column(int32_t col, double *out_host, std::string &err) = 0; // device copy of Plan::columns[col] (fp)
   virtual int host_register(void *p, size_t bytes, std::string &err) = 0;
   virtual int host_unregister(void *p, std::string &err) = 0;

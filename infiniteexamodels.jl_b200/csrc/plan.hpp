@@ -820,6 +820,70 @@ struct Plan {
     return m;
   }
 
+  // ---- what a rank keeps on ITS device when world > 1 (shard the inputs, not just the outputs) ----------
+  // positions [lo, hi) of column c that this rank's generators visit: j = (k / div) % mod over k in [k0, k1) for every
+  // reference to the column (a hull; a wrapping or longer-than-mod walk keeps the whole column).  lo == hi: not read at all.
+  // Parameter functions are evaluated over their whole iterator on every rank, so their columns stay whole.
+  std::vector<std::pair<int64_t, int64_t>> column_read_ranges() const {
+    std::vector<std::pair<int64_t, int64_t>> rr(columns.size(), {INT64_MAX, 0});
+    auto visit = [&](const ColRef &r, int64_t k0, int64_t k1) {
+      if (k1 <= k0) return;
+      int64_t q0 = k0 / r.div, q1 = (k1 - 1) / r.div, j0 = 0, j1 = r.mod - 1;
+      if (q1 - q0 + 1 < r.mod && q0 % r.mod <= q1 % r.mod) { j0 = q0 % r.mod; j1 = q1 % r.mod; }
+      rr[r.col].first = std::min(rr[r.col].first, j0);
+      rr[r.col].second = std::max(rr[r.col].second, j1 + 1);
+    };
+    auto scan = [&](const Generator &g, bool whole) {
+      const Iterator &it = itrs[g.itr];
+      const int64_t k0 = whole ? 0 : g.k0, k1 = whole ? g.K : g.k1;
+      for (int32_t s : g.c.int_cols) visit(it.int_cols[s], k0, k1);
+      for (int32_t s : g.c.fp_cols) visit(it.fp_cols[s], k0, k1);
+    };
+    for (auto &g : objs) scan(g, false);
+    for (auto &g : cons) scan(g, false);
+    for (auto &g : pfuncs) scan(g, true);
+    for (size_t c = 0; c < columns.size(); ++c) {
+      if (rr[c].first == INT64_MAX) rr[c] = {0, 0};
+      const HostColumn &hc = columns[c];
+      if (!hc.is_int && hc.gen_kind == 3 && hc.gen_src >= 0 && rr[c].second > rr[c].first) { // TRAPEZOID reads src[j-1 .. j+1]
+        auto &sr = rr[hc.gen_src];
+        const int64_t lo = std::max<int64_t>(rr[c].first - 1, 0), hi = std::min<int64_t>(rr[c].second + 1, columns[hc.gen_src].K);
+        if (sr.second <= sr.first) sr = {lo, hi};
+        else { sr.first = std::min(sr.first, lo); sr.second = std::max(sr.second, hi); }
+      }
+    }
+    return rr;
+  }
+  // the parts of theta this rank's programs read (0-based [lo, hi), merged, sorted; a cover).  With parameter functions the
+  // blocks they fill are written whole on every rank: everything stays resident.
+  std::vector<std::pair<int64_t, int64_t>> theta_read_ranges() const {
+    std::vector<std::pair<int64_t, int64_t>> iv, m;
+    if (npar <= 0) return m;
+    if (!pfuncs.empty() || world <= 1) { m.emplace_back(0, npar); return m; }
+    auto scan = [&](const Generator &g) {
+      if (g.k1 <= g.k0) return;
+      const Iterator &it = itrs[g.itr];
+      std::vector<uint8_t> used(g.c.uidx.size(), 0);
+      const Program *pr[] = {&g.c.val, &g.c.d1, &g.c.d2, &g.c.jv, &g.c.jtv, &g.c.hv};
+      for (const Program *q : pr) for (const Instr &I : q->code) if (I.op == D_LOADP && I.a >= 0 && (size_t)I.a < used.size()) used[I.a] = 1;
+      for (size_t s2 = 0; s2 < used.size(); ++s2) {
+        if (!used[s2]) continue;
+        int64_t lo, hi;
+        index_range(it, g.c.int_cols, g.c.uidx[s2], g.k0, g.k1, lo, hi);
+        lo = std::max<int64_t>(lo, 1); hi = std::min<int64_t>(hi, npar);
+        if (lo <= hi) iv.emplace_back(lo - 1, hi);
+      }
+    };
+    for (auto &g : objs) scan(g);
+    for (auto &g : cons) scan(g);
+    std::sort(iv.begin(), iv.end());
+    for (auto &r : iv) {
+      if (!m.empty() && r.first <= m.back().second) m.back().second = std::max(m.back().second, r.second);
+      else m.push_back(r);
+    }
+    return m;
+  }
+
   // IEXA_SLOT_ORDER_JAC_ROW_SORTED.  perm[p] = policy-order slot that comes p-th when the first-order slots of a row are sorted by
   // column index — provided that order is STATIC (the same for every support k in [0, K)) and strict (no two slots share a
   // column at any k).  Pairs of slots with identical term structure differ by a constant; every other pair is checked over

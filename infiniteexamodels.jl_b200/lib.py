@@ -44,7 +44,7 @@ SYMBOLS = [
     "iexa_launches_per_call", "iexa_engine_note", "iexa_debug_codegen_source", "iexa_debug_set_class_mode", "iexa_debug_codegen_compile", "iexa_debug_codegen_source_of", "iexa_debug_codegen_compile_of", "iexa_debug_cache_stats",
     "iexa_halo_create", "iexa_halo_export", "iexa_halo_connect", "iexa_halo_set_sends", "iexa_halo_set_recvs", "iexa_halo_exchange",
     "iexa_halo_allreduce_small", "iexa_halo_status", "iexa_halo_destroy",
-    "iexa_csr_create", "iexa_csr_create_keyed", "iexa_coo_locality", "iexa_jac_is_csr", "iexa_jac_csr_rowptr", "iexa_csr_destroy", "iexa_csr_nnz", "iexa_csr_pattern", "iexa_csr_apply",
+    "iexa_csr_create", "iexa_csr_create_keyed", "iexa_coo_locality", "iexa_jac_is_csr", "iexa_jac_csr_rowptr", "iexa_device_bytes", "iexa_csr_destroy", "iexa_csr_nnz", "iexa_csr_pattern", "iexa_csr_apply",
 ]
 
 _vp, _i64, _i32, _dbl, _u32 = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_uint32
@@ -110,6 +110,7 @@ def _declare(L):
     sig("iexa_csr_create_keyed", _i32, C.POINTER(_vp), _i64, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _i32)
     sig("iexa_coo_locality", _i32, _vp, _i32, _vp, _i32, _vp)
     sig("iexa_jac_is_csr", _i32, _vp, _vp)
+    sig("iexa_device_bytes", _i32, _vp, _vp)
     sig("iexa_jac_csr_rowptr", _i32, _vp, _vp, _i32, _i32, _vp)
     sig("iexa_csr_destroy", _i32, _vp)
     sig("iexa_csr_nnz", _i64, _vp)
@@ -127,6 +128,8 @@ def _declare(L):
     # test-only entry points of tests/hostcheck (absent from the product library)
     sig("hostcheck_eval", _i32, _vp, _i32, _vp, _vp, _dbl, _vp)
     sig("hostcheck_eval_local", _i32, _vp, _i32, _vp, _vp, _dbl, _vp)
+    sig("hostcheck_residency_misses", _i64)
+    sig("hostcheck_residency_bytes", _i32, _vp, _vp)
     sig("hostcheck_eval_groups", _i32, _vp, _i32, _vp, _vp, _dbl, _vp, C.POINTER(_i32))
     sig("hostcheck_set_class_mode", _i32, _vp, _i32)
     sig("hostcheck_structure", _i32, _vp, _i32, _vp, _vp)

@@ -235,6 +235,13 @@ def jac_structure_(m: ExaModel, rows, cols):
     return rows, cols
 
 
+def device_bytes(m: ExaModel) -> dict:
+    """device memory the engine holds for this plan on this rank (iexa.h iexa_device_bytes)"""
+    out = (C.c_int64 * 6)()
+    _lib.check(m.L, m.L.iexa_device_bytes(m.h, out))
+    return dict(zip(("columns", "columns_unsharded", "theta", "theta_unsharded", "programs_tables", "host_path_staging"), [int(v) for v in out]))
+
+
 def jac_is_csr(m: ExaModel) -> bool:
     """The jac_coord! array is already a CSR value array (slot_order=2, iexa.h IEXA_SLOT_ORDER_JAC_ROW_SORTED)."""
     out = C.c_int32(0)

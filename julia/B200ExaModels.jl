@@ -393,6 +393,12 @@ end
 array; `jac_csr_rowptr!(m, rowptr)` fills the `ncon + 1` zero-based row pointers and `jac_structure!`'s cols are the column
 indices, so a KKT assembly needs no COO->CSR pass for the Jacobian.
 """
+"engine-held device bytes of this rank: (columns, columns_unsharded, theta, theta_unsharded, programs_tables, host_path_staging)"
+function device_bytes(m::B200ExaModel)
+    out = zeros(Int64, 6)
+    GC.@preserve out check(ccall((:iexa_device_bytes, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}), m.plan.h, out))
+    return NamedTuple{(:columns, :columns_unsharded, :theta, :theta_unsharded, :programs_tables, :host_path_staging)}(Tuple(out))
+end
 function jac_is_csr(m::B200ExaModel)
     out = Ref{Int32}(0)
     check(ccall((:iexa_jac_is_csr, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}), m.plan.h, out))

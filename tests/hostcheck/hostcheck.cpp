@@ -18,9 +18,31 @@ Engine *make_cuda_engine(Plan &, int, uint32_t, std::string &err) {
   return nullptr;
 }
 
+// Residency emulation (world > 1): what the CUDA engine keeps on a rank's device — the slices of Plan::column_read_ranges and the
+// theta ranges of Plan::theta_read_ranges.  hostcheck_eval_local counts every access outside them (hostcheck_residency_misses).
+struct Residency {
+  std::vector<std::pair<int64_t, int64_t>> cols, theta;
+  int64_t misses = 0;
+  void check_col(int32_t col, int64_t j) { if (j < cols[col].first || j >= cols[col].second) ++misses; }
+  void check_theta(int64_t i0) {
+    for (auto &r : theta) if (i0 >= r.first && i0 < r.second) return;
+    ++misses;
+  }
+};
+static Residency *g_res = nullptr;
+static int64_t g_last_misses = -1;
+
 static void run_program(const Plan &P, const Generator &g, const Program &pr, int64_t k, const double *x,
                         double W, std::vector<double> &r, double *out, const double *v = nullptr) {
   r.resize(pr.nreg > 0 ? pr.nreg : 1);
+  if (g_res) { // every column position and theta entry this support touches must be resident on this rank
+    const Iterator &it = P.itrs[g.itr];
+    for (int32_t s : g.c.int_cols) { const ColRef &c = it.int_cols[s]; if (!P.columns[c.col].affine) g_res->check_col(c.col, (k / c.div) % c.mod); }
+    for (const Instr &I : pr.code) {
+      if (I.op == D_FIELD) { const ColRef &c = it.fp_cols[g.c.fp_cols[I.a]]; g_res->check_col(c.col, (k / c.div) % c.mod); }
+      if (I.op == D_LOADP) g_res->check_theta(P.index_value(g, I.a, k) - 1);
+    }
+  }
   for (const Instr &I : pr.code) {
     switch (I.op) {
       case D_FIELD: r[I.dst] = P.fp_col_value(g, I.a, k); break;
@@ -112,9 +134,45 @@ int32_t hostcheck_eval(iexa_plan *p, int32_t which, const double *x, const doubl
 
 // this rank's shard only, LOCAL layout (what the CUDA engine produces when world > 1); y is local too.
 // which: 0 obj partial, 1 grad partial (dense nvar), 2 cons, 3 jac_coord, 4 hess_coord
+int64_t hostcheck_residency_misses(void) { return g_last_misses; }
+// out4: [column bytes resident on this rank, column bytes of the whole model, theta bytes read by this rank, 8 * npar]
+int32_t hostcheck_residency_bytes(iexa_plan *p, int64_t *out4) {
+  if (!p || !p->plan.finalized) return IEXA_ERR_STATE;
+  const Plan &P = p->plan;
+  auto rr = P.column_read_ranges();
+  out4[0] = out4[1] = out4[2] = 0;
+  std::vector<char> used(P.columns.size(), 0);
+  auto mark = [&](const Generator &g) {
+    const Iterator &it = P.itrs[g.itr];
+    for (int32_t s : g.c.int_cols) used[it.int_cols[s].col] = 1;
+    for (int32_t s : g.c.fp_cols) used[it.fp_cols[s].col] = 1;
+  };
+  for (auto &g : P.objs) mark(g);
+  for (auto &g : P.cons) mark(g);
+  for (auto &g : P.pfuncs) mark(g);
+  for (size_t c = 0; c < P.columns.size(); ++c) {
+    const HostColumn &hc = P.columns[c];
+    if (hc.gen_src >= 0 && used[c]) used[hc.gen_src] = 1;
+  }
+  for (size_t c = 0; c < P.columns.size(); ++c) {
+    const HostColumn &hc = P.columns[c];
+    if (!used[c] || (hc.is_int && hc.affine)) continue;
+    const int64_t w = hc.is_int ? 4 : 8;
+    out4[0] += w * std::max<int64_t>(rr[c].second - rr[c].first, 0);
+    out4[1] += w * hc.K;
+  }
+  for (auto &r : P.theta_read_ranges()) out4[2] += 8 * (r.second - r.first);
+  out4[3] = 8 * P.npar;
+  return IEXA_OK;
+}
 int32_t hostcheck_eval_local(iexa_plan *p, int32_t which, const double *x, const double *y, double sigma, double *out) {
   if (!p || !p->plan.finalized) return IEXA_ERR_STATE;
   const Plan &P = p->plan;
+  Residency res;
+  res.cols = P.column_read_ranges();
+  res.theta = P.theta_read_ranges();
+  g_res = &res;
+  struct Done { Residency &r; ~Done() { g_last_misses = r.misses; g_res = nullptr; } } done{res};
   std::vector<double> r, tmp;
   if (which == 0) out[0] = 0.0;
   if (which == 1) std::memset(out, 0, sizeof(double) * (size_t)P.nvar);

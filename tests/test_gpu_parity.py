@@ -270,6 +270,61 @@ def test_sharded_plans_tile_the_model_on_one_gpu(world, oracle_cache):
     assert np.allclose(g, om.grad(x), rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize("device_side", [False, True])
+def test_a_rank_keeps_its_slices_of_columns_and_theta_on_the_device(device_side):
+    """world > 1 on the device: iterator columns are uploaded (or generated) as the slice the rank's supports visit, theta is a
+    full-length virtual range with only the rank's granules backed (CUDA virtual-memory API) — sized so that path is taken
+    (theta = 3 x 8*10^5 doubles = 19 MB, 10 granules, of which a rank of 4 maps <= 6).  Results: bit-identical to the unsharded
+    model on the same GPU, slice by slice; set_parameter! on a block reaches the resident part and is ignored elsewhere."""
+    import torch
+    N, world = 400_000, 4
+    core = models.quadrotor(N, "oc", device_side=device_side)
+    full = ex.ExaModel(core, device=0)
+    x, y = eval_point(core, seed=3)
+    xd = torch.from_numpy(x).cuda()
+    dev = torch.device("cuda:0")
+    z = lambda n: torch.zeros(max(n, 1), dtype=torch.float64, device=dev)
+    cF, jF, hF = z(full.meta.ncon), z(full.meta.nnzj), z(full.meta.nnzh)
+    yd = torch.from_numpy(y).cuda()
+    ex.cons_(full, xd, cF); ex.jac_coord_(full, xd, jF); ex.hess_coord_(full, xd, yd, hF, 0.7)
+    b1 = ex.device_bytes(full)
+    assert b1["columns"] == b1["columns_unsharded"] and b1["theta"] == b1["theta_unsharded"]
+    for rank in (1, 3):
+        m = ex.ExaModel(core, device=0, rank=rank, world=world)
+        b = ex.device_bytes(m)
+        if device_side:   # parameter functions evaluated on the device fill whole theta blocks on every rank: theta and the columns they read stay whole
+            assert b["columns"] < b["columns_unsharded"] and b["theta"] == b["theta_unsharded"], b
+        else:
+            assert b["columns"] <= b["columns_unsharded"] / world + 4096, b
+            assert b["theta"] <= 0.75 * b["theta_unsharded"], b
+        segs = {}
+        for which in range(3):
+            arr = (ex.lib.Segment * 4096)()
+            n = m.L.iexa_segments(m.h, which, arr, 4096)
+            segs[which] = [(s.global_start, s.local_start, s.length) for s in arr[:n]]
+        yl = z(m.loc_ncon)
+        for gs, ls, ln in segs[0]:
+            yl[ls:ls + ln] = yd[gs:gs + ln]
+        c, jv, hv = z(m.loc_ncon), z(m.loc_nnzj), z(m.loc_nnzh)
+        ex.cons_(m, xd, c); ex.jac_coord_(m, xd, jv); ex.hess_coord_(m, xd, yl, hv, 0.7)
+        for (ref, loc, which) in ((cF, c, 0), (jF, jv, 1), (hF, hv, 2)):
+            for gs, ls, ln in segs[which]:
+                assert torch.equal(loc[ls:ls + ln], ref[gs:gs + ln]), (rank, which)
+        if not device_side:
+            # update the first theta block (d1 of ESCAPE34/quadrotor.jl:16) on both models: same results again
+            T = core.npar // 3
+            new = np.linspace(-1.0, 1.0, T)
+            for mm in (full, m):
+                ex.lib.check(mm.L, mm.L.iexa_set_par(mm.h, 0, T, new.ctypes.data))
+            ex.cons_(full, xd, cF); ex.cons_(m, xd, c)
+            for gs, ls, ln in segs[0]:
+                assert torch.equal(c[ls:ls + ln], cF[gs:gs + ln]), rank
+            old = np.ascontiguousarray(core.theta_vec[:T])
+            ex.lib.check(full.L, full.L.iexa_set_par(full.h, 0, T, old.ctypes.data))
+            ex.cons_(full, xd, cF)
+        del m
+
+
 def test_opf_shape_classes_and_budget_fallback(oracle_cache, monkeypatch):
     """BASELINE configs[3] (ESCAPE34/opf.jl) through the general lowering: the embedded 3-bus case (fused
     groups), a 30-bus grid with 722 generators (its fused source exceeds the NVRTC budget -> generators
