@@ -510,6 +510,25 @@ def main():
     jv = torch.empty(max(m.loc_nnzj, 1), dtype=torch.float64, device=dev)
     hv = torch.empty(max(m.loc_nnzh, 1), dtype=torch.float64, device=dev)
 
+    # ---- device memory per rank (inputs sharded, not just outputs); EVERY rank takes part in the max
+    db = ex.device_bytes(m)
+    nxr = m.L.iexa_x_ranges(m.h, None, 0)
+    xsegs = (ex.lib.Segment * max(nxr, 1))()
+    m.L.iexa_x_ranges(m.h, xsegs, nxr)
+    xr = 8 * sum(sg.length for sg in xsegs[:nxr]) if world > 1 else 8 * m.meta.nvar
+    caller_local = 8 * (m.loc_ncon * 2 + m.loc_nnzj + m.loc_nnzh)           # y, c, Jacobian values, Hessian values of this rank
+    mine = [db["columns"] + db["theta"] + db["programs_tables"], caller_local, xr, 8 * m.meta.nvar]
+    mx = [float(v) for v in ctx.max_over_ranks([float(v) for v in mine])]
+    whole = 8 * (core.ncon * 2 + m.meta.nnzj + m.meta.nnzh) + db["columns_unsharded"] + db["theta_unsharded"]
+    device_memory = {
+        "engine_bytes_per_rank_max": int(mx[0]), "engine_columns": db["columns"], "engine_columns_unsharded": db["columns_unsharded"],
+        "engine_theta": db["theta"], "engine_theta_unsharded": db["theta_unsharded"], "engine_programs_tables": db["programs_tables"],
+        "caller_y_c_jac_hess_bytes_per_rank_max": int(mx[1]), "x_bytes_touched_per_rank_max": int(mx[2]), "x_bytes_addressed": int(mx[3]),
+        "per_rank_over_unsharded": (mx[0] + mx[1] + mx[2]) / float(whole + 8 * m.meta.nvar),
+        "note": "engine = iterator columns (the slice this rank's supports visit) + theta (full-length virtual range, only this rank's 2 MB granules "
+                "backed) + programs / tables; caller = y, c and the value arrays of the rank's rows; x is addressed full-length by contract "
+                "(global indices) — a rank touches x_bytes_touched of it (iexa_x_ranges); per_rank_over_unsharded counts the touched part"}
+
     # buffers are bound once (raw pointers + stream), like a Julia ccall on CuArray pointers: every
     # callback below is exactly one call into the C ABI
     f_cons = bind(m, "cons", x, c)
@@ -729,25 +748,6 @@ def main():
                              "sample": "same model, OpenMP over supports, best of 3 full evals"}}
         del om
 
-    # ---- device memory per rank (inputs sharded, not just outputs)
-    db = ex.device_bytes(m)
-    nxr = m.L.iexa_x_ranges(m.h, None, 0)
-    xsegs = (ex.lib.Segment * max(nxr, 1))()
-    m.L.iexa_x_ranges(m.h, xsegs, nxr)
-    xr = 8 * sum(sg.length for sg in xsegs[:nxr]) if world > 1 else 8 * m.meta.nvar
-    caller_local = 8 * (m.loc_ncon * 2 + m.loc_nnzj + m.loc_nnzh)           # y, c, Jacobian values, Hessian values of this rank
-    mine = [db["columns"] + db["theta"] + db["programs_tables"], caller_local, xr, 8 * m.meta.nvar]
-    mx = [float(v) for v in ctx.max_over_ranks([float(v) for v in mine])]
-    whole = 8 * (core.ncon * 2 + bytes_meta["nnzj"] + bytes_meta["nnzh"]) + db["columns_unsharded"] + db["theta_unsharded"]
-    device_memory = {
-        "engine_bytes_per_rank_max": int(mx[0]), "engine_columns": db["columns"], "engine_columns_unsharded": db["columns_unsharded"],
-        "engine_theta": db["theta"], "engine_theta_unsharded": db["theta_unsharded"], "engine_programs_tables": db["programs_tables"],
-        "host_path_staging_rank0": db["host_path_staging"],
-        "caller_y_c_jac_hess_bytes_per_rank_max": int(mx[1]), "x_bytes_touched_per_rank_max": int(mx[2]), "x_bytes_addressed": int(mx[3]),
-        "per_rank_over_unsharded": (mx[0] + mx[1] + mx[2]) / float(whole + 8 * m.meta.nvar),
-        "note": "engine = iterator columns (the slice this rank's supports visit) + theta (full-length virtual range, only this rank's 2 MB granules "
-                "backed) + programs / tables; caller = y, c and the value arrays of the rank's rows; x is addressed full-length by contract "
-                "(global indices) — a rank touches x_bytes_touched of it (iexa_x_ranges); per_rank_over_unsharded counts the touched part"}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -864,7 +864,10 @@ def measure_iteration(ctx, ex, m, core, x, y, c, jv, hv, args, peak):
     # ---- the same iteration on the ROW-SORTED slot policy (iexa.h IEXA_SLOT_ORDER_JAC_ROW_SORTED): jac_coord! writes the CSR
     #      value array directly, so the Jacobian's COO->CSR pass is not part of the step at all.  Checked in-run against the
     #      default model: same CSR pattern, bit-identical CSR values.
-    if csr[0] is not None and not getattr(args, "no_row_sorted", False):
+    # Every rank takes the same path: set-up (which may fail) happens first, the ranks then AGREE whether to run the timed part.
+    rs, rs_err = None, None
+    want = not getattr(args, "no_row_sorted", False)
+    if want and csr[0] is not None:
         try:
             t0 = time.perf_counter()
             mr = ex.ExaModel(core, device=ctx.local_rank, rank=ctx.rank, world=world, slot_order=2,
@@ -878,18 +881,6 @@ def measure_iteration(ctx, ex, m, core, x, y, c, jv, hv, args, peak):
                 ex.jac_structure_(mr, rr, cr)
                 r_grad = bind(mr, "grad", x, g)
                 r_cons, r_jac, r_hess = bind(mr, "cons", x, c), bind(mr, "jac_coord", x, jr), bind(mr, "hess_coord", x, hv, y, 1.0)
-
-                def step_r():
-                    if world > 1:
-                        sm.exchange_x(x)
-                    L.iexa_obj_device(mr.h, xp, fp, vp(st))
-                    r_grad()
-                    if world > 1:
-                        sm.allreduce_obj_grad_(f_dev, g)
-                    r_cons(); r_jac(); r_hess()
-                    if csr[1] is not None:
-                        L.iexa_csr_apply(csr[1][0], vp(hv.data_ptr()), vp(csr[1][1].data_ptr()), 1, vp(st))
-
                 # parity first: the default model's CSR (its own COO->CSR map) against the array jac_coord! wrote here
                 f_jac(); L.iexa_csr_apply(csr[0][0], vp(jv.data_ptr()), vp(csr[0][1].data_ptr()), 1, vp(st))
                 r_jac()
@@ -897,33 +888,55 @@ def measure_iteration(ctx, ex, m, core, x, y, c, jv, hv, args, peak):
                 prp = torch.zeros(m.meta.ncon + 1, dtype=torch.int32, device=dev); pci = torch.zeros(mr.loc_nnzj, dtype=torch.int32, device=dev)
                 ex.lib.check(L, L.iexa_csr_pattern(csr[0][0], vp(prp.data_ptr()), vp(pci.data_ptr()), 1))
                 torch.cuda.synchronize()
-                # a rank's rows are global row numbers in the default CSR map; local row r of the row-sorted model is the r-th non-empty range
                 same_vals = bool(torch.equal(csr[0][1], jr[: csr[0][1].numel()]))
                 same_cols = bool(torch.equal(pci, cr - 1))
-                same_rows = bool(torch.equal(prp, rp)) if world == 1 else None
-                for _ in range(3):
-                    step_r()
-                ctx.barrier()
-                a, b = ctx.ev(), ctx.ev()
-                ctx.barrier()
-                a.record()
-                for _ in range(n):
-                    step_r()
-                b.record()
-                ctx.barrier()
-                msr = float(ctx.max_over_ranks(a.elapsed_time(b) / n)[0])
-                tj = per_callback_ms(ctx, [r_jac], max(5, min(args.steps, 30)), flush=False)
-                out["row_sorted"] = {"ms": msr, "iterations/s": 1e3 / msr, "jac_coord_ms": float(tj[0]),
-                                     "csr_values_bit_identical_to_default_policy_plus_csr_apply": same_vals,
-                                     "csr_colind_identical": same_cols, "csr_rowptr_identical": same_rows, "build_s": t_build,
-                                     "what": "the same step with IEXA_OPT_SLOT_ORDER = JAC_ROW_SORTED: jac_coord! output IS the CSR value array "
-                                             "(iexa_jac_csr_rowptr + jac_structure cols), so only the Hessian goes through iexa_csr_apply"}
-                del jr, rp, rr, cr, prp, pci
+                same_rows = bool(torch.equal(prp, rp)) if world == 1 else True   # world > 1: the default map numbers rows globally
+                rs = (mr, r_grad, r_cons, r_jac, r_hess, same_vals, same_cols, same_rows, t_build)
+                del rp, rr, cr, prp, pci
             else:
-                out["row_sorted"] = {"unavailable": "a generator of this model has no static column order"}
-            del mr
+                rs_err = "a generator of this model has no static column order"
         except Exception as e:      # the variant must never take the headline down
-            out["row_sorted"] = {"error": repr(e)[:300]}
+            rs, rs_err = None, repr(e)[:300]
+    elif want:
+        rs_err = "no Jacobian entries on this rank"
+    if want:
+        go = float(ctx.max_over_ranks(0.0 if rs is not None else 1.0)[0]) == 0.0
+        if go:
+            mr, r_grad, r_cons, r_jac, r_hess, same_vals, same_cols, same_rows, t_build = rs
+
+            def step_r():
+                if world > 1:
+                    sm.exchange_x(x)
+                L.iexa_obj_device(mr.h, xp, fp, vp(st))
+                r_grad()
+                if world > 1:
+                    sm.allreduce_obj_grad_(f_dev, g)
+                r_cons(); r_jac(); r_hess()
+                if csr[1] is not None:
+                    L.iexa_csr_apply(csr[1][0], vp(hv.data_ptr()), vp(csr[1][1].data_ptr()), 1, vp(st))
+
+            for _ in range(3):
+                step_r()
+            ctx.barrier()
+            a, b = ctx.ev(), ctx.ev()
+            ctx.barrier()
+            a.record()
+            for _ in range(n):
+                step_r()
+            b.record()
+            ctx.barrier()
+            msr = float(ctx.max_over_ranks(a.elapsed_time(b) / n)[0])
+            tj = per_callback_ms(ctx, [r_jac], max(5, min(args.steps, 30)), flush=False)
+            bad = ctx.max_over_ranks([0.0 if same_vals else 1.0, 0.0 if same_cols else 1.0, 0.0 if same_rows else 1.0])   # AND over the ranks
+            out["row_sorted"] = {"ms": msr, "iterations/s": 1e3 / msr, "jac_coord_ms": float(tj[0]),
+                                 "csr_values_bit_identical_to_default_policy_plus_csr_apply": bool(bad[0] == 0.0),
+                                 "csr_colind_identical": bool(bad[1] == 0.0), "csr_rowptr_identical": bool(bad[2] == 0.0) if world == 1 else None,
+                                 "build_s": t_build,
+                                 "what": "the same step with IEXA_OPT_SLOT_ORDER = JAC_ROW_SORTED: jac_coord! output IS the CSR value array "
+                                         "(iexa_jac_csr_rowptr + jac_structure cols), so only the Hessian goes through iexa_csr_apply"}
+        else:
+            out["row_sorted"] = {"unavailable": rs_err or "unavailable on another rank"}
+        rs = None
     sm.close_peer_halo()
     for k in range(2):
         if csr[k] is not None:
