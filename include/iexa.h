@@ -222,6 +222,10 @@ int32_t iexa_set_vector(iexa_plan *p, int32_t which, const double *in); /* x0 / 
  * callback (values are staged in a pinned buffer of the engine; vals_host may be reused as soon as the call returns). */
 int32_t iexa_set_par(iexa_plan *p, int64_t offset0, int64_t n, const double *vals_host);
 int32_t iexa_set_par_stream(iexa_plan *p, int64_t offset0, int64_t n, const double *vals_host, void *stream);
+/* world > 1: a rank's device holds the slices of theta its own supports read (iexa_device_bytes); iexa_set_par writes the resident
+ * part of the range and skips the rest.  iexa_get_par serves the host mirror: complete for blocks given as values; for a block
+ * evaluated on the device (iexa_add_par_function) a rank of world > 1 has computed — and returns — only the entries its supports
+ * read (zeros elsewhere; IEXA_NO_PFUNC_SHARDING=1 evaluates whole blocks on every rank).                                      */
 int32_t iexa_get_par(const iexa_plan *p, int64_t offset0, int64_t n, double *vals_host);
 
 /* ---- NLPModels callbacks (ExaModels 0.11.2 methods reached from

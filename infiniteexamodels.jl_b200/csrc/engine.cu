@@ -816,7 +816,7 @@ class CudaEngine : public Engine {
     {
       std::vector<std::pair<size_t, size_t>> tr;
       for (auto &r : P.theta_read_ranges()) tr.emplace_back((size_t)r.first * 8, (size_t)r.second * 8);
-      CK(theta_.alloc((size_t)(P.npar > 0 ? P.npar : 1) * 8, tr, device_, P.world > 1 && P.pfuncs.empty()));
+      CK(theta_.alloc((size_t)(P.npar > 0 ? P.npar : 1) * 8, tr, device_, P.world > 1));
       if (P.npar > 0) CK(theta_.upload((const char *)P.theta.data(), 0, (size_t)P.npar * 8, nullptr, false));
     }
 
@@ -853,8 +853,9 @@ class CudaEngine : public Engine {
     for (size_t pi = 0; pi < P.pfuncs.size(); ++pi) {
       const Generator &g = P.pfuncs[pi];
       const int gi = nobj + ncon + (int)pi;
-      std::vector<WorkItem> pw;
-      for (int64_t b = 0; b * BLOCK < g.K; ++b) pw.push_back(WorkItem{gi, (int32_t)b});
+      std::vector<WorkItem> pw;   // world > 1: the k-range whose theta entries this rank reads (Plan::shard_pfuncs)
+      const int64_t nk = g.k1 - g.k0;
+      for (int64_t b = 0; b * BLOCK < nk; ++b) pw.push_back(WorkItem{gi, (int32_t)b});
       if (pw.empty()) continue;
       DevBuf wb;
       CK(wb.ensure(pw.size() * sizeof(WorkItem)));
@@ -864,7 +865,7 @@ class CudaEngine : public Engine {
       int rc = launch_interp(T, g.c.val.nreg, PROG_VAL, SINK_DENSE, nullptr, nullptr, nullptr, 1.0, theta_ptr(), nullptr, err);
       if (rc) return rc;
       CK(cudaDeviceSynchronize());
-      CK(cudaMemcpy(P.theta.data() + g.o0, theta_ptr() + g.o0, (size_t)g.K * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(P.theta.data() + g.l0, theta_ptr() + g.l0, (size_t)nk * 8, cudaMemcpyDeviceToHost));
     }
     return IEXA_OK;
   }

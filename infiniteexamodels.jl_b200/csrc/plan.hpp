@@ -435,6 +435,7 @@ struct Plan {
       g.l1 = loc_nnzj; loc_nnzj += (g.k1 - g.k0) * g.c.o1step;
       g.l2 = loc_nnzh; loc_nnzh += (g.k1 - g.k0) * g.c.o2step;
     }
+    shard_pfuncs();
     build_groups();
     analyse_grad();
     finalized = true;
@@ -823,7 +824,7 @@ struct Plan {
   // ---- what a rank keeps on ITS device when world > 1 (shard the inputs, not just the outputs) ----------
   // positions [lo, hi) of column c that this rank's generators visit: j = (k / div) % mod over k in [k0, k1) for every
   // reference to the column (a hull; a wrapping or longer-than-mod walk keeps the whole column).  lo == hi: not read at all.
-  // Parameter functions are evaluated over their whole iterator on every rank, so their columns stay whole.
+  // Parameter functions are evaluated over the k-range whose theta entries this rank reads (shard_pfuncs).
   std::vector<std::pair<int64_t, int64_t>> column_read_ranges() const {
     std::vector<std::pair<int64_t, int64_t>> rr(columns.size(), {INT64_MAX, 0});
     auto visit = [&](const ColRef &r, int64_t k0, int64_t k1) {
@@ -833,15 +834,14 @@ struct Plan {
       rr[r.col].first = std::min(rr[r.col].first, j0);
       rr[r.col].second = std::max(rr[r.col].second, j1 + 1);
     };
-    auto scan = [&](const Generator &g, bool whole) {
+    auto scan = [&](const Generator &g) {
       const Iterator &it = itrs[g.itr];
-      const int64_t k0 = whole ? 0 : g.k0, k1 = whole ? g.K : g.k1;
-      for (int32_t s : g.c.int_cols) visit(it.int_cols[s], k0, k1);
-      for (int32_t s : g.c.fp_cols) visit(it.fp_cols[s], k0, k1);
+      for (int32_t s : g.c.int_cols) visit(it.int_cols[s], g.k0, g.k1);
+      for (int32_t s : g.c.fp_cols) visit(it.fp_cols[s], g.k0, g.k1);
     };
-    for (auto &g : objs) scan(g, false);
-    for (auto &g : cons) scan(g, false);
-    for (auto &g : pfuncs) scan(g, true);
+    for (auto &g : objs) scan(g);
+    for (auto &g : cons) scan(g);
+    for (auto &g : pfuncs) scan(g);
     for (size_t c = 0; c < columns.size(); ++c) {
       if (rr[c].first == INT64_MAX) rr[c] = {0, 0};
       const HostColumn &hc = columns[c];
@@ -854,28 +854,55 @@ struct Plan {
     }
     return rr;
   }
-  // the parts of theta this rank's programs read (0-based [lo, hi), merged, sorted; a cover).  With parameter functions the
-  // blocks they fill are written whole on every rank: everything stays resident.
+  // theta entries [lo, hi) (0-based) that the programs of generator g read over its supports [k0, k1) (a cover)
+  void theta_reads_of(const Generator &g, std::vector<std::pair<int64_t, int64_t>> &iv) const {
+    if (g.k1 <= g.k0) return;
+    const Iterator &it = itrs[g.itr];
+    std::vector<uint8_t> used(g.c.uidx.size(), 0);
+    const Program *pr[] = {&g.c.val, &g.c.d1, &g.c.d2, &g.c.jv, &g.c.jtv, &g.c.hv};
+    for (const Program *q : pr) for (const Instr &I : q->code) if (I.op == D_LOADP && I.a >= 0 && (size_t)I.a < used.size()) used[I.a] = 1;
+    for (size_t s2 = 0; s2 < used.size(); ++s2) {
+      if (!used[s2]) continue;
+      int64_t lo, hi;
+      index_range(it, g.c.int_cols, g.c.uidx[s2], g.k0, g.k1, lo, hi);
+      lo = std::max<int64_t>(lo, 1); hi = std::min<int64_t>(hi, npar);
+      if (lo <= hi) iv.emplace_back(lo - 1, hi);
+    }
+  }
+  // world > 1: a parameter function (a theta block evaluated on the device at finalize) runs over the k-range whose entries this
+  // rank's generators — or a later parameter function, through PAR leaves — read; the rest of the block belongs to other ranks.
+  // Walked last to first, so that what a restricted function reads is known when the earlier ones are restricted.
+  void shard_pfuncs() {
+    for (auto &g : pfuncs) { g.k0 = 0; g.k1 = g.K; g.l0 = g.o0; }
+    if (world <= 1 || pfuncs.empty() || getenv("IEXA_NO_PFUNC_SHARDING")) return;
+    std::vector<std::pair<int64_t, int64_t>> reads;
+    for (auto &g : objs) theta_reads_of(g, reads);
+    for (auto &g : cons) theta_reads_of(g, reads);
+    for (size_t pi = pfuncs.size(); pi-- > 0;) {
+      Generator &g = pfuncs[pi];
+      int64_t lo = INT64_MAX, hi = 0;
+      for (auto &r : reads) {
+        const int64_t a = std::max(r.first, g.o0), b = std::min(r.second, g.o0 + g.K);
+        if (a < b) { lo = std::min(lo, a); hi = std::max(hi, b); }
+      }
+      if (lo == INT64_MAX) { g.k0 = g.k1 = 0; }
+      else { g.k0 = lo - g.o0; g.k1 = hi - g.o0; }
+      g.l0 = g.o0 + g.k0;
+      theta_reads_of(g, reads);
+    }
+  }
+  // the parts of theta resident on this rank (0-based [lo, hi), merged, sorted; a cover): what its generators read and what its
+  // share of every parameter function reads and writes
   std::vector<std::pair<int64_t, int64_t>> theta_read_ranges() const {
     std::vector<std::pair<int64_t, int64_t>> iv, m;
     if (npar <= 0) return m;
-    if (!pfuncs.empty() || world <= 1) { m.emplace_back(0, npar); return m; }
-    auto scan = [&](const Generator &g) {
-      if (g.k1 <= g.k0) return;
-      const Iterator &it = itrs[g.itr];
-      std::vector<uint8_t> used(g.c.uidx.size(), 0);
-      const Program *pr[] = {&g.c.val, &g.c.d1, &g.c.d2, &g.c.jv, &g.c.jtv, &g.c.hv};
-      for (const Program *q : pr) for (const Instr &I : q->code) if (I.op == D_LOADP && I.a >= 0 && (size_t)I.a < used.size()) used[I.a] = 1;
-      for (size_t s2 = 0; s2 < used.size(); ++s2) {
-        if (!used[s2]) continue;
-        int64_t lo, hi;
-        index_range(it, g.c.int_cols, g.c.uidx[s2], g.k0, g.k1, lo, hi);
-        lo = std::max<int64_t>(lo, 1); hi = std::min<int64_t>(hi, npar);
-        if (lo <= hi) iv.emplace_back(lo - 1, hi);
-      }
-    };
-    for (auto &g : objs) scan(g);
-    for (auto &g : cons) scan(g);
+    if (world <= 1) { m.emplace_back(0, npar); return m; }
+    for (auto &g : objs) theta_reads_of(g, iv);
+    for (auto &g : cons) theta_reads_of(g, iv);
+    for (auto &g : pfuncs) {
+      theta_reads_of(g, iv);
+      if (g.k1 > g.k0) iv.emplace_back(g.o0 + g.k0, g.o0 + g.k1);
+    }
     std::sort(iv.begin(), iv.end());
     for (auto &r : iv) {
       if (!m.empty() && r.first <= m.back().second) m.back().second = std::max(m.back().second, r.second);

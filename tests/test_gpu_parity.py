@@ -292,11 +292,15 @@ def test_a_rank_keeps_its_slices_of_columns_and_theta_on_the_device(device_side)
     for rank in (1, 3):
         m = ex.ExaModel(core, device=0, rank=rank, world=world)
         b = ex.device_bytes(m)
-        if device_side:   # parameter functions evaluated on the device fill whole theta blocks on every rank: theta and the columns they read stay whole
-            assert b["columns"] < b["columns_unsharded"] and b["theta"] == b["theta_unsharded"], b
-        else:
-            assert b["columns"] <= b["columns_unsharded"] / world + 4096, b
-            assert b["theta"] <= 0.75 * b["theta_unsharded"], b
+        # device_side: the parameter functions, too, are evaluated over the rank's share only
+        assert b["columns"] <= b["columns_unsharded"] / world + 4096, b
+        assert b["theta"] <= 0.75 * b["theta_unsharded"], b
+        if device_side:
+            T = core.npar // 3
+            k0, k1 = (T * rank) // world, (T * (rank + 1)) // world
+            th, ref = m.θ, full.θ
+            for blk in range(3):       # the rank's own share of every block is there, bit-identical to the whole-block evaluation
+                assert np.array_equal(th[blk * T + k0 + 2: blk * T + k1 - 2], ref[blk * T + k0 + 2: blk * T + k1 - 2]), (rank, blk)
         segs = {}
         for which in range(3):
             arr = (ex.lib.Segment * 4096)()
