@@ -185,3 +185,29 @@ def test_options_are_frozen_once_a_generator_exists(hostcheck_lib):
     assert L.iexa_set_option(h, 99, 0) != 0
     assert L.iexa_set_option(h, ex.lib.IEXA_OPT_SLOT_ORDER, 1) == 0 and L.iexa_set_option(h, ex.lib.IEXA_OPT_STRICT_IEEE, 1) == 0
     L.iexa_plan_destroy(h)
+
+
+@pytest.mark.parametrize("seed", range(0, 40, 3))
+def test_row_sorted_policy_on_random_models(seed, hostcheck_lib):
+    """fuzzed generators (arbitrary integer columns, product iterators, repeated variables): the plan compiler's structural
+    decision and the oracle's brute-force decision agree generator by generator — including 'no static order' — and the structure /
+    values agree under the policy; when every generator is sortable the COO pattern is CSR"""
+    import test_fuzz
+    from oracle.oracle import OracleModel
+    L = hostcheck_lib
+    core = test_fuzz.random_model(seed, K1=37, K2=3)[0]
+    om = OracleModel(core, slot_order=2)
+    m = ex.ExaModel(core, flags=ex.lib.IEXA_F_NO_DEVICE, library=L, slot_order=2)
+    is_csr = ex.jac_is_csr(m)
+    assert bool(om.L.orc_jac_is_csr(om.h)) == is_csr
+    ro, co = om.jac_structure()
+    r = np.zeros(max(len(ro), 1), dtype=np.int64); c = np.zeros_like(r)
+    assert L.hostcheck_structure(m.h, 0, r.ctypes.data, c.ctypes.data) == 0
+    assert (r[:len(ro)] == ro).all() and (c[:len(co)] == co).all()
+    x, _ = eval_point(core)
+    x = np.where(np.isfinite(x), x, 0.0)
+    assert_close(_hc(L, m, "hostcheck_eval_groups", 3, om.nnzj, x), om.jac_coord(x), "jac")
+    assert_close(_hc(L, m, "hostcheck_eval", 3, om.nnzj, x), om.jac_coord(x), "jac")
+    if is_csr and len(ro) > 1:
+        same = np.diff(ro) == 0
+        assert (np.diff(ro) >= 0).all() and (np.diff(co)[same] > 0).all()
