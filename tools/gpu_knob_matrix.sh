@@ -24,4 +24,5 @@ run IEXA_NO_SCATTER_DIRECT=1
 run IEXA_MINBLOCKS_PROD=8,8,8 IEXA_HOIST_PROD=0,0,0
 run IEXA_ORDER=g
 run IEXA_CACHE_DIR=off
-run IEXA_NO_VMM=1 IEXA_NO_COLUMN_SLICES=1
+run IEXA_NO_VMM=1
+run IEXA_NO_COLUMN_SLICES=1 IEXA_NO_PFUNC_SHARDING=1
