@@ -150,8 +150,9 @@ constexpr int kMaxStagedStep = 64; // members with more slots than this store di
 // measured on B200 (config 3): capping registers at 64 (8 blocks of 128 threads per SM) lifts hess from 64% to 82% of the
 // HBM roofline and cons/jac by 3 points; the occasional spill stays in L1
 // products (round 2, config 3): hprod! with its rider body needs registers — 8 blocks/SM (64 registers, 400 B of spills) 0.291 ms,
-// 6 blocks (80 registers) 0.215 ms; jtprod! 0.310 -> 0.300 ms at 6; jprod 0.139 at 8 (0.144 at 10)
-static const int kDefaultMinBlocks[KS__N] = {8, 8, 8, 8, 8, 8, 6, 6, 6, 6, 6};
+// 6 blocks (80 registers, 336 B of stack) 0.215 ms, 4 blocks (128 registers, 88 B) 0.193 ms, 3 blocks (158 registers: its natural need,
+// no spills) 0.236 ms — bandwidth needs the warps more than the last registers; jtprod! 0.310 -> 0.300 ms at 6; jprod 0.139 at 8 (0.144 at 10)
+static const int kDefaultMinBlocks[KS__N] = {8, 8, 8, 8, 8, 8, 6, 6, 4, 6, 6};
 int spec_block() {
   // threads per block of the specialised kernels (a multiple of 32).  Measured on B200, config 3:
   // 128 -> 0.585 ms/eval, 64 -> 0.597, 32 -> 0.627; on a 1/8 shard 64 and 128 tie (0.092 ms).
