@@ -938,11 +938,26 @@ struct Plan {
       const IndexExpr &ea = ctx.uidx[jac_slot[perm[p]]], &eb = ctx.uidx[jac_slot[perm[p + 1]]];
       if (key0[perm[p]] >= key0[perm[p + 1]]) return false;      // duplicate column at k = 0
       if (ea.terms == eb.terms) continue;                         // constant difference: static
-      for (int64_t k = 1; k < it.K; ++k)                          // neighbours in the sorted order stay strictly ordered
-        if (idx_at(ea, k) >= idx_at(eb, k)) return false;
+      // The answer depends on the iterator, on the two term lists (in the iterator's own column numbering) and on the
+      // difference of the bases only: the nine state rows of a collocation scheme ask the same question nine times
+      std::string key;
+      auto put = [&](int64_t v) { key.append(reinterpret_cast<const char *>(&v), sizeof v); };
+      put((int64_t)(&it - itrs.data())); put(eb.base - ea.base);
+      for (const IndexExpr *e : {&ea, &eb}) { put((int64_t)e->terms.size()); for (auto &t : e->terms) { put(ctx.int_cols[t.first]); put(t.second); } }
+      auto hit = row_sort_memo_.find(key);
+      bool ok;
+      if (hit != row_sort_memo_.end()) ok = hit->second;
+      else {
+        ok = true;
+        for (int64_t k = 1; k < it.K && ok; ++k)                  // neighbours in the sorted order stay strictly ordered
+          ok = idx_at(ea, k) < idx_at(eb, k);
+        row_sort_memo_[key] = ok;
+      }
+      if (!ok) return false;
     }
     return true;
   }
+  mutable std::map<std::string, bool> row_sort_memo_;
   // every constraint generator's rows are column-sorted (policy IEXA_SLOT_ORDER_JAC_ROW_SORTED and a static order exists)
   bool jac_is_csr() const {
     for (const Generator &g : cons) if (g.c.o1step > 1 && !g.c.jac_row_sorted) return false;
