@@ -65,3 +65,34 @@ def test_state_errors():
     assert L.iexa_finalize(h, 0, 3, 2, ex.lib.IEXA_F_NO_DEVICE) == 1      # rank >= world
     assert L.iexa_plan_destroy(h) == 0
     assert L.iexa_get_meta(None, C.byref(m)) == 1
+
+
+def test_round2_queries_state_and_argument_errors():
+    """iexa_jac_is_csr / iexa_jac_csr_rowptr / iexa_device_bytes: argument and state errors are codes + messages, never a crash;
+    the structure query works on a host-only plan, the device-memory query needs an engine"""
+    from iexa_b200 import models
+    L = ex.lib.load()
+    h = C.c_void_p()
+    assert L.iexa_plan_create(C.byref(h), 1) == 0
+    flag = C.c_int32(7)
+    assert L.iexa_jac_is_csr(h, C.byref(flag)) == 2 and b"not finalized" in L.iexa_last_error()
+    assert L.iexa_jac_is_csr(h, None) == 1
+    assert L.iexa_jac_is_csr(None, C.byref(flag)) == 1
+    rp = np.zeros(4, dtype=np.int64)
+    assert L.iexa_jac_csr_rowptr(h, rp.ctypes.data, 8, 0, None) == 2          # not finalized
+    out6 = (C.c_int64 * 6)()
+    assert L.iexa_device_bytes(h, out6) == 2
+    assert L.iexa_device_bytes(h, None) == 1
+    assert L.iexa_plan_destroy(h) == 0
+    # a finalized host-only plan under the default policy: not CSR -> STATE with a message that names the policy
+    m = ex.ExaModel(models.farmer(4), flags=ex.lib.IEXA_F_NO_DEVICE)
+    assert not ex.jac_is_csr(m)
+    rp = np.zeros(m.meta.ncon + 1, dtype=np.int64)
+    assert L.iexa_jac_csr_rowptr(m.h, rp.ctypes.data, 8, 0, None) == 2 and b"IEXA_SLOT_ORDER_JAC_ROW_SORTED" in L.iexa_last_error()
+    assert L.iexa_device_bytes(m.h, out6) == 2 and b"no device engine" in L.iexa_last_error()
+    # under the row-sorted policy: host buffers are served from the plan; a bad index width falls through to the engine path
+    m2 = ex.ExaModel(models.farmer(4), flags=ex.lib.IEXA_F_NO_DEVICE, slot_order=2)
+    assert ex.jac_is_csr(m2)
+    assert L.iexa_jac_csr_rowptr(m2.h, rp.ctypes.data, 8, 0, None) == 0 and rp[0] == 0 and rp[-1] == m2.meta.nnzj
+    assert L.iexa_jac_csr_rowptr(m2.h, rp.ctypes.data, 3, 0, None) != 0
+    assert L.iexa_jac_csr_rowptr(m2.h, None, 8, 0, None) != 0
