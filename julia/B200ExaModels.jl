@@ -257,7 +257,7 @@ function add_par_function(h::Ptr{Cvoid}, nodes::Vector{IexaNode}, idx::Vector{Ie
     return off[]
 end
 
-"plan options (before the first generator): key 1 = slot-order policy (0 left to right, 1 right to left), key 2 = strict IEEE"
+"plan options (before the first generator): key 1 = slot-order policy (0 left to right, 1 right to left, 2 left to right with the first-order slots of every constraint row in column order: `jac_is_csr`), key 2 = strict IEEE"
 set_option!(h::Ptr{Cvoid}, key::Integer, value::Integer) =
     check(ccall((:iexa_set_option, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), h, key, value))
 
